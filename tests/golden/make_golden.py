@@ -1,0 +1,244 @@
+"""Generate the committed golden vectors by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+Writes tests/golden/*.npz.  Every expected value below is produced by reference
+code imported from /root/reference (GradLoss, tools.py, edge.py,
+eval_depth_edges.py) or by the exact third-party call the reference makes
+(cv2.Canny / cv2.Sobel); inputs are seeded synthetic tensors.
+The reference's matcher/thinner (py-bsds500) is not available, so the
+eval_depth_edges goldens use the oracle stand-in for `bsds_metric.bsds`; they pin
+the arithmetic around the matcher (binarise, crop, threshold grid, sums, P/R),
+not the matcher itself.
+"""
+import os
+import sys
+import tempfile
+import warnings
+
+import cv2
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+warnings.filterwarnings("ignore")
+
+from _reference_loader import load_edge, load_eval_depth_edges, load_gradloss, load_tools  # noqa: E402
+
+
+def synth_scene(H, W, seed, n_rect=24, noise=0.3):
+    r = np.random.default_rng(seed)
+    d = np.full((H, W), 40.0, np.float32)
+    for _ in range(n_rect):
+        y0, x0 = r.integers(0, H), r.integers(0, W)
+        h, w = r.integers(1, max(2, H // 2)), r.integers(1, max(2, W // 2))
+        d[y0:y0 + h, x0:x0 + w] = r.uniform(1, 80)
+    d += r.normal(0, noise, (H, W)).astype(np.float32)
+    return d
+
+
+def loss_inputs(B, H, W, seed, h=None, w=None):
+    g = torch.Generator().manual_seed(seed)
+    h, w = h or H, w or W
+    depth = torch.stack([torch.from_numpy(synth_scene(h, w, seed * 10 + b, noise=0.05)) for b in range(B)])[:, None]
+    depth = depth * 0.2 + torch.rand(B, 1, h, w, generator=g) * 2.0
+    u = torch.rand(B, 1, H, W, generator=g)
+    edge = (u < 0.05).float() * torch.clamp(torch.rand(B, 1, H, W, generator=g), min=0.3)
+    k = torch.randint(0, 256, (B, 1, H, W), generator=g).float()
+    normal = (360 * k / 255 - 180) * np.pi / 180
+    return depth.float(), edge, normal.float()
+
+
+def gen_edge_loss():
+    GradLoss = load_gradloss()
+    cases = {}
+
+    def run(name, depth, edge, mask, normal, is_grad=True, is_sigmoid=True, thresh=4, weight=10.0, p2n=1.0):
+        head = GradLoss("cross_entropy", True, [], weight, p2n)
+        x = depth.clone().requires_grad_(True)
+        loss, gmap = head(x, edge, mask, is_grad, is_sigmoid, thresh, normal)
+        loss.backward()
+        cases[name] = dict(
+            depth=depth.numpy(), edge=edge.numpy(),
+            mask=np.zeros(0, np.float32) if mask is None else mask.numpy(),
+            normal=np.zeros(0, np.float32) if normal is None else normal.numpy(),
+            attrs=np.array([is_grad, is_sigmoid, thresh, weight, p2n], np.float64),
+            loss=np.float32(loss.item()), grad_map=gmap.numpy(), dgrad=x.grad.numpy())
+
+    g = torch.Generator().manual_seed(123)
+    d, e, n = loss_inputs(2, 48, 64, 1)
+    run("normals_nomask", d, e, None, n)
+    run("normals_binmask", d, e, (torch.rand(2, 1, 48, 64, generator=g) < 0.5).float(), n)
+    run("normals_softmask", d, e, torch.rand(2, 1, 48, 64, generator=g), n)
+    run("normals_onesmask", d, e, torch.ones(2, 1, 48, 64), n)
+    run("normals_zerosmask", d, e, torch.zeros(2, 1, 48, 64), n)
+    run("magnitude_nomask", d, e, None, None)
+    run("p2n_weight", d, e, None, n, weight=3.0, p2n=2.5, thresh=2)
+    # continuous normals with the band limits injected exactly (fp32-rounded k*pi/8)
+    nc = (torch.rand(2, 1, 48, 64, generator=g) * 2 - 1) * np.pi
+    lim = torch.tensor([np.float32(s * k * np.pi / 8) for k in range(1, 9, 2) for s in (-1, 1)])
+    nc.view(-1)[: 8 * 40] = lim.repeat(40)
+    nc.view(-1)[400:408] = torch.nextafter(lim, torch.tensor(10.0))
+    nc.view(-1)[408:416] = torch.nextafter(lim, torch.tensor(-10.0))
+    nc.view(-1)[416] = float("nan")
+    run("normals_continuous", d, e, None, nc)
+    # odd sizes (scalar path), single image
+    d2, e2, n2 = loss_inputs(1, 37, 53, 2)
+    run("odd_shape", d2, e2, None, n2)
+    d3, e3, n3 = loss_inputs(3, 24, 40, 3)
+    run("three_images_binmask", d3, e3, (torch.rand(3, 1, 24, 40, generator=g) < 0.7).float(), n3)
+    # resize paths: prediction at half / 1.5x resolution of the targets
+    d4, e4, n4 = loss_inputs(2, 48, 64, 4, h=24, w=32)
+    run("resize_up", d4, e4, None, n4)
+    d5, e5, n5 = loss_inputs(2, 32, 48, 5, h=48, w=72)
+    run("resize_down", d5, e5, None, n5)
+    # DEE-training mode: input already a probability (EdgeEstimationLIDARModel.py:139-144)
+    prob = torch.rand(2, 1, 48, 64, generator=g) * 0.98 + 0.01
+    run("dee_mode", prob, e, None, None, is_grad=False, is_sigmoid=False)
+    flat = {}
+    for k, c in cases.items():
+        for f, v in c.items():
+            flat[f"{k}/{f}"] = v
+    np.savez_compressed(os.path.join(HERE, "edge_loss.npz"), **flat)
+    print("edge_loss:", list(cases))
+
+
+def gen_canny():
+    ref_edge = load_edge()
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for i, (H, W) in enumerate([(96, 160), (64, 200), (37, 53), (5, 7), (1, 9), (128, 128)]):
+            d = synth_scene(H, W, 100 + i)
+            if i == 5:
+                d = np.random.default_rng(7).uniform(-5, 95, (H, W)).astype(np.float32)
+            path = os.path.join(tmp, f"d{i}.npy")
+            np.save(path, d)
+            out[f"depth{i}"] = d
+            for t in (20, 60, 120, 240):
+                e = ref_edge.edge_from_depth(path, None, os.path.join(tmp, "e.jpeg"),
+                                             thresh_1=int(t / 2), thresh_2=int(t), is_write_edge=False)
+                out[f"edges{i}_t{t}"] = np.packbits(e > 0)
+        # resize branch (cv2.resize INTER_LINEAR to the GT size) -- host-side in the drop-in
+        d = synth_scene(48, 80, 200)
+        path = os.path.join(tmp, "dr.npy")
+        np.save(path, d)
+        out["depth_resize"] = d
+        e = ref_edge.edge_from_depth(path, (160, 96), os.path.join(tmp, "e.jpeg"), thresh_1=20, thresh_2=40,
+                                     is_write_edge=False)
+        out["edges_resize"] = np.packbits(e > 0)
+    np.savez_compressed(os.path.join(HERE, "canny.npz"), **out)
+    print("canny:", len(out))
+
+
+def synth_prob(H, W, seed):
+    r = np.random.default_rng(seed)
+    p = 1 / (1 + np.exp(-r.normal(-3, 2, (H, W))))
+    p = cv2.blur(p, (7, 7))
+    for _ in range(5):
+        p[r.integers(0, H), :] += 0.6
+        p[:, r.integers(0, W)] += 0.5
+    return np.clip(p, 0, 1).astype(np.float32)
+
+
+def gen_dee():
+    tools = load_tools()
+    out = {}
+    for i, (H, W) in enumerate([(40, 56), (64, 96), (7, 9), (3, 3), (33, 70)]):
+        p = synth_prob(H, W, 300 + i)
+        if i == 1:
+            p *= np.random.default_rng(5).choice([1e-12, 1e-3, 1, 1], size=p.shape).astype(np.float32)
+        out[f"prob{i}"] = p
+        # infer_edge_estimation.py:244-250 (the normals block, verbatim calls)
+        sx = cv2.Sobel(p, cv2.CV_64F, 1, 0, ksize=5)
+        sy = cv2.Sobel(p, cv2.CV_64F, 0, 1, ksize=5)
+        ang = np.arctan2(-sy, sx)
+        out[f"normals{i}"] = (((ang * (180 / np.pi) + 180) / 360) * 255).astype("uint8")
+        nms = tools.non_max_suppression(p)
+        out[f"nms{i}"] = nms
+        out[f"hyst{i}"] = tools.hysteresis(nms)
+        out[f"hyst_raw{i}"] = tools.hysteresis(p)
+        out[f"hyst_custom{i}"] = tools.hysteresis(nms, 0.2, 0.5)
+    np.savez_compressed(os.path.join(HERE, "dee.npz"), **out)
+    print("dee:", len(out))
+
+
+def synth_gt_and_depth(H, W, seed):
+    """GT = region boundaries of a piecewise-constant scene; predicted depth =
+    that scene, slightly shifted and noisy (so pred edges sit near GT edges)."""
+    r = np.random.default_rng(seed)
+    d = np.full((H, W), 40.0, np.float32)
+    for _ in range(14):
+        y0, x0 = r.integers(0, H), r.integers(0, W)
+        h, w = r.integers(8, H // 2), r.integers(8, W // 2)
+        d[y0:y0 + h, x0:x0 + w] = r.uniform(3, 80)
+    gt = np.zeros((H, W), bool)
+    gt[:, 1:] |= d[:, 1:] != d[:, :-1]
+    gt[1:, :] |= d[1:, :] != d[:-1, :]
+    pred = np.roll(d, (int(r.integers(-2, 3)), int(r.integers(-2, 3))), (0, 1))
+    pred = pred + r.normal(0, 0.4, (H, W)).astype(np.float32)
+    # 1/256 m fixed point (the KITTI u16 depth format) so the fixture stores as uint16
+    pred = np.round(np.clip(pred, 0, 200) * 256).astype(np.uint16)
+    return gt, (pred / 256).astype(np.float32)
+
+
+def gen_pr():
+    from oracle import pr_counts as opr, thin as othin
+    import types
+    cp = types.ModuleType("correspond_pixels")
+    cp.correspond_pixels = opr.correspond_pixels
+    th = types.ModuleType("thin")
+    th.binary_thin = othin.binary_thin
+    ede = load_eval_depth_edges(th, cp)
+    out = {}
+    # (a) evaluate_boundaries on a soft map, 9 thresholds, thinning off/on
+    gt, depth = synth_gt_and_depth(80, 120, 400)
+    r = np.random.default_rng(1)
+    soft = cv2.GaussianBlur(np.roll(gt, (1, -1), (0, 1)).astype(np.float64), (5, 5), 1.0)
+    soft = np.clip(soft / soft.max() + r.uniform(0, 0.15, soft.shape), 0, 1)
+    out["soft"] = soft
+    out["soft_gt"] = gt
+    for thin_flag in (False, True):
+        c_r, s_r, c_p, s_p, thr = ede.evaluate_boundaries(soft, [gt.astype(np.float64)], thresholds=9,
+                                                          max_dist=0.0075, apply_thinning=thin_flag)
+        out[f"soft_counts_thin{int(thin_flag)}"] = np.stack([c_r, s_r, c_p, s_p], 1).astype(np.int64)
+        out["soft_thr"] = thr
+    # (b) pr_evaluation end to end (files, JPEG round trip, pool) on 3 small scenes
+    with tempfile.TemporaryDirectory() as tmp:
+        H, W = 200, 520
+        crop = [10, 510, 20, 190]  # diagonal 528 px -> match radius 1.06 px
+        gts, preds = [], []
+        for i in range(3):
+            g, d = synth_gt_and_depth(H, W, 500 + i)
+            gp = os.path.join(tmp, f"gt{i}.png")
+            cv2.imwrite(gp, g.astype(np.uint8) * 255)
+            dp = os.path.join(tmp, f"pred{i}.npy")
+            np.save(dp, d)
+            gts.append(gp)
+            preds.append(dp)
+            out[f"pr_gt{i}"] = np.packbits(g)
+            out["pr_shape"] = np.array([H, W])
+            out[f"pr_depth_u16_{i}"] = np.round(d * 256).astype(np.uint16)
+        rng = [40, 100, 160, 240]
+        pv, rv = ede.pr_evaluation(gts, preds, edge_thresh_range=rng, gt_crop=crop,
+                                   save_folder=os.path.join(tmp, "out"), num_workers=2)
+        out["pr_range"] = np.array(rng)
+        out["pr_crop"] = np.array(crop)
+        out["pr_precision"] = np.array(pv, np.float64)
+        out["pr_recall"] = np.array(rv, np.float64)
+        pr = np.vstack((pv, rv)).transpose()
+        out["pr_auc_full"] = np.float64(ede.mean_recall_at_precision_range(pr))
+        out["pr_auc_part"] = np.float64(ede.mean_recall_at_precision_range(pr, 0.12, 0.65))
+    np.savez_compressed(os.path.join(HERE, "pr.npz"), **out)
+    print("pr:", {k: v for k, v in out.items() if k.startswith("pr_") and np.size(v) < 8})
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    gen_edge_loss()
+    gen_canny()
+    gen_dee()
+    gen_pr()
