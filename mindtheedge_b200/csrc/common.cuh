@@ -1,0 +1,54 @@
+// Shared device/host helpers for libmte (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mte.h"
+
+#define MTE_FULL_MASK 0xffffffffu
+
+#define MTE_RETURN_IF_CUDA_ERROR()                        \
+    do {                                                  \
+        cudaError_t e__ = cudaGetLastError();             \
+        if (e__ != cudaSuccess) return (int)e__;          \
+    } while (0)
+
+namespace mte {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// First 256 bytes of every workspace: self-resetting tickets / flags.
+struct WsHeader {
+    unsigned int ticket[16];
+    unsigned int flag[16];
+    unsigned int pad[32];
+};
+static_assert(sizeof(WsHeader) == MTE_WS_HEADER_BYTES, "workspace header size");
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(MTE_FULL_MASK, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(MTE_FULL_MASK, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned warp_or(unsigned v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(MTE_FULL_MASK, v, o);
+    return v;
+}
+
+// 128-bit streaming loads/stores (read-once planes: evict-first, no L1 allocation)
+__device__ __forceinline__ float4 ld_stream4(const float *p) { return __ldcs(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float4 ld_cached4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ void st_stream4(float *p, float4 v) { __stcs(reinterpret_cast<float4 *>(p), v); }
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace mte

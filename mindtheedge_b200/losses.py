@@ -1,0 +1,205 @@
+"""Edge-loss head: drop-in for the reference ``GradLoss``.
+
+Mirrors the plugin interface of
+``packnet_code/packnet_sfm/losses/grad_loss.py:97-159`` (constructor arguments of
+``setup_depth_edge_loss``, ``models/model_wrapper.py:589-596``; call signature of
+``SemiSupEdgeModel.edge_loss``, ``models/SemiSupEdgeModel.py:94-96``), so
+``model.add_edge_loss(GradLoss(...))`` (``models/SfmModel.py:54-56``) works
+unchanged.  The arithmetic runs in libmte.so (``mte_edge_loss_fwd`` /
+``mte_edge_loss_bwd``) as PyTorch custom ops ``mte::edge_loss_fwd`` /
+``mte::edge_loss_bwd`` with a hand-written backward.  No CPU path exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib, runtime
+
+__all__ = ["GradLoss", "edge_loss", "multiscale_edge_loss"]
+
+
+def _prep(t: torch.Tensor, name: str) -> torch.Tensor:
+    runtime.require_cuda(t, name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _scales_struct(pred, edge, normal, mask, grad_map, grad_pred, weights):
+    n = len(pred)
+    arr = (_lib.LossScale * n)()
+    for i in range(n):
+        B, c, h, w = pred[i].shape
+        Be, ce, H, W = edge[i].shape
+        if c != 1 or ce != 1:
+            raise _lib.MteError("edge loss expects single-channel [B,1,H,W] planes")
+        if Be != B:
+            raise _lib.MteError("batch size of prediction and edge target differ")
+        s = arr[i]
+        s.pred = pred[i].data_ptr()
+        s.edge = edge[i].data_ptr()
+        s.normal = normal[i].data_ptr() if normal else None
+        s.mask = mask[i].data_ptr() if mask else None
+        s.grad_map = grad_map[i].data_ptr() if grad_map else None
+        s.grad_pred = grad_pred[i].data_ptr() if grad_pred else None
+        s.B, s.h, s.w, s.H, s.W = B, h, w, H, W
+        s.scale_weight = float(weights[i])
+        for other, nm in ((normal, "normal"), (mask, "mask")):
+            if other and tuple(other[i].shape) != (B, 1, H, W):
+                raise _lib.MteError(f"{nm} must have the shape of the edge target")
+    return arr
+
+
+def _attrs(is_grad, is_sigmoid, pred_is_inverse, sigmoid_thresh, weight, pos_to_neg):
+    return _lib.LossAttrs(int(is_grad), int(is_sigmoid), int(pred_is_inverse), float(sigmoid_thresh),
+                          float(weight), float(pos_to_neg))
+
+
+# ---------------------------------------------------------------------------
+# PyTorch custom ops (schemas) backed by the C ABI
+# ---------------------------------------------------------------------------
+_LIBDEF = torch.library.Library("mte", "DEF")
+_LIBDEF.define(
+    "edge_loss_fwd(Tensor[] pred, Tensor[] edge, Tensor[] normal, Tensor[] mask, float[] scale_weights, "
+    "bool is_grad, bool is_sigmoid, bool pred_is_inverse, float sigmoid_thresh, float weight, float pos_to_neg) "
+    "-> (Tensor, Tensor, Tensor[])")
+_LIBDEF.define(
+    "edge_loss_bwd(Tensor grad_losses, Tensor ctx, Tensor[] pred, Tensor[] edge, Tensor[] normal, Tensor[] mask, "
+    "float[] scale_weights, bool is_grad, bool is_sigmoid, bool pred_is_inverse, float sigmoid_thresh, "
+    "float weight, float pos_to_neg) -> Tensor[]")
+
+
+def _edge_loss_fwd_cuda(pred, edge, normal, mask, scale_weights, is_grad, is_sigmoid, pred_is_inverse,
+                        sigmoid_thresh, weight, pos_to_neg):
+    dev = pred[0].device
+    n = len(pred)
+    grad_maps = [torch.empty_like(e) for e in edge]
+    sc = _scales_struct(pred, edge, normal, mask, grad_maps, None, scale_weights)
+    at = _attrs(is_grad, is_sigmoid, pred_is_inverse, sigmoid_thresh, weight, pos_to_neg)
+    losses = torch.empty(1 + n, dtype=torch.float32, device=dev)
+    ctx = torch.empty(_lib.lib.mte_edge_loss_ctx_bytes(sc, n) // 4, dtype=torch.float32, device=dev)
+    nbytes = _lib.lib.mte_edge_loss_workspace_bytes(sc, n)
+    ws = runtime.workspace(dev, nbytes)
+    _lib.check(_lib.lib.mte_edge_loss_fwd(sc, n, C.byref(at), losses.data_ptr(), ctx.data_ptr(), ws.data_ptr(),
+                                          ws.numel(), runtime.current_stream_ptr(dev)), "mte_edge_loss_fwd")
+    return losses, ctx, grad_maps
+
+
+def _edge_loss_bwd_cuda(grad_losses, ctx, pred, edge, normal, mask, scale_weights, is_grad, is_sigmoid,
+                        pred_is_inverse, sigmoid_thresh, weight, pos_to_neg):
+    dev = pred[0].device
+    n = len(pred)
+    grads = [torch.empty_like(p) for p in pred]
+    sc = _scales_struct(pred, edge, normal, mask, None, grads, scale_weights)
+    at = _attrs(is_grad, is_sigmoid, pred_is_inverse, sigmoid_thresh, weight, pos_to_neg)
+    nbytes = _lib.lib.mte_edge_loss_workspace_bytes(sc, n)
+    ws = runtime.workspace(dev, nbytes)
+    _lib.check(_lib.lib.mte_edge_loss_bwd(sc, n, C.byref(at), grad_losses.data_ptr(), ctx.data_ptr(),
+                                          ws.data_ptr(), ws.numel(), runtime.current_stream_ptr(dev)),
+               "mte_edge_loss_bwd")
+    return grads
+
+
+_LIBIMPL = torch.library.Library("mte", "IMPL", "CUDA")
+_LIBIMPL.impl("edge_loss_fwd", _edge_loss_fwd_cuda)
+_LIBIMPL.impl("edge_loss_bwd", _edge_loss_bwd_cuda)
+
+
+class _EdgeLossFn(torch.autograd.Function):
+    """forward(*pred) -> losses[1+n]; backward is the hand-written kernel."""
+
+    @staticmethod
+    def forward(ctx, cfg, *pred):
+        edge, normal, mask, weights, flags = cfg
+        losses, saved, grad_maps = torch.ops.mte.edge_loss_fwd(list(pred), edge, normal, mask, weights, *flags)
+        ctx.cfg = cfg
+        ctx.save_for_backward(saved, *pred)
+        ctx.mark_non_differentiable(*grad_maps)
+        return (losses, *grad_maps)
+
+    @staticmethod
+    def backward(ctx, grad_losses, *_unused):
+        edge, normal, mask, weights, flags = ctx.cfg
+        saved, *pred = ctx.saved_tensors
+        g = grad_losses.contiguous().float()
+        grads = torch.ops.mte.edge_loss_bwd(g, saved, list(pred), edge, normal, mask, weights, *flags)
+        return (None, *grads)
+
+
+def multiscale_edge_loss(
+    preds: Sequence[torch.Tensor],
+    gt_edges: Sequence[torch.Tensor],
+    gt_masks: Optional[Sequence[torch.Tensor]] = None,
+    gt_normals: Optional[Sequence[torch.Tensor]] = None,
+    *,
+    scale_weights: Optional[Sequence[float]] = None,
+    is_grad: bool = True,
+    is_sigmoid: bool = True,
+    sigmoid_thresh: float = 4,
+    weight: float = 1.0,
+    pos_to_neg: float = 1.0,
+    pred_is_inverse: bool = False,
+):
+    """All pyramid scales in one launch per direction.
+
+    Equivalent to the loop of ``compute_edge_loss_with_all_scales``
+    (``models/SemiSupEdgeModel.py:164-198``): returns
+    ``(sum_s scale_weights[s] * loss_s, per_scale_losses[n], grad_maps[n])``.
+    With ``pred_is_inverse`` the ``inv2depth`` step (``utils/depth.py:104-121``)
+    is fused into the kernels.
+    """
+    n = len(preds)
+    if not 1 <= n <= _lib.MTE_MAX_SCALES:
+        raise _lib.MteError(f"1..{_lib.MTE_MAX_SCALES} scales supported, got {n}")
+    if scale_weights is None:
+        scale_weights = [1.0 / n] * n
+    pred = [_prep(p, "prediction") for p in preds]
+    edge = [_prep(e, "gt_edge") for e in gt_edges]
+    normal = [_prep(t, "gt_normals") for t in gt_normals] if gt_normals is not None else []
+    mask = [_prep(t, "gt_mask") for t in gt_masks] if gt_masks is not None else []
+    flags = (bool(is_grad), bool(is_sigmoid), bool(pred_is_inverse), float(sigmoid_thresh), float(weight),
+             float(pos_to_neg))
+    cfg = (edge, normal, mask, [float(w) for w in scale_weights], flags)
+    losses, *grad_maps = _EdgeLossFn.apply(cfg, *pred)
+    return losses[0], losses[1:], list(grad_maps)
+
+
+def edge_loss(output, gt_edge, gt_mask=None, is_grad=True, is_sigmoid=True, sigmoid_thresh=4, gt_normals=None, *,
+              weight=1.0, pos_to_neg=1.0):
+    """Single-scale functional form -> (loss, grad_map)."""
+    total, _, maps = multiscale_edge_loss(
+        [output], [gt_edge], None if gt_mask is None else [gt_mask], None if gt_normals is None else [gt_normals],
+        scale_weights=[1.0], is_grad=is_grad, is_sigmoid=is_sigmoid, sigmoid_thresh=sigmoid_thresh, weight=weight,
+        pos_to_neg=pos_to_neg)
+    return total, maps[0]
+
+
+class GradLoss(nn.Module):
+    """Same constructor and call signature as the reference ``GradLoss``
+    (``losses/grad_loss.py:97-122``).  ``edge_loss_type`` must contain
+    ``cross_entropy`` (the shipped configuration,
+    ``configs/train_packnet_san_kitti_with_edges.yaml:59-68``)."""
+
+    def __init__(self, edge_loss_type, use_external_edges_for_loss=True, edge_loss_class_list_to_mask_out=[],
+                 depth_edges_loss_weight=1.0, depth_edges_loss_pos_to_neg_weight=1.0):
+        super().__init__()
+        if "cross_entropy" not in edge_loss_type or "dice" in edge_loss_type or \
+                "attention_loss" in edge_loss_type or "spatially_adaptive" in edge_loss_type:
+            raise NotImplementedError(
+                f"edge_loss_type={edge_loss_type!r}: only 'cross_entropy' runs on the sm_100a path "
+                "(the attention/dice variants are listed under SURVEY.md 8(f))")
+        self.weight = depth_edges_loss_weight
+        self.depth_edges_loss_pos_to_neg_weight = depth_edges_loss_pos_to_neg_weight
+        self.edge_loss_type = edge_loss_type
+        self.use_external_edges_for_loss = use_external_edges_for_loss
+        self.edge_loss_class_list_to_mask_out = edge_loss_class_list_to_mask_out
+        self.device = "cuda"
+
+    def forward(self, output, gt_edge, gt_mask=None, is_grad=True, is_sigmoid=True, sigmoid_thresh=4,
+                gt_normals=None):
+        return edge_loss(output, gt_edge, gt_mask, is_grad, is_sigmoid, sigmoid_thresh, gt_normals,
+                         weight=self.weight, pos_to_neg=self.depth_edges_loss_pos_to_neg_weight)
