@@ -149,7 +149,11 @@ __device__ __forceinline__ void responses(const Row<VEC> &up, const Row<VEC> &mi
     crl = R - P;
 }
 
+// Forward: the loss is a 2M-term average, MUFU-accuracy sigmoid is far inside 1e-5.
 __device__ __forceinline__ float sigmoidf_fast(float z) { return __frcp_rn(1.0f + __expf(-z)); }
+// Backward: p*(1-p)/(1-p+eps) amplifies the last bits of p where the sigmoid saturates, so p is computed
+// the way eager PyTorch does (accurate expf, IEEE divide) to reproduce the reference gradient, not just the math.
+__device__ __forceinline__ float sigmoidf_ref(float z) { return 1.0f / (1.0f + expf(-z)); }
 
 // ---------------------------------------------------------------------------
 // Forward
@@ -382,7 +386,7 @@ struct BwdImg {
 
 template <int MODE, bool MASK>
 __device__ __forceinline__ float dloss_dg(float g, float ee, float mm, const BwdImg &I, bool isSigmoid, float T) {
-    const float p = isSigmoid ? sigmoidf_fast(g - T) : g;
+    const float p = isSigmoid ? sigmoidf_ref(g - T) : g;
     float d = I.cp * ee * __frcp_rn(p + kEps) + I.cn * (1.0f - ee) * __frcp_rn((1.0f - p) + kEps);
     if (MASK) {
         if (I.maskBinary && mm == 0.f) d = 0.f;

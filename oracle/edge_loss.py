@@ -58,8 +58,22 @@ def direction_index(theta: np.ndarray) -> np.ndarray:
     return d
 
 
-def _stencil_bank(dtype=torch.float32) -> torch.Tensor:
-    return torch.tensor(STENCILS, dtype=dtype).unsqueeze(1)  # [4,1,3,3]
+def _stencil_bank(dtype=torch.float32, device="cpu") -> torch.Tensor:
+    return torch.tensor(STENCILS, dtype=dtype, device=device).unsqueeze(1)  # [4,1,3,3]
+
+
+def direction_index_torch(theta: torch.Tensor) -> torch.Tensor:
+    """Same quantisation as ``direction_index`` with torch ops on theta's device."""
+    t = theta.float()
+    b = [float(np.float32(k * np.pi / 8)) for k in range(9)]
+    d = torch.full_like(t, DIR_H, dtype=torch.long)
+    band_v = ((t >= -b[5]) & (t < -b[3])) | ((t >= b[3]) & (t < b[5]))
+    band_rl = ((t >= -b[7]) & (t < -b[5])) | ((t >= b[1]) & (t < b[3]))
+    band_lr = ((t >= -b[3]) & (t < -b[1])) | ((t >= b[5]) & (t < b[7]))
+    d[band_v] = DIR_V
+    d[band_rl] = DIR_RL
+    d[band_lr] = DIR_LR
+    return d
 
 
 def edge_loss_torch(
@@ -74,7 +88,7 @@ def edge_loss_torch(
     weight: float = 1.0,
     pos_to_neg: float = 1.0,
 ):
-    """``GradLoss('cross_entropy').forward`` on CPU tensors -> (loss, grad_map).
+    """``GradLoss('cross_entropy').forward`` on CPU (or any device) tensors -> (loss, grad_map).
 
     ``output`` may require grad; ``loss.backward()`` then gives the reference
     gradient through plain autograd.
@@ -82,11 +96,11 @@ def edge_loss_torch(
     H, W = gt_edge.shape[-2:]
     x = F.interpolate(output, size=(H, W), mode="bilinear")  # grad_loss.py:127
     if is_grad:
-        resp = F.conv2d(x, _stencil_bank(x.dtype), padding=1)  # [B,4,H,W]
+        resp = F.conv2d(x, _stencil_bank(x.dtype, x.device), padding=1)  # [B,4,H,W]
         if gt_normals is None:
             g = torch.sqrt(resp[:, 0:1] ** 2 + resp[:, 1:2] ** 2 + 1e-6)  # :73
         else:
-            d = torch.from_numpy(direction_index(gt_normals.detach().numpy())).long()
+            d = direction_index_torch(gt_normals.detach())
             g = torch.gather(resp, 1, d).abs()
     else:
         g = x
