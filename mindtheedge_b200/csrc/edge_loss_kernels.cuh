@@ -1,0 +1,569 @@
+// Edge-loss kernels (templates).  See edge_loss.cu for the host API and the reference map.
+//
+// Design (HBM-bound stencil + reduction, no tensor cores):
+//  * one launch covers every image of up to 4 pyramid scales;
+//  * a warp owns a strip of 32 lanes x VEC px (VEC=4: 128-bit coalesced loads); the strips of the
+//    stencil kernels overlap by one lane on each side, so horizontal neighbours always come from a
+//    warp shuffle and vertical ones from registers -- no shared memory, no divergent edge loads,
+//    straight-line code so every load of a work item is in flight before the first use;
+//  * forward: 3x3 directional responses -> pick by quantised normal -> sigmoid -> soft-label BCE
+//    terms; per-thread fp32 partials -> warp shuffle -> one fp64 partial row per CTA -> the last CTA
+//    (atomic ticket) folds all partials in a fixed order, computes the per-image class balance alpha
+//    and writes the loss: single launch, no host sync, bit-reproducible run to run;
+//  * backward: recomputes the per-pixel coefficient from depth/edge/normal (16 B/px of traffic;
+//    the forward stashes only alpha) and gathers the 3x3 adjoint from registers + shuffles.
+#pragma once
+#include <math.h>
+
+#include "common.cuh"
+
+namespace mte {
+namespace loss {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kAcc = 8;
+enum { A_WP = 0, A_WN, A_SPU, A_SNU, A_SPM, A_SNM, A_SUMM, A_FLAGS };
+enum { F_HAS0 = 1u, F_HAS1 = 2u, F_OTHER = 4u };
+enum { MODE_NONE = 0, MODE_MAG = 1, MODE_DIR = 2 };
+
+constexpr int kFwdRH = 4;   // output rows per forward work item
+constexpr int kBwdRH = 8;   // output rows per backward work item
+constexpr int kHaloLanes = 30;  // writing lanes of an overlapped strip (one halo lane per side)
+// The backward needs the coefficient of the neighbouring pixel, i.e. depth two columns out: with
+// VEC=1 that is two halo lanes per side.
+__host__ __device__ constexpr int bwd_halo(int vec) { return vec == 1 ? 2 : 1; }
+__host__ __device__ constexpr int bwd_lanes(int vec) { return 32 - 2 * bwd_halo(vec); }
+
+constexpr float kEps = 0.001f;  // grad_loss.py:167,180
+constexpr float kLn2 = 0.6931471805599453f;
+
+struct ScaleP {
+    const float *x, *e, *n, *m;
+    float *g, *dx;
+    int B, H, W;
+    int strips, rowBlocks, items, ctasPerImage;
+    int ctaBase, imgBase;
+    float scaleWeight;
+};
+
+struct LossP {
+    ScaleP s[MTE_MAX_SCALES];
+    int nScales, totalCtas, totalImages;
+    float T, weight, p2n;
+    double *partials;       // [totalCtas][kAcc]
+    double *segsums;        // [totalImages][kAcc]
+    unsigned *ticket;
+    float *lossOut;         // [1+nScales]
+    float *ctx;             // [totalImages] alpha, then per scale {coef, maskBinary}
+    const float *gradLoss;  // bwd: [1+nScales]
+};
+
+// fp32-rounded k*pi/8, exactly the constants torch compares against (grad_loss.py:80-93)
+#define MTE_B1 ((float)(1 * M_PI / 8))
+#define MTE_B3 ((float)(3 * M_PI / 8))
+#define MTE_B5 ((float)(5 * M_PI / 8))
+#define MTE_B7 ((float)(7 * M_PI / 8))
+
+// Quantised normal direction 0:h 1:rl 2:v 3:lr (grad_loss.py:80-93).  The reference bands are
+// [B3,B5)->v [B1,B3)->rl [B5,B7)->lr for theta >= 0 and [-B5,-B3)->v [-B7,-B5)->rl [-B3,-B1)->lr for
+// theta < 0, everything else (incl. NaN) -> h.  With u = |theta| the negative side is the mirrored
+// table with the closed end on the other side, so u is stepped down one ulp there (u > B <=> pred(u) >= B)
+// and four compares decide both signs exactly.
+__device__ __forceinline__ int dir_index(float t) {
+    const bool neg = t < 0.f;
+    const int ub = (__float_as_int(t) & 0x7fffffff) - (neg ? 1 : 0);
+    const float u = __int_as_float(ub);
+    const int n = (u >= MTE_B1) + (u >= MTE_B3) + (u >= MTE_B5) + (u >= MTE_B7);
+    return (neg ? -n : n) & 3;
+}
+
+// cond ? a : b as a real SELP: keeps ptxas from turning value selections into divergent branches
+__device__ __forceinline__ float fsel(bool cond, float a, float b) {
+    float r;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f32 %0, %1, %2, p;\n\t}" : "=f"(r) : "f"(a), "f"(b), "r"((int)cond));
+    return r;
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// 1/d correctly rounded for d in the normal range (two FMA Newton steps on MUFU.RCP), branch-free.
+__device__ __forceinline__ float rcp_rn_normal(float d) {
+    float r = rcp_approx(d);
+    float e = fmaf(-d, r, 1.0f);
+    r = fmaf(r, e, r);
+    e = fmaf(-d, r, 1.0f);
+    return fmaf(r, e, r);
+}
+__device__ __forceinline__ float inv_to_depth(float v) { return rcp_rn_normal(fmaxf(v, 1e-6f)); }
+
+// Forward: the loss is a mean over millions of terms; MUFU-accuracy sigmoid is far inside 1e-5.
+__device__ __forceinline__ float sigmoid_fast(float z) { return rcp_approx(1.0f + __expf(-z)); }
+// Backward: p(1-p)/(1-p+eps) amplifies the last bits of p where the sigmoid saturates, so p is
+// computed the way eager PyTorch does (accurate expf, correctly rounded divide): the gradient then
+// reproduces the reference's own rounding, not only the underlying math.
+__device__ __forceinline__ float sigmoid_ref(float z) { return rcp_rn_normal(1.0f + expf(-z)); }
+
+template <int VEC>
+struct Row {
+    float c[VEC];
+    float l, r;
+    __device__ __forceinline__ float at(int v) const { return v < 0 ? l : (v >= VEC ? r : c[v]); }
+};
+
+template <int VEC>
+__device__ __forceinline__ void load_vec(float (&out)[VEC], const float *img, int row, int H, int W, int col0,
+                                         bool cached) {
+    const bool ok = (row >= 0) && (row < H) && (col0 >= 0) && (col0 < W);
+    const float *p = img + (size_t)(ok ? row : 0) * W + (ok ? col0 : 0);
+    if (VEC == 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) v = cached ? ld_cached4(p) : ld_stream4(p);
+        out[0] = v.x; out[1 % VEC] = v.y; out[2 % VEC] = v.z; out[3 % VEC] = v.w;
+    } else {
+        float v = 0.f;
+        if (ok) v = cached ? __ldg(p) : __ldcs(p);
+        out[0] = v;
+    }
+}
+
+// Centre values of one depth row; out-of-image reads give 0 (the zero padding of conv2d(padding=1)).
+template <int VEC, bool INV>
+__device__ __forceinline__ void load_row(Row<VEC> &R, const float *img, int row, int H, int W, int col0) {
+    load_vec<VEC>(R.c, img, row, H, W, col0, true);
+    if (INV) {
+        const bool ok = (row >= 0) && (row < H) && (col0 >= 0) && (col0 < W);
+#pragma unroll
+        for (int v = 0; v < VEC; v++) R.c[v] = ok ? inv_to_depth(R.c[v]) : 0.f;
+    }
+}
+// Horizontal neighbours across the lane boundary (lanes 0 / 31 get don't-care values: they are halo lanes).
+template <int VEC>
+__device__ __forceinline__ void exchange_row(Row<VEC> &R) {
+    R.l = __shfl_up_sync(MTE_FULL_MASK, R.c[VEC - 1], 1);
+    R.r = __shfl_down_sync(MTE_FULL_MASK, R.c[0], 1);
+}
+
+// Separable parts of the four zero-padded 3x3 cross-correlations of grad_loss.py:20-31 at column v of
+// the middle row:  c_v = P + dv,  c_h = R + Dm,  c_lr = P + R,  c_rl = R - P.
+template <int VEC>
+__device__ __forceinline__ void stencil_parts(const Row<VEC> &up, const Row<VEC> &mid, const Row<VEC> &dn, int v,
+                                              float &P, float &R, float &Dm, float &dv) {
+    const float tl = up.at(v - 1), tc = up.at(v), tr = up.at(v + 1);
+    const float ml = mid.at(v - 1), mr = mid.at(v + 1);
+    const float bl = dn.at(v - 1), bc = dn.at(v), br = dn.at(v + 1);
+    P = (bl + bc + br) - (tl + tc + tr);
+    Dm = mr - ml;
+    R = (tr - tl) + Dm + (br - bl);
+    dv = bc - tc;
+}
+// Response of direction k (0:h 1:rl 2:v 3:lr) by operand selection: no divergent branches.
+__device__ __forceinline__ float pick_response(int k, float P, float R, float Dm, float dv) {
+    const float a = fsel(k < 2, R, P);
+    const float b = fsel(k == 0, Dm, fsel(k == 1, -P, fsel(k == 2, dv, R)));
+    return a + b;
+}
+
+// ---------------------------------------------------------------------------
+// Forward
+// ---------------------------------------------------------------------------
+static __device__ __noinline__ void finalize_loss(const LossP &P, bool hasMask) {
+    // Run by every thread of the LAST CTA.  Fixed summation order => reproducible.
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int si = 0; si < P.nScales; si++) {
+        const ScaleP &S = P.s[si];
+        for (int b = warp; b < S.B; b += kWarps) {
+            double a[kAcc];
+            unsigned fl = 0;
+#pragma unroll
+            for (int k = 0; k < kAcc; k++) a[k] = 0.0;
+            const double *base = P.partials + (size_t)(S.ctaBase + b * S.ctasPerImage) * kAcc;
+            for (int c = lane; c < S.ctasPerImage; c += 32) {
+                const double *q = base + (size_t)c * kAcc;
+#pragma unroll
+                for (int k = 0; k < kAcc - 1; k++) a[k] += __ldcg(q + k);
+                fl |= (unsigned)__ldcg(q + A_FLAGS);
+            }
+#pragma unroll
+            for (int k = 0; k < kAcc - 1; k++) a[k] = warp_sum(a[k]);
+            fl = warp_or(fl);
+            if (lane == 0) {
+                double *o = P.segsums + (size_t)(S.imgBase + b) * kAcc;
+#pragma unroll
+                for (int k = 0; k < kAcc - 1; k++) o[k] = a[k];
+                o[A_FLAGS] = (double)fl;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double total = 0.0;
+        for (int si = 0; si < P.nScales; si++) {
+            const ScaleP &S = P.s[si];
+            const double npix = (double)S.H * (double)S.W;
+            unsigned fl = 0;
+            double wnAll = 0.0, sumM = 0.0;
+            for (int b = 0; b < S.B; b++) {
+                const double *o = P.segsums + (size_t)(S.imgBase + b) * kAcc;
+                fl |= (unsigned)o[A_FLAGS];
+                wnAll += hasMask ? o[A_WN] : (npix - o[A_WP]);
+                sumM += o[A_SUMM];
+            }
+            // grad_loss.py:183-187: the mask only masks when its value set is exactly {0,1}
+            const bool binary = hasMask && fl == (F_HAS0 | F_HAS1);
+            const double valid = binary ? sumM : npix * (double)S.B;
+            double acc = 0.0;
+            for (int b = 0; b < S.B; b++) {
+                const double *o = P.segsums + (size_t)(S.imgBase + b) * kAcc;
+                const double wp = o[A_WP];
+                const double wn = hasMask ? o[A_WN] : (npix - wp);
+                const float alpha = (wnAll == 0.0) ? 1.0f : (float)(wn / (wp + wn));  // grad_loss.py:175-178
+                const double sp = (double)kLn2 * (binary ? o[A_SPM] : o[A_SPU]);
+                const double sn = (double)kLn2 * (binary ? o[A_SNM] : o[A_SNU]);
+                acc += -(double)P.p2n * (double)alpha * sp - (1.0 - (double)alpha) * sn;
+                P.ctx[S.imgBase + b] = alpha;
+            }
+            const double lossS = (double)P.weight * (acc / valid);
+            P.lossOut[1 + si] = (float)lossS;
+            P.ctx[P.totalImages + 2 * si] = (float)((double)P.weight / valid);
+            P.ctx[P.totalImages + 2 * si + 1] = binary ? 1.0f : 0.0f;
+            total += (double)S.scaleWeight * lossS;
+        }
+        P.lossOut[0] = (float)total;
+        *P.ticket = 0u;  // leave the workspace header clean for the next launch
+    }
+}
+
+template <int VEC, int MODE, bool MASK, bool INV, bool SIG>
+__global__ void __launch_bounds__(kThreads) edge_loss_fwd_kernel(const __grid_constant__ LossP P) {
+    constexpr int RH = kFwdRH;
+    constexpr int LANES = (MODE == MODE_NONE) ? 32 : kHaloLanes;
+    constexpr int OFF = (MODE == MODE_NONE) ? 0 : 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int si = 0;
+#pragma unroll
+    for (int k = 1; k < MTE_MAX_SCALES; k++)
+        if (k < P.nScales && (int)blockIdx.x >= P.s[k].ctaBase) si = k;
+    const ScaleP &S = P.s[si];
+    const int local = blockIdx.x - S.ctaBase;
+    const int img = local / S.ctasPerImage;
+    const int item = (local - img * S.ctasPerImage) * kWarps + warp;
+
+    float acc[kAcc - 1];
+#pragma unroll
+    for (int k = 0; k < kAcc - 1; k++) acc[k] = 0.f;
+    unsigned flags = 0;
+
+    if (item < S.items) {  // warp-uniform
+        const int H = S.H, W = S.W;
+        const int strip = item / S.rowBlocks;  // vertically adjacent row blocks share a CTA (L1 halo reuse)
+        const int rb = item - strip * S.rowBlocks;
+        const int row0 = rb * RH;
+        const int col0 = (strip * LANES + lane - OFF) * VEC;
+        const size_t plane = (size_t)img * H * W;
+        const float *x = S.x + plane;
+        const bool writer = (MODE == MODE_NONE) || (lane >= 1 && lane <= kHaloLanes);
+        const bool colOk = writer && col0 >= 0 && col0 < W;
+
+        constexpr int NR = (MODE == MODE_NONE) ? RH : RH + 2;
+        Row<VEC> rows[NR];
+        float e[RH][VEC], th[RH][VEC], m[RH][VEC];
+        // every load of the item is issued before the first use
+#pragma unroll
+        for (int r = 0; r < NR; r++) load_row<VEC, INV>(rows[r], x, row0 - OFF + r, H, W, col0);
+#pragma unroll
+        for (int r = 0; r < RH; r++) {
+            load_vec<VEC>(e[r], S.e + plane, row0 + r, H, W, col0, false);
+            if (MODE == MODE_DIR) load_vec<VEC>(th[r], S.n + plane, row0 + r, H, W, col0, false);
+            if (MASK) load_vec<VEC>(m[r], S.m + plane, row0 + r, H, W, col0, false);
+        }
+        if (MODE != MODE_NONE) {
+#pragma unroll
+            for (int r = 0; r < NR; r++) exchange_row<VEC>(rows[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < RH; r++) {
+            const int row = row0 + r;
+            const bool ok = colOk && row < H;
+            const float okf = ok ? 1.f : 0.f;
+            float g[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; v++) {
+                if (MODE == MODE_NONE) {
+                    g[v] = rows[r].c[v];
+                } else {
+                    float sP, sR, sDm, sdv;
+                    stencil_parts<VEC>(rows[r], rows[r + 1], rows[r + 2], v, sP, sR, sDm, sdv);
+                    if (MODE == MODE_MAG) {
+                        const float cv = sP + sdv, ch = sR + sDm;
+                        g[v] = sqrtf(cv * cv + ch * ch + 1e-6f);
+                    } else {
+                        g[v] = fabsf(pick_response(dir_index(th[r][v]), sP, sR, sDm, sdv));
+                    }
+                }
+                const float p = SIG ? sigmoid_fast(g[v] - P.T) : g[v];
+                const float ee = okf * e[r][v];
+                const float ne = okf - ee;
+                float lp = __log2f(p + kEps);
+                float ln = __log2f((1.0f - p) + kEps);
+                if (!ok) { lp = 0.f; ln = 0.f; }  // select: halo lanes may hold garbage neighbours
+                acc[A_SPU] = fmaf(ee, lp, acc[A_SPU]);
+                acc[A_SNU] = fmaf(ne, ln, acc[A_SNU]);
+                if (MASK) {
+                    const float mm = okf * m[r][v];
+                    acc[A_WP] = fmaf(ee, mm, acc[A_WP]);
+                    acc[A_WN] = fmaf(ne, mm, acc[A_WN]);
+                    acc[A_SUMM] += mm;
+                    const bool keep = m[r][v] != 0.f;
+                    acc[A_SPM] += keep ? ee * lp : 0.f;
+                    acc[A_SNM] += keep ? ne * ln : 0.f;
+                    const unsigned f = (m[r][v] == 0.f) ? F_HAS0 : ((m[r][v] == 1.f) ? F_HAS1 : F_OTHER);
+                    flags |= ok ? f : 0u;
+                } else {
+                    acc[A_WP] += ee;
+                }
+            }
+            if (S.g != nullptr && ok) {
+                float *gp = S.g + plane + (size_t)row * W + col0;
+                if (VEC == 4) st_stream4(gp, make_float4(g[0], g[1 % VEC], g[2 % VEC], g[3 % VEC]));
+                else __stcs(gp, g[0]);
+            }
+        }
+    }
+
+    // warp -> CTA -> one fp64 partial row per CTA
+    __shared__ float sAcc[kWarps][kAcc];
+#pragma unroll
+    for (int k = 0; k < kAcc - 1; k++)
+        if (MASK || k == A_WP || k == A_SPU || k == A_SNU) acc[k] = warp_sum(acc[k]);
+    if (MASK) flags = warp_or(flags);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kAcc - 1; k++) sAcc[warp][k] = acc[k];
+        sAcc[warp][A_FLAGS] = __uint_as_float(flags);
+    }
+    __syncthreads();
+    __shared__ bool sLast;
+    if (threadIdx.x < kAcc) {
+        const int k = threadIdx.x;
+        double v;
+        if (k == A_FLAGS) {
+            unsigned f = 0;
+            for (int w = 0; w < kWarps; w++) f |= __float_as_uint(sAcc[w][k]);
+            v = (double)f;
+        } else {
+            v = 0.0;
+            for (int w = 0; w < kWarps; w++) v += (double)sAcc[w][k];
+        }
+        __stcg(P.partials + (size_t)blockIdx.x * kAcc + k, v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(P.ticket, 1u);
+        sLast = (t == (unsigned)P.totalCtas - 1u);
+    }
+    __syncthreads();
+    if (sLast) {
+        __threadfence();
+        finalize_loss(P, MASK);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Backward
+// ---------------------------------------------------------------------------
+// Adjoint coefficients of one response pixel n: its contribution to the 3x3 neighbourhood is U / V
+// on the two diagonals, A2 above/below, C2 left/right -- from
+// K_d[a][b] = alpha*a*(1+beta*(1-|b|)) + gamma*b*(1+beta*(1-|a|)),  a,b in {-1,0,1}.
+struct Coef {
+    float U, V, A2, C2;
+};
+
+template <int VEC>
+struct CoefRow {
+    Coef c[VEC];
+    Coef l, r;
+    __device__ __forceinline__ const Coef &at(int v) const { return v < 0 ? l : (v >= VEC ? r : c[v]); }
+};
+
+struct BwdImg {
+    float cp, cn;  // -G*coef*lambda*alpha , G*coef*(1-alpha)
+    bool maskBinary;
+};
+
+template <bool MASK, bool SIG>
+__device__ __forceinline__ float dloss_dg(float g, float ee, float mm, const BwdImg &I, float T) {
+    const float p = SIG ? sigmoid_ref(g - T) : g;
+    const float q = 1.0f - p;
+    float d = I.cp * ee * rcp_approx(p + kEps) + I.cn * (1.0f - ee) * rcp_approx(q + kEps);
+    if (MASK) d = (I.maskBinary && mm == 0.f) ? 0.f : d;
+    return SIG ? d * p * q : d;
+}
+
+template <int VEC, int MODE, bool MASK, bool INV, bool SIG>
+__global__ void __launch_bounds__(kThreads) edge_loss_bwd_kernel(const __grid_constant__ LossP P) {
+    static_assert(MODE != MODE_NONE, "pointwise backward has its own kernel");
+    constexpr int RH = kBwdRH;
+    constexpr int PD = 3;  // rows prefetched ahead of the one being consumed
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int si = 0;
+#pragma unroll
+    for (int k = 1; k < MTE_MAX_SCALES; k++)
+        if (k < P.nScales && (int)blockIdx.x >= P.s[k].ctaBase) si = k;
+    const ScaleP &S = P.s[si];
+    const int local = blockIdx.x - S.ctaBase;
+    const int img = local / S.ctasPerImage;
+    const int item = (local - img * S.ctasPerImage) * kWarps + warp;
+    if (item >= S.items) return;  // warp-uniform
+
+    const int H = S.H, W = S.W;
+    const int strip = item / S.rowBlocks;
+    const int rb = item - strip * S.rowBlocks;
+    const int row0 = rb * RH;
+    // writing lanes in the middle of the strip; the outer lanes only supply halo depth / coefficients
+    constexpr int HALO = bwd_halo(VEC), LANES = bwd_lanes(VEC);
+    const int col0 = (strip * LANES + lane - HALO) * VEC;
+    const size_t plane = (size_t)img * H * W;
+    const float *x = S.x + plane;
+    const bool colOk = col0 >= 0 && col0 < W;
+    const bool writer = lane >= HALO && lane < HALO + LANES && colOk;
+
+    BwdImg I;
+    {
+        const float G = __ldg(P.gradLoss) * S.scaleWeight + __ldg(P.gradLoss + 1 + si);
+        const float coef = __ldg(P.ctx + P.totalImages + 2 * si) * G;
+        const float alpha = __ldg(P.ctx + S.imgBase + img);
+        I.cp = -coef * P.p2n * alpha;
+        I.cn = coef * (1.0f - alpha);
+        I.maskBinary = MASK && (__ldg(P.ctx + P.totalImages + 2 * si + 1) != 0.f);
+    }
+
+    // Software pipeline over coefficient rows j = 0..RH+1 (image row row0-1+j).  Depth rows are indexed
+    // d = 0..RH+3 (image row row0-2+d); coefficient row j needs depth rows j, j+1, j+2.
+    Row<VEC> xr[3];                       // rolling depth window, xr[d % 3]
+    Row<VEC> pfx[PD];                     // prefetched depth rows (centre values only)
+    float pfe[PD][VEC], pft[PD][VEC], pfm[PD][VEC];
+    float oacc[3][VEC];                   // rolling output accumulators, oacc[o % 3]
+    load_row<VEC, INV>(xr[0], x, row0 - 2, H, W, col0);
+    load_row<VEC, INV>(xr[1], x, row0 - 1, H, W, col0);
+#pragma unroll
+    for (int k = 0; k < PD; k++) {
+        load_row<VEC, INV>(pfx[k], x, row0 + k, H, W, col0);
+        load_vec<VEC>(pfe[k], S.e + plane, row0 - 1 + k, H, W, col0, false);
+        if (MODE == MODE_DIR) load_vec<VEC>(pft[k], S.n + plane, row0 - 1 + k, H, W, col0, false);
+        if (MASK) load_vec<VEC>(pfm[k], S.m + plane, row0 - 1 + k, H, W, col0, false);
+    }
+    exchange_row<VEC>(xr[0]);
+    exchange_row<VEC>(xr[1]);
+#pragma unroll
+    for (int o = 0; o < 3; o++)
+#pragma unroll
+        for (int v = 0; v < VEC; v++) oacc[o][v] = 0.f;
+
+#pragma unroll
+    for (int j = 0; j < RH + 2; j++) {
+        const int row = row0 - 1 + j;
+        // consume the prefetched row, refill the slot PD rows ahead
+        float e[VEC], th[VEC], m[VEC];
+        xr[(j + 2) % 3] = pfx[j % PD];
+#pragma unroll
+        for (int v = 0; v < VEC; v++) {
+            e[v] = pfe[j % PD][v];
+            th[v] = (MODE == MODE_DIR) ? pft[j % PD][v] : 0.f;
+            m[v] = MASK ? pfm[j % PD][v] : 1.f;
+        }
+        if (j + PD < RH + 2) {
+            load_row<VEC, INV>(pfx[j % PD], x, row0 + j + PD, H, W, col0);
+            load_vec<VEC>(pfe[j % PD], S.e + plane, row + PD, H, W, col0, false);
+            if (MODE == MODE_DIR) load_vec<VEC>(pft[j % PD], S.n + plane, row + PD, H, W, col0, false);
+            if (MASK) load_vec<VEC>(pfm[j % PD], S.m + plane, row + PD, H, W, col0, false);
+        }
+        exchange_row<VEC>(xr[(j + 2) % 3]);
+        const Row<VEC> &up = xr[j % 3], &mid = xr[(j + 1) % 3], &dn = xr[(j + 2) % 3];
+        const bool live = colOk && row >= 0 && row < H;
+        CoefRow<VEC> C;
+#pragma unroll
+        for (int v = 0; v < VEC; v++) {
+            float sP, sR, sDm, sdv;
+            stencil_parts<VEC>(up, mid, dn, v, sP, sR, sDm, sdv);
+            Coef k;
+            if (MODE == MODE_MAG) {
+                const float cv = sP + sdv, ch = sR + sDm;
+                const float g = sqrtf(cv * cv + ch * ch + 1e-6f);
+                const float d = dloss_dg<MASK, SIG>(g, e[v], m[v], I, P.T);
+                const float rg = d * rcp_rn_normal(g);
+                const float sv = rg * cv, sh = rg * ch;
+                k.U = sv + sh; k.V = sv - sh; k.A2 = 2.f * sv; k.C2 = 2.f * sh;
+            } else {
+                const int di = dir_index(th[v]);
+                const float c = pick_response(di, sP, sR, sDm, sdv);
+                const float d = dloss_dg<MASK, SIG>(fabsf(c), e[v], m[v], I, P.T);
+                const float s = fsel(c > 0.f, d, fsel(c < 0.f, -d, 0.f));
+                const float s2 = 2.f * s;
+                // h: U=s V=-s A2=0 C2=2s | rl: U=0 V=-2s A2=-s C2=s | v: U=s V=s A2=2s C2=0 | lr: U=2s V=0 A2=s C2=s
+                k.U = fsel(di == 1, 0.f, fsel(di == 3, s2, s));
+                k.V = fsel(di == 0, -s, fsel(di == 1, -s2, fsel(di == 2, s, 0.f)));
+                k.A2 = fsel(di == 0, 0.f, fsel(di == 1, -s, fsel(di == 2, s2, s)));
+                k.C2 = fsel(di == 0, s2, fsel(di == 2, 0.f, s));
+            }
+            C.c[v].U = live ? k.U : 0.f;
+            C.c[v].V = live ? k.V : 0.f;
+            C.c[v].A2 = live ? k.A2 : 0.f;
+            C.c[v].C2 = live ? k.C2 : 0.f;
+        }
+        C.l.U = __shfl_up_sync(MTE_FULL_MASK, C.c[VEC - 1].U, 1);
+        C.l.V = __shfl_up_sync(MTE_FULL_MASK, C.c[VEC - 1].V, 1);
+        C.l.C2 = __shfl_up_sync(MTE_FULL_MASK, C.c[VEC - 1].C2, 1);
+        C.r.U = __shfl_down_sync(MTE_FULL_MASK, C.c[0].U, 1);
+        C.r.V = __shfl_down_sync(MTE_FULL_MASK, C.c[0].V, 1);
+        C.r.C2 = __shfl_down_sync(MTE_FULL_MASK, C.c[0].C2, 1);
+        C.l.A2 = 0.f;
+        C.r.A2 = 0.f;
+        // scatter this coefficient row into the output rows o = j-2 (as "down"), j-1 ("mid"), j ("up")
+#pragma unroll
+        for (int v = 0; v < VEC; v++) {
+            const float asUp = C.at(v - 1).U + C.c[v].A2 + C.at(v + 1).V;
+            const float asMid = C.at(v - 1).C2 - C.at(v + 1).C2;
+            const float asDn = C.at(v - 1).V + C.c[v].A2 + C.at(v + 1).U;
+            oacc[j % 3][v] = asUp;              // first contribution of output row j (overwrites the retired slot)
+            if (j >= 1) oacc[(j + 2) % 3][v] += asMid;   // output row j-1
+            if (j >= 2) oacc[(j + 1) % 3][v] -= asDn;    // output row j-2 (now complete)
+        }
+        if (j >= 2) {
+            const int o = j - 2;
+            const int orow = row0 + o;
+            float out[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; v++) {
+                float d = oacc[o % 3][v];
+                if (INV) {
+                    // d depth / d inv = -depth^2 where the clamp passes (inv > 1e-6 <=> depth < 1e6), else 0
+                    const float dep = xr[j % 3].c[v];  // depth row index j == image row row0 + o
+                    d = (dep < 1e6f) ? -d * dep * dep : 0.f;
+                }
+                out[v] = d;
+            }
+            if (writer && orow < H) {
+                float *op = S.dx + plane + (size_t)orow * W + col0;
+                if (VEC == 4) st_stream4(op, make_float4(out[0], out[1 % VEC], out[2 % VEC], out[3 % VEC]));
+                else __stcs(op, out[0]);
+            }
+        }
+    }
+}
+
+// launchers implemented one translation unit per (direction, VEC) so they compile in parallel
+void launch_fwd_v4(const LossP &P, int mode, bool mask, bool inv, bool sig, cudaStream_t st);
+void launch_fwd_v1(const LossP &P, int mode, bool mask, bool inv, bool sig, cudaStream_t st);
+void launch_bwd_v4(const LossP &P, int mode, bool mask, bool inv, bool sig, cudaStream_t st);
+void launch_bwd_v1(const LossP &P, int mode, bool mask, bool inv, bool sig, cudaStream_t st);
+
+#define MTE_LOSS_DISPATCH_BOOL(flag, NAME, ...) \
+    if (flag) { constexpr bool NAME = true; __VA_ARGS__ } else { constexpr bool NAME = false; __VA_ARGS__ }
+
+}  // namespace loss
+}  // namespace mte

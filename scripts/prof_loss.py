@@ -1,0 +1,7 @@
+"""Tiny driver for ncu: a few fwd+bwd launches at config-3 shape (B=8, 4 scales) and B=32 single scale."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "scripts"))
+import quick_loss_bench as q
+for cfg in [(8, 384, 1280, 4, 2), (32, 384, 1280, 1, 2)]:
+    print(q.run(*cfg, iters=3))
