@@ -110,6 +110,8 @@ __global__ void resize_bwd_kernel(const float *__restrict__ gout, float *__restr
 // ---------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------
+constexpr int kCtaWaves = 4;
+
 struct Plan {
     LossP P;
     bool vec, hasNormal, hasMask, isGrad;
@@ -163,12 +165,26 @@ static int make_plan(Plan &pl, const mte_loss_scale_t *sc, int n, const mte_loss
         S.strips = ceil_div(S.W, lanesOut * VEC);
         S.rowBlocks = ceil_div(S.H, RH);
         S.items = S.strips * S.rowBlocks;
-        S.ctasPerImage = ceil_div(S.items, kWarps);
+        S.ctasPerImage = ceil_div(S.items, kWarps);  // capped below: warps loop over several items
         S.ctaBase = cta; S.imgBase = img;
         S.scaleWeight = sc[i].scale_weight;
         cta += S.ctasPerImage * S.B;
         img += S.B;
         pl.resized[i] = sc[i].h != sc[i].H || sc[i].w != sc[i].W;
+    }
+    // Cap the grid near kCtaWaves resident waves so the per-CTA epilogue (partials, ticket) is amortised over
+    // several items per warp; every scale keeps at least one CTA per image.
+    const int cap = kNumSMs * 2 * kCtaWaves;
+    if (cta > cap) {
+        const double shrink = (double)cap / (double)cta;
+        cta = 0;
+        for (int i = 0; i < n; i++) {
+            ScaleP &S = P.s[i];
+            int c = (int)(S.ctasPerImage * shrink);
+            S.ctasPerImage = c < 1 ? 1 : c;
+            S.ctaBase = cta;
+            cta += S.ctasPerImage * S.B;
+        }
     }
     P.nScales = n; P.totalCtas = cta; P.totalImages = img;
     if (at) {

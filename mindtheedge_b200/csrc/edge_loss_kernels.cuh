@@ -238,7 +238,7 @@ static __device__ __noinline__ void finalize_loss(const LossP &P, bool hasMask) 
 }
 
 template <int VEC, int MODE, bool MASK, bool INV, bool SIG>
-__global__ void __launch_bounds__(kThreads) edge_loss_fwd_kernel(const __grid_constant__ LossP P) {
+__global__ void __launch_bounds__(kThreads, 2) edge_loss_fwd_kernel(const __grid_constant__ LossP P) {
     constexpr int RH = kFwdRH;
     constexpr int LANES = (MODE == MODE_NONE) ? 32 : kHaloLanes;
     constexpr int OFF = (MODE == MODE_NONE) ? 0 : 1;
@@ -250,14 +250,15 @@ __global__ void __launch_bounds__(kThreads) edge_loss_fwd_kernel(const __grid_co
     const ScaleP &S = P.s[si];
     const int local = blockIdx.x - S.ctaBase;
     const int img = local / S.ctasPerImage;
-    const int item = (local - img * S.ctasPerImage) * kWarps + warp;
+    const int item0 = (local - img * S.ctasPerImage) * kWarps + warp;
 
     float acc[kAcc - 1];
 #pragma unroll
     for (int k = 0; k < kAcc - 1; k++) acc[k] = 0.f;
     unsigned flags = 0;
 
-    if (item < S.items) {  // warp-uniform
+    // a warp walks the items of its image with stride ctasPerImage*kWarps (warp-uniform trip count)
+    for (int item = item0; item < S.items; item += S.ctasPerImage * kWarps) {
         const int H = S.H, W = S.W;
         const int strip = item / S.rowBlocks;  // vertically adjacent row blocks share a CTA (L1 halo reuse)
         const int rb = item - strip * S.rowBlocks;
@@ -359,8 +360,8 @@ __global__ void __launch_bounds__(kThreads) edge_loss_fwd_kernel(const __grid_co
             for (int w = 0; w < kWarps; w++) v += (double)sAcc[w][k];
         }
         __stcg(P.partials + (size_t)blockIdx.x * kAcc + k, v);
+        __threadfence();  // only the writers fence; the ticket below is taken after the barrier
     }
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned t = atomicAdd(P.ticket, 1u);
@@ -405,10 +406,10 @@ __device__ __forceinline__ float dloss_dg(float g, float ee, float mm, const Bwd
 }
 
 template <int VEC, int MODE, bool MASK, bool INV, bool SIG>
-__global__ void __launch_bounds__(kThreads) edge_loss_bwd_kernel(const __grid_constant__ LossP P) {
+__global__ void __launch_bounds__(kThreads, 2) edge_loss_bwd_kernel(const __grid_constant__ LossP P) {
     static_assert(MODE != MODE_NONE, "pointwise backward has its own kernel");
     constexpr int RH = kBwdRH;
-    constexpr int PD = 3;  // rows prefetched ahead of the one being consumed
+    constexpr int PD = 2;  // rows prefetched ahead of the one being consumed (register budget: 128)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int si = 0;
 #pragma unroll
@@ -417,20 +418,8 @@ __global__ void __launch_bounds__(kThreads) edge_loss_bwd_kernel(const __grid_co
     const ScaleP &S = P.s[si];
     const int local = blockIdx.x - S.ctaBase;
     const int img = local / S.ctasPerImage;
-    const int item = (local - img * S.ctasPerImage) * kWarps + warp;
-    if (item >= S.items) return;  // warp-uniform
-
+    const int item0 = (local - img * S.ctasPerImage) * kWarps + warp;
     const int H = S.H, W = S.W;
-    const int strip = item / S.rowBlocks;
-    const int rb = item - strip * S.rowBlocks;
-    const int row0 = rb * RH;
-    // writing lanes in the middle of the strip; the outer lanes only supply halo depth / coefficients
-    constexpr int HALO = bwd_halo(VEC), LANES = bwd_lanes(VEC);
-    const int col0 = (strip * LANES + lane - HALO) * VEC;
-    const size_t plane = (size_t)img * H * W;
-    const float *x = S.x + plane;
-    const bool colOk = col0 >= 0 && col0 < W;
-    const bool writer = lane >= HALO && lane < HALO + LANES && colOk;
 
     BwdImg I;
     {
@@ -441,6 +430,18 @@ __global__ void __launch_bounds__(kThreads) edge_loss_bwd_kernel(const __grid_co
         I.cn = coef * (1.0f - alpha);
         I.maskBinary = MASK && (__ldg(P.ctx + P.totalImages + 2 * si + 1) != 0.f);
     }
+
+    for (int item = item0; item < S.items; item += S.ctasPerImage * kWarps) {  // warp-uniform
+    const int strip = item / S.rowBlocks;
+    const int rb = item - strip * S.rowBlocks;
+    const int row0 = rb * RH;
+    // writing lanes in the middle of the strip; the outer lanes only supply halo depth / coefficients
+    constexpr int HALO = bwd_halo(VEC), LANES = bwd_lanes(VEC);
+    const int col0 = (strip * LANES + lane - HALO) * VEC;
+    const size_t plane = (size_t)img * H * W;
+    const float *x = S.x + plane;
+    const bool colOk = col0 >= 0 && col0 < W;
+    const bool writer = lane >= HALO && lane < HALO + LANES && colOk;
 
     // Software pipeline over coefficient rows j = 0..RH+1 (image row row0-1+j).  Depth rows are indexed
     // d = 0..RH+3 (image row row0-2+d); coefficient row j needs depth rows j, j+1, j+2.
@@ -554,6 +555,7 @@ __global__ void __launch_bounds__(kThreads) edge_loss_bwd_kernel(const __grid_co
             }
         }
     }
+    }  // item loop
 }
 
 // launchers implemented one translation unit per (direction, VEC) so they compile in parallel

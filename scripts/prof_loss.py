@@ -3,5 +3,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "scripts"))
 import quick_loss_bench as q
-for cfg in [(8, 384, 1280, 4, 2), (32, 384, 1280, 1, 2)]:
-    print(q.run(*cfg, iters=3))
+cfgs = [(8, 384, 1280, 4, 2), (32, 384, 1280, 1, 2)]
+if len(sys.argv) > 1: cfgs = [cfgs[int(sys.argv[1])]]
+for cfg in cfgs:
+    print(q.run(*cfg, iters=2))
