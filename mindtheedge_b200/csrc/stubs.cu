@@ -1,7 +1,5 @@
 // Entry points not implemented yet (replaced as their kernels land).
 #include "common.cuh"
-extern "C" size_t mte_canny_workspace_bytes(int, int, int, int) { return 0; }
-extern "C" int mte_canny_from_depth(const void *, int, int, int, int, double, double, const int32_t *, const int32_t *, int, uint8_t *, uint8_t *, void *, size_t, mte_stream_t) { return MTE_ERR_ARG; }
 extern "C" size_t mte_dee_workspace_bytes(int, int, int) { return 0; }
 extern "C" int mte_dee_postprocess(const void *, int, int, int, int, int, int, double, double, uint8_t *, void *, int, void *, size_t, mte_stream_t) { return MTE_ERR_ARG; }
 extern "C" size_t mte_pr_workspace_bytes(int, int, int, int, double) { return 0; }
