@@ -1,0 +1,493 @@
+// Precision / recall counts for the depth-edge AUC metric (sm_100a).
+//
+// Replaces (reference root relative):
+//   evaluate_boundaries        eval_depth_edges.py:67-145   (threshold loop :117-143)
+//   crop of _pred_eval         eval_depth_edges.py:195-197, 206-208
+//   per-image sum              eval_depth_edges.py:298-301
+//   correspond_pixels          py-bsds500 (not vendored), call sites eval_depth_edges.py:50-52, 130-132
+//
+// The matcher is an exact maximum-cardinality bipartite matching between predicted and GT boundary
+// pixels closer than max_dist * diagonal (counts are unique for any maximum matching).
+// One persistent CTA per (image, threshold) problem, problems handed out through an atomic counter:
+//   scan   the cropped window once (the 2 B/px of algorithmic traffic), compact predicted pixels,
+//   greedy nearest-first proposals with 16-bit CAS on the GT side,
+//   then phases of { exhaustive alternating-forest BFS from all free predicted pixels, level-synchronous
+//   with warp-per-vertex expansion; one vertex-disjoint augmenting path per tree, claimed with CAS }
+//   until a phase finds no free GT pixel => no augmenting path exists => the matching is maximum.
+// Per-pixel state is 16-bit offset codes in an L2-resident per-CTA arena; nothing is allocated.
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace mte {
+namespace pr {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr unsigned short kFree = 0xFFFF;
+constexpr unsigned short kDead = 0xFFFE;  // predicted pixel without any GT pixel in range
+constexpr int kMaxOffsets = 0xFFF0;
+constexpr int kCtasPerSm = 2;
+
+enum { IN_LEVELS = 0, IN_BINARY = 1, IN_F32 = 2, IN_F64 = 3 };
+
+struct MatchP {
+    const void *pred;          // [N,H,W] levels u8 / binary u8 / f32 / f64   (binary mode: [nProblems,H,W])
+    const unsigned char *gt;   // [N,H,W]   (binary mode: [nProblems,H,W])
+    int inMode;
+    int N, H, W, T;
+    int x0, y0, w, h;          // window
+    int nProblems;             // N*T
+    const double *thr;         // [T] device (float modes)
+    int noff;
+    const short2 *off;         // [noff] (dx, dy), nearest first
+    const unsigned short *neg; // [noff] index of the negated offset
+    unsigned long long *counts;  // [T][4] count_r,sum_r,count_p,sum_p (accumulated)   (pr mode)
+    long long *countPerProblem;  // [nProblems] (correspond_pixels mode) or nullptr
+    unsigned char *matchA, *matchB;  // optional outputs [nProblems,h,w]
+    char *arena;               // kArenas * arenaBytes
+    size_t arenaBytes;
+    unsigned int *nextProblem; // dynamic scheduler (self-resetting)
+    unsigned int *doneCtas;
+};
+
+// Small tables ride in the kernel parameters (graph-capturable, no staging copy); larger ones (radius > 7 px
+// or > kParamThr thresholds) are copied into the workspace first.  Either way the CTA stages the offsets in
+// shared memory: lanes index them divergently.
+constexpr int kParamOff = 256, kParamThr = 160, kSmemOff = 4096;
+struct ParamTables {
+    short2 off[kParamOff];
+    unsigned short neg[kParamOff];
+    double thr[kParamThr];
+};
+
+struct Arena {
+    unsigned short *mateP, *mateQ, *parentQ, *stampQ, *claimP;
+    int *plist, *fa, *fb, *ends;
+};
+
+__host__ __device__ inline size_t arena_bytes(int h, int w) {
+    const size_t px = (size_t)h * w;
+    return align_up(px * 2, 256) * 5 + align_up(px * 4, 256) * 4;
+}
+
+__device__ inline Arena carve(char *base, int h, int w) {
+    const size_t px = (size_t)h * w;
+    const size_t s2 = align_up(px * 2, 256), s4 = align_up(px * 4, 256);
+    Arena A;
+    A.mateP = (unsigned short *)base; base += s2;
+    A.mateQ = (unsigned short *)base; base += s2;
+    A.parentQ = (unsigned short *)base; base += s2;
+    A.stampQ = (unsigned short *)base; base += s2;
+    A.claimP = (unsigned short *)base; base += s2;
+    A.plist = (int *)base; base += s4;
+    A.fa = (int *)base; base += s4;
+    A.fb = (int *)base; base += s4;
+    A.ends = (int *)base;
+    return A;
+}
+
+__device__ __forceinline__ unsigned short cas16(unsigned short *addr, unsigned short expected, unsigned short val) {
+    return atomicCAS(addr, expected, val);
+}
+
+__device__ __forceinline__ bool is_pred(const MatchP &P, int img, int t, int prob, int gy, int gx) {
+    const size_t o = (size_t)gy * P.W + gx;
+    switch (P.inMode) {
+        case IN_LEVELS: return ((const unsigned char *)P.pred)[(size_t)img * P.H * P.W + o] <= t;
+        case IN_BINARY: return ((const unsigned char *)P.pred)[(size_t)prob * P.H * P.W + o] != 0;
+        case IN_F32: return (double)((const float *)P.pred)[(size_t)img * P.H * P.W + o] >= P.thr[t];
+        default: return ((const double *)P.pred)[(size_t)img * P.H * P.W + o] >= P.thr[t];
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) match_kernel(const __grid_constant__ MatchP Pin,
+                                                         const __grid_constant__ ParamTables tabs, int tablesInParam) {
+    __shared__ int sProblem, sNP, sNQ, sCntA, sCntB, sEnds, sMatched;
+    __shared__ short2 sOff[kSmemOff];
+    __shared__ unsigned short sNeg[kSmemOff];
+    __shared__ double sThr[MTE_MAX_THRESHOLDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    MatchP P = Pin;
+    const int w = P.w, h = P.h;
+    const Arena A = carve(P.arena + (size_t)blockIdx.x * P.arenaBytes, h, w);
+    for (int i = threadIdx.x; i < P.noff; i += kThreads) {
+        sOff[i] = tablesInParam ? tabs.off[i] : P.off[i];
+        sNeg[i] = tablesInParam ? tabs.neg[i] : P.neg[i];
+    }
+    if (P.inMode == IN_F32 || P.inMode == IN_F64)
+        for (int i = threadIdx.x; i < P.T; i += kThreads) sThr[i] = tablesInParam ? tabs.thr[i] : P.thr[i];
+    P.off = sOff;
+    P.neg = sNeg;
+    P.thr = sThr;
+    __syncthreads();
+
+    for (;;) {
+        if (threadIdx.x == 0) sProblem = (int)atomicAdd(P.nextProblem, 1u);
+        __syncthreads();
+        const int prob = sProblem;
+        if (prob >= P.nProblems) break;
+        // problems are ordered image-major so consecutive CTAs share the GT plane in L2
+        const int img = (P.inMode == IN_BINARY) ? prob : prob / P.T;
+        const int t = (P.inMode == IN_BINARY) ? 0 : prob - img * P.T;
+        const unsigned char *gt = P.gt + (size_t)img * P.H * P.W;
+        if (threadIdx.x == 0) { sNP = 0; sNQ = 0; sMatched = 0; }
+        __syncthreads();
+
+        // ---- scan the window: initialise per-pixel state at boundary pixels, compact predicted pixels
+        int myQ = 0;
+        for (int base = 0; base < w * h; base += kThreads) {
+            const int i = base + threadIdx.x;
+            bool isP = false;
+            if (i < w * h) {
+                const int y = i / w, x = i - y * w;
+                const int gy = P.y0 + y, gx = P.x0 + x;
+                isP = is_pred(P, img, t, prob, gy, gx);
+                if (gt[(size_t)gy * P.W + gx] != 0) {
+                    A.mateQ[i] = kFree;
+                    A.stampQ[i] = 0;
+                    myQ++;
+                }
+                if (isP) { A.mateP[i] = kFree; A.claimP[i] = 0; }
+            }
+            const unsigned m = __ballot_sync(MTE_FULL_MASK, isP);
+            int wbase = 0;
+            if (lane == 0 && m) wbase = atomicAdd(&sNP, __popc(m));
+            wbase = __shfl_sync(MTE_FULL_MASK, wbase, 0);
+            if (isP) A.plist[wbase + __popc(m & ((1u << lane) - 1))] = i;
+        }
+        myQ = __reduce_add_sync(MTE_FULL_MASK, myQ);
+        if (lane == 0 && myQ) atomicAdd(&sNQ, myQ);
+        __syncthreads();
+        const int nP = sNP, nQ = sNQ;
+
+        // ---- greedy start: nearest free GT pixel (warp per predicted pixel, lanes over offsets)
+        for (int pi = warp; pi < nP; pi += kWarps) {
+            const int p = A.plist[pi];
+            const int py = p / w, px = p - py * w;
+            bool done = false, anyQ = false;
+            for (int k0 = 0; k0 < P.noff && !done; k0 += 32) {
+                const int k = k0 + lane;
+                bool cand = false;
+                int q = 0;
+                if (k < P.noff) {
+                    const short2 o = P.off[k];
+                    const int qy = py + o.y, qx = px + o.x;
+                    if (qy >= 0 && qy < h && qx >= 0 && qx < w) {
+                        q = qy * w + qx;
+                        cand = gt[(size_t)(P.y0 + qy) * P.W + P.x0 + qx] != 0;
+                    }
+                }
+                unsigned m = __ballot_sync(MTE_FULL_MASK, cand);
+                anyQ |= m != 0;
+                while (m && !done) {  // try candidates nearest first
+                    const int l = __ffs(m) - 1;
+                    m &= m - 1;
+                    int ok = 0;
+                    if (lane == l) {
+                        ok = cas16(&A.mateQ[q], kFree, P.neg[k]) == kFree;
+                        if (ok) A.mateP[p] = (unsigned short)k;
+                    }
+                    done = __shfl_sync(MTE_FULL_MASK, ok, l) != 0;
+                }
+            }
+            if (done && lane == 0) atomicAdd(&sMatched, 1);
+            if (!done && !anyQ && lane == 0) A.mateP[p] = kDead;
+        }
+        __syncthreads();
+
+        // ---- augmenting phases
+        for (unsigned short phase = 1;; phase++) {
+            // frontier 0: free (not dead) predicted pixels
+            if (threadIdx.x == 0) { sCntA = 0; sEnds = 0; }
+            __syncthreads();
+            for (int base = 0; base < nP; base += kThreads) {
+                const int pi = base + threadIdx.x;
+                bool fr = false;
+                int p = 0;
+                if (pi < nP) { p = A.plist[pi]; fr = A.mateP[p] == kFree; }
+                const unsigned m = __ballot_sync(MTE_FULL_MASK, fr);
+                int wbase = 0;
+                if (lane == 0 && m) wbase = atomicAdd(&sCntA, __popc(m));
+                wbase = __shfl_sync(MTE_FULL_MASK, wbase, 0);
+                if (fr) A.fa[wbase + __popc(m & ((1u << lane) - 1))] = p;
+            }
+            __syncthreads();
+            int *cur = A.fa, *nxt = A.fb;
+            int nCur = sCntA;
+            if (nCur == 0) break;
+            // exhaustive alternating-forest BFS
+            while (nCur > 0) {
+                if (threadIdx.x == 0) sCntB = 0;
+                __syncthreads();
+                for (int fi = warp; fi < nCur; fi += kWarps) {
+                    const int p = cur[fi];
+                    const int py = p / w, px = p - py * w;
+                    for (int k0 = 0; k0 < P.noff; k0 += 32) {
+                        const int k = k0 + lane;
+                        if (k >= P.noff) continue;
+                        const short2 o = P.off[k];
+                        const int qy = py + o.y, qx = px + o.x;
+                        if (qy < 0 || qy >= h || qx < 0 || qx >= w) continue;
+                        if (gt[(size_t)(P.y0 + qy) * P.W + P.x0 + qx] == 0) continue;
+                        const int q = qy * w + qx;
+                        const unsigned short s = A.stampQ[q];
+                        if (s == phase) continue;
+                        if (cas16(&A.stampQ[q], s, phase) != s) continue;  // someone else got it
+                        A.parentQ[q] = P.neg[k];
+                        const unsigned short mq = A.mateQ[q];
+                        if (mq == kFree) {
+                            A.ends[atomicAdd(&sEnds, 1)] = q;
+                        } else {
+                            const short2 om = P.off[mq];
+                            nxt[atomicAdd(&sCntB, 1)] = (qy + om.y) * w + (qx + om.x);
+                        }
+                    }
+                }
+                __syncthreads();
+                nCur = sCntB;
+                int *tmp = cur; cur = nxt; nxt = tmp;
+                __syncthreads();
+            }
+            const int nEnds = sEnds;
+            if (nEnds == 0) break;  // no augmenting path anywhere: maximum
+            // one vertex-disjoint augmenting path per tree
+            for (int ei = threadIdx.x; ei < nEnds; ei += kThreads) {
+                const int qEnd = A.ends[ei];
+                int q = qEnd;
+                bool ok = true;
+                for (;;) {  // claim walk (no mate is touched)
+                    const short2 o = P.off[A.parentQ[q]];
+                    const int qy = q / w, qx = q - qy * w;
+                    const int p = (qy + o.y) * w + (qx + o.x);
+                    const unsigned short c = A.claimP[p];
+                    if (c == phase || cas16(&A.claimP[p], c, phase) != c) { ok = false; break; }
+                    const unsigned short mp = A.mateP[p];
+                    if (mp == kFree) break;  // reached the root
+                    const short2 om = P.off[mp];
+                    const int py = qy + o.y, px = qx + o.x;
+                    q = (py + om.y) * w + (px + om.x);
+                }
+                if (!ok) continue;
+                q = qEnd;
+                for (;;) {  // flip walk
+                    const unsigned short pc = A.parentQ[q];
+                    const short2 o = P.off[pc];
+                    const int qy = q / w, qx = q - qy * w;
+                    const int py = qy + o.y, px = qx + o.x;
+                    const int p = py * w + px;
+                    const unsigned short prev = A.mateP[p];
+                    A.mateP[p] = P.neg[pc];
+                    A.mateQ[q] = pc;
+                    if (prev == kFree) break;
+                    const short2 om = P.off[prev];
+                    q = (py + om.y) * w + (px + om.x);
+                }
+                atomicAdd(&sMatched, 1);
+            }
+            __syncthreads();
+            if (phase == 0xFFF0) break;  // unreachable in practice (each phase adds >= 1 match)
+        }
+        __syncthreads();
+
+        // ---- results
+        const int matched = sMatched;
+        if (threadIdx.x == 0) {
+            if (P.counts) {
+                unsigned long long *c = P.counts + (size_t)t * 4;
+                atomicAdd(c + 0, (unsigned long long)matched);
+                atomicAdd(c + 1, (unsigned long long)nQ);
+                atomicAdd(c + 2, (unsigned long long)matched);
+                atomicAdd(c + 3, (unsigned long long)nP);
+            }
+            if (P.countPerProblem) P.countPerProblem[prob] = matched;
+        }
+        if (P.matchA || P.matchB) {
+            for (int i = threadIdx.x; i < w * h; i += kThreads) {
+                const int y = i / w, x = i - y * w;
+                const int gy = P.y0 + y, gx = P.x0 + x;
+                if (P.matchA) {
+                    const bool isP = is_pred(P, img, t, prob, gy, gx);
+                    P.matchA[(size_t)prob * w * h + i] = (isP && A.mateP[i] < kDead) ? 1 : 0;
+                }
+                if (P.matchB) {
+                    const bool isQ = gt[(size_t)gy * P.W + gx] != 0;
+                    P.matchB[(size_t)prob * w * h + i] = (isQ && A.mateQ[i] != kFree) ? 1 : 0;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // last CTA out resets the scheduler so the workspace header is clean for the next launch
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned d = atomicAdd(P.doneCtas, 1u);
+        if (d == gridDim.x - 1) {
+            *P.nextProblem = 0u;
+            *P.doneCtas = 0u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct OffsetTable {
+    int n;
+    short2 off[4096];
+    unsigned short neg[4096];
+};
+
+static int build_offsets(double radius, OffsetTable &tb) {
+    const int r = (int)radius;
+    const double r2 = radius * radius;
+    tb.n = 0;
+    if (r > 31) return MTE_ERR_ARG;  // (2r+1)^2 <= 3969 entries
+    for (int d2 = 0; d2 <= 2 * r * r; d2++)
+        for (int dy = -r; dy <= r; dy++)
+            for (int dx = -r; dx <= r; dx++)
+                if (dy * dy + dx * dx == d2 && (double)d2 <= r2) {
+                    tb.off[tb.n].x = (short)dx;
+                    tb.off[tb.n].y = (short)dy;
+                    tb.n++;
+                }
+    for (int i = 0; i < tb.n; i++)
+        for (int j = 0; j < tb.n; j++)
+            if (tb.off[j].x == -tb.off[i].x && tb.off[j].y == -tb.off[i].y) tb.neg[i] = (unsigned short)j;
+    return MTE_OK;
+}
+
+struct Layout {
+    size_t offTable, offNeg, offThr, offArena, arenaBytes, total;
+    int nArenas;
+};
+
+static Layout layout(int nProblems, int h, int w, int T) {
+    Layout L;
+    size_t off = MTE_WS_HEADER_BYTES;
+    L.offTable = off; off += align_up(sizeof(short2) * 4096, 256);
+    L.offNeg = off; off += align_up(sizeof(unsigned short) * 4096, 256);
+    L.offThr = off; off += align_up(sizeof(double) * (size_t)(T > 0 ? T : 1), 256);
+    L.arenaBytes = align_up(arena_bytes(h, w), 256);
+    int n = kNumSMs * kCtasPerSm;
+    if (n > nProblems) n = nProblems;
+    if (n < 1) n = 1;
+    L.nArenas = n;
+    L.offArena = off; off += L.arenaBytes * (size_t)n;
+    L.total = off;
+    return L;
+}
+
+static void clip_crop(const int32_t *crop, int H, int W, int &x0, int &y0, int &w, int &h) {
+    int cx0 = 0, cx1 = W, cy0 = 0, cy1 = H;
+    if (crop) {
+        // python slice semantics of pred[c2:c3, c0:c1] for non-negative bounds
+        cx0 = crop[0] < 0 ? 0 : (crop[0] > W ? W : crop[0]);
+        cx1 = crop[1] < 0 ? 0 : (crop[1] > W ? W : crop[1]);
+        cy0 = crop[2] < 0 ? 0 : (crop[2] > H ? H : crop[2]);
+        cy1 = crop[3] < 0 ? 0 : (crop[3] > H ? H : crop[3]);
+    }
+    x0 = cx0; y0 = cy0;
+    w = cx1 > cx0 ? cx1 - cx0 : 0;
+    h = cy1 > cy0 ? cy1 - cy0 : 0;
+}
+
+static int launch(MatchP &P, const Layout &L, char *ws, double max_dist, const double *thr_host, cudaStream_t st) {
+    OffsetTable tb;
+    const double radius = max_dist * sqrt((double)P.h * P.h + (double)P.w * P.w);
+    int rc = build_offsets(radius, tb);
+    if (rc) return rc;
+    static_assert(sizeof(MatchP) + sizeof(ParamTables) + 16 <= 4096, "kernel parameters exceed 4 KB");
+    ParamTables pt;
+    const bool inParam = tb.n <= kParamOff && (!thr_host || P.T <= kParamThr);
+    if (inParam) {
+        memcpy(pt.off, tb.off, sizeof(short2) * tb.n);
+        memcpy(pt.neg, tb.neg, sizeof(unsigned short) * tb.n);
+        if (thr_host) memcpy(pt.thr, thr_host, sizeof(double) * P.T);
+    } else {
+        // pageable-host async copies are staged by the runtime before they return (not graph-capturable)
+        cudaError_t e = cudaMemcpyAsync(ws + L.offTable, tb.off, sizeof(short2) * tb.n, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaMemcpyAsync(ws + L.offNeg, tb.neg, sizeof(unsigned short) * tb.n, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return (int)e;
+        if (thr_host && P.T > 0) {
+            e = cudaMemcpyAsync(ws + L.offThr, thr_host, sizeof(double) * P.T, cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) return (int)e;
+        }
+    }
+    P.noff = tb.n;
+    P.off = reinterpret_cast<const short2 *>(ws + L.offTable);
+    P.neg = reinterpret_cast<const unsigned short *>(ws + L.offNeg);
+    P.thr = reinterpret_cast<const double *>(ws + L.offThr);
+    P.arena = ws + L.offArena;
+    P.arenaBytes = L.arenaBytes;
+    WsHeader *hdr = reinterpret_cast<WsHeader *>(ws);
+    P.nextProblem = hdr->ticket + 4;
+    P.doneCtas = hdr->ticket + 5;
+    match_kernel<<<L.nArenas, kThreads, 0, st>>>(P, pt, inParam ? 1 : 0);
+    MTE_RETURN_IF_CUDA_ERROR();
+    return MTE_OK;
+}
+
+}  // namespace pr
+}  // namespace mte
+
+using namespace mte;
+using namespace mte::pr;
+
+extern "C" size_t mte_match_workspace_bytes(int n_problems, int h, int w, double max_dist) {
+    if (n_problems < 1 || h < 1 || w < 1) return 0;
+    (void)max_dist;
+    return layout(n_problems, h, w, 1).total;
+}
+
+extern "C" int mte_correspond_pixels(const uint8_t *a, const uint8_t *b, int n_problems, int h, int w,
+                                     double max_dist, uint8_t *match_a, uint8_t *match_b, int64_t *count,
+                                     void *workspace, size_t ws_bytes, mte_stream_t stream) {
+    if (!a || !b || !workspace) return MTE_ERR_NULL;
+    if (n_problems < 1 || h < 1 || w < 1) return MTE_ERR_SHAPE;
+    if (!(max_dist >= 0.0)) return MTE_ERR_ARG;
+    const Layout L = layout(n_problems, h, w, 1);
+    if (ws_bytes < L.total) return MTE_ERR_WORKSPACE;
+    MatchP P;
+    memset(&P, 0, sizeof(P));
+    P.pred = a; P.gt = b; P.inMode = IN_BINARY;
+    P.N = n_problems; P.H = h; P.W = w; P.T = 1;
+    P.x0 = 0; P.y0 = 0; P.w = w; P.h = h;
+    P.nProblems = n_problems;
+    P.countPerProblem = reinterpret_cast<long long *>(count);
+    P.matchA = match_a; P.matchB = match_b;
+    return launch(P, L, static_cast<char *>(workspace), max_dist, nullptr, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t mte_pr_workspace_bytes(int n_images, int H, int W, int T, double max_dist) {
+    if (n_images < 1 || H < 1 || W < 1 || T < 1) return 0;
+    (void)max_dist;
+    // sized for the un-cropped window (a crop only shrinks it)
+    return layout(n_images * T, H, W, T).total;
+}
+
+extern "C" int mte_pr_counts(const void *pred, int pred_dtype, const uint8_t *gt, int N, int H, int W,
+                             const int32_t *crop, const double *thresholds, int T, double max_dist,
+                             int apply_thinning, int64_t *counts, void *workspace, size_t ws_bytes,
+                             mte_stream_t stream) {
+    if (!pred || !gt || !counts || !workspace) return MTE_ERR_NULL;
+    if (N < 1 || H < 1 || W < 1) return MTE_ERR_SHAPE;
+    if (T < 1 || T > MTE_MAX_THRESHOLDS) return MTE_ERR_ARG;
+    if (!(max_dist >= 0.0)) return MTE_ERR_ARG;
+    if (apply_thinning) return MTE_ERR_ARG;  // thinning runs as mte_binary_thin + mte_correspond_pixels (host layer)
+    if (pred_dtype != MTE_U8 && !thresholds) return MTE_ERR_NULL;
+    const Layout L = layout(N * T, H, W, T);
+    if (ws_bytes < L.total) return MTE_ERR_WORKSPACE;
+    MatchP P;
+    memset(&P, 0, sizeof(P));
+    P.pred = pred; P.gt = gt;
+    P.inMode = pred_dtype == MTE_U8 ? IN_LEVELS : (pred_dtype == MTE_F32 ? IN_F32 : IN_F64);
+    P.N = N; P.H = H; P.W = W; P.T = T;
+    clip_crop(crop, H, W, P.x0, P.y0, P.w, P.h);
+    P.nProblems = N * T;
+    P.counts = reinterpret_cast<unsigned long long *>(counts);
+    if (P.w == 0 || P.h == 0) return MTE_OK;  // empty window: nothing to count
+    return launch(P, L, static_cast<char *>(workspace), max_dist, thresholds, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,261 @@
+"""Depth-edge precision/recall evaluation: drop-in for the reference
+``eval_depth_edges.py``.
+
+Function names, arguments and return values follow the reference
+(``evaluate_boundaries`` :67, ``evaluate_boundaries_bin`` :18,
+``compute_rec_prec_f1`` :147, ``pr_evaluation`` :232,
+``mean_recall_at_precision_range`` :365).  The per-pixel work -- Canny
+extraction for every threshold, binarise + crop, the bipartite matcher and the
+four counts -- runs in libmte.so on the GPU; the final P/R/AUC arithmetic on
+``[T]`` vectors stays in NumPy, exactly as in the reference.
+
+Differences from the reference wiring, none of which changes a count:
+* predicted edge maps are never written to disk; the reference round-trips them
+  through a lossy JPEG and re-thresholds at 0.5 (edge.py:90-91,
+  eval_depth_edges.py:191-194), which flips no pixel of a {0,255} map;
+* the 12 Canny settings share one NMS pass and one hysteresis pass (a single
+  "birth level" plane), and all (image, threshold) matchings run concurrently
+  instead of in a 4-process pool (:262, :296);
+* with ``torch.distributed`` initialised, images are sharded over ranks and the
+  ``int64[T,4]`` counts are summed with ONE all-reduce (mirrors the Python
+  ``sum`` at :298-301).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, runtime
+from .edge import canny_from_depth, read_depth_file
+
+__all__ = [
+    "pr_counts", "correspond_pixels_batch", "evaluate_boundaries", "evaluate_boundaries_bin",
+    "compute_rec_prec_f1", "pr_evaluation", "pr_evaluation_arrays", "mean_recall_at_precision_range",
+]
+
+_DT = {torch.float32: _lib.MTE_F32, torch.float64: _lib.MTE_F64, torch.uint8: _lib.MTE_U8}
+
+
+# ---------------------------------------------------------------------------
+# tensor-level ops
+# ---------------------------------------------------------------------------
+def pr_counts(pred: torch.Tensor, gt: torch.Tensor, thresholds=None, *, n_levels: Optional[int] = None,
+              max_dist: float = 0.0075, crop: Optional[Sequence[int]] = None,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Counts for a batch of images, one GT map each.
+
+    pred  [N,H,W] CUDA: float32/float64 strength map (``pred >= thresholds[t]``) or uint8 level
+          plane from ``canny_from_depth(..., want_levels=True)`` (edge at t iff level <= t; give
+          ``n_levels``).
+    gt    [N,H,W] uint8, non-zero = boundary.
+    crop  ``[x0, x1, y0, y1]`` as the reference's ``gt_crop`` (python slices ``[y0:y1, x0:x1]``).
+    ->    int64 [T,4] on the device, columns count_r, sum_r, count_p, sum_p, summed over the
+          batch and ACCUMULATED into ``out`` when given."""
+    runtime.require_cuda(pred, "pred")
+    runtime.require_cuda(gt, "gt")
+    if pred.dim() == 2:
+        pred, gt = pred.unsqueeze(0), gt.unsqueeze(0)
+    if pred.dtype not in _DT:
+        raise _lib.MteError(f"unsupported pred dtype {pred.dtype}")
+    pred = pred.contiguous()
+    gt = gt.contiguous()
+    if gt.dtype != torch.uint8:
+        gt = (gt != 0).to(torch.uint8)
+    if gt.shape != pred.shape:
+        raise _lib.MteError("pred and gt must have the same [N,H,W] shape")
+    N, H, W = pred.shape
+    dev = pred.device
+    if pred.dtype == torch.uint8:
+        if n_levels is None:
+            raise _lib.MteError("n_levels is required with a uint8 level plane")
+        T, thr = int(n_levels), None
+    else:
+        t = np.ascontiguousarray(np.asarray(thresholds, dtype=np.float64))
+        T = int(t.shape[0])
+        thr = t.ctypes.data_as(C.POINTER(C.c_double))
+    if out is None:
+        out = torch.zeros((T, 4), dtype=torch.int64, device=dev)
+    cr = None if crop is None or len(crop) == 0 else (C.c_int32 * 4)(*[int(v) for v in crop])
+    ws = runtime.workspace(dev, _lib.lib.mte_pr_workspace_bytes(N, H, W, T, float(max_dist)))
+    _lib.check(_lib.lib.mte_pr_counts(pred.data_ptr(), _DT[pred.dtype], gt.data_ptr(), N, H, W, cr, thr, T,
+                                      float(max_dist), 0, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                      runtime.current_stream_ptr(dev)), "mte_pr_counts")
+    return out
+
+
+def correspond_pixels_batch(a: torch.Tensor, b: torch.Tensor, max_dist: float = 0.0075, want_maps: bool = True):
+    """Maximum matching between boundary maps a[k], b[k] ([P,h,w] uint8 CUDA).
+    -> (match_a, match_b, count int64[P])."""
+    runtime.require_cuda(a, "a")
+    a = a.contiguous()
+    b = b.contiguous()
+    Pn, h, w = a.shape
+    dev = a.device
+    ma = torch.empty_like(a) if want_maps else None
+    mb = torch.empty_like(b) if want_maps else None
+    cnt = torch.empty(Pn, dtype=torch.int64, device=dev)
+    ws = runtime.workspace(dev, _lib.lib.mte_match_workspace_bytes(Pn, h, w, float(max_dist)))
+    _lib.check(_lib.lib.mte_correspond_pixels(a.data_ptr(), b.data_ptr(), Pn, h, w, float(max_dist),
+                                              runtime.ptr(ma), runtime.ptr(mb), cnt.data_ptr(), ws.data_ptr(),
+                                              ws.numel(), runtime.current_stream_ptr(dev)), "mte_correspond_pixels")
+    return ma, mb, cnt
+
+
+# ---------------------------------------------------------------------------
+# NumPy-level mirrors of the reference functions
+# ---------------------------------------------------------------------------
+def _threshold_grid(thresholds):
+    if isinstance(thresholds, int):
+        return np.linspace(1.0 / (thresholds + 1), 1.0 - 1.0 / (thresholds + 1), thresholds)
+    if isinstance(thresholds, np.ndarray):
+        if thresholds.ndim != 1:
+            raise ValueError("thresholds array should have 1 dimension, not {}".format(thresholds.ndim))
+        return thresholds
+    raise ValueError("thresholds should be an int or a NumPy array, not a {}".format(type(thresholds)))
+
+
+def evaluate_boundaries(predicted_boundaries, gt_boundaries, thresholds=99, max_dist=0.0075,
+                        apply_thinning=True, progress=None):
+    """eval_depth_edges.py:67-145 -> (count_r, sum_r, count_p, sum_p, thresholds)."""
+    thresholds = _threshold_grid(thresholds)
+    T = thresholds.shape[0]
+    pred = np.ascontiguousarray(predicted_boundaries)
+    if pred.dtype not in (np.float32, np.float64):
+        pred = pred.astype(np.float64)
+    count_r = np.zeros(T)
+    sum_r = np.zeros(T)
+    count_p = np.zeros(T)
+    sum_p = np.zeros(T)
+    d_pred = torch.from_numpy(pred).cuda()
+    if not apply_thinning and len(gt_boundaries) == 1:
+        gt = torch.from_numpy(np.ascontiguousarray(np.asarray(gt_boundaries[0]) != 0).astype(np.uint8)).cuda()
+        c = pr_counts(d_pred[None], gt[None], thresholds, max_dist=max_dist).cpu().numpy()
+        return (c[:, 0].astype(np.float64), c[:, 1].astype(np.float64), c[:, 2].astype(np.float64),
+                c[:, 3].astype(np.float64), thresholds)
+    # general path (thinning and/or several GT maps): binarise per threshold, thin, match against every GT
+    from .bsds import thin as _thin
+    thr_dev = torch.from_numpy(np.asarray(thresholds, dtype=np.float64)).cuda()
+    bins = (d_pred.double()[None] >= thr_dev[:, None, None]).to(torch.uint8)  # [T,h,w]
+    if apply_thinning:
+        bins = _thin.binary_thin_batch(bins)
+    sum_p[:] = bins.flatten(1).sum(1).cpu().numpy()
+    acc = torch.zeros_like(bins)
+    for g in gt_boundaries:
+        g_np = np.asarray(g)
+        gt = torch.from_numpy(np.ascontiguousarray(g_np != 0).astype(np.uint8)).cuda()
+        ma, mb, _ = correspond_pixels_batch(bins, gt[None].expand_as(bins).contiguous(), max_dist)
+        acc |= ma
+        sum_r += float(g_np.sum())
+        count_r += mb.flatten(1).sum(1).cpu().numpy()
+    count_p[:] = acc.flatten(1).sum(1).cpu().numpy()
+    return count_r, sum_r, count_p, sum_p, thresholds
+
+
+def evaluate_boundaries_bin(predicted_boundaries_bin, gt_boundaries, max_dist=0.0075, apply_thinning=True):
+    """eval_depth_edges.py:18-65 -> (count_r, sum_r, count_p, sum_p)."""
+    b = (np.asarray(predicted_boundaries_bin) != 0).astype(np.float64)
+    c_r, s_r, c_p, s_p, _ = evaluate_boundaries(b, gt_boundaries, thresholds=np.array([0.5]), max_dist=max_dist,
+                                                apply_thinning=apply_thinning)
+    return c_r[0], s_r[0], c_p[0], s_p[0]
+
+
+def compute_rec_prec_f1(count_r, sum_r, count_p, sum_p):
+    """eval_depth_edges.py:147-161."""
+    rec = count_r / (sum_r + (sum_r == 0))
+    prec = count_p / (sum_p + (sum_p == 0))
+    f1_denom = (prec + rec + ((prec + rec) == 0))
+    f1 = 2.0 * prec * rec / f1_denom
+    return rec, prec, f1
+
+
+def mean_recall_at_precision_range(arr, small_lim=0.0, large_lim=1.0):
+    """eval_depth_edges.py:365-375."""
+    interp_x = np.array(range(int(small_lim * 100), int(large_lim * 100))) / 100
+    interp_y = np.interp(interp_x, arr[:, 0], arr[:, 1])
+    interp_y[interp_y < 0] = 0
+    interp_y[interp_y > 1] = 1
+    return np.mean(interp_y)
+
+
+def _dist_info():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def sweep_counts(depth: torch.Tensor, gt: torch.Tensor, edge_thresh_range, gt_crop, min_depth, max_depth,
+                 max_dist=0.002, out=None) -> torch.Tensor:
+    """Device part of ``pr_evaluation`` for a batch: depth [N,H,W] (already at GT size), gt [N,H,W]
+    uint8 -> int64[len(range),4].  Thresholds are swept strictest first internally (the level plane
+    needs nested pairs) and returned in the caller's order."""
+    order = np.argsort(-np.asarray(edge_thresh_range), kind="stable")
+    pairs = [(int(edge_thresh_range[i] / 2), int(edge_thresh_range[i])) for i in order]
+    levels = canny_from_depth(depth, pairs, min_depth, max_depth, want_edges=False, want_levels=True)
+    c = pr_counts(levels, gt, n_levels=len(pairs), max_dist=max_dist, crop=gt_crop)
+    inv = torch.from_numpy(np.argsort(order)).to(c.device)
+    c = c[inv]
+    if out is not None:
+        out += c
+        return out
+    return c
+
+
+def pr_evaluation_arrays(depths: Sequence[np.ndarray], gts: Sequence[np.ndarray], edge_thresh_range=None,
+                         gt_crop=(44, 1197, 153, 371), min_depth=0.0, max_depth=80.0, batch: int = 32):
+    """Array-level ``pr_evaluation``: predicted depth maps (any size; resized to the GT size on the
+    host with cv2.INTER_LINEAR as edge.py:76-78 does) and GT edge images (uint8, >127 = edge).
+    Images are sharded over ``torch.distributed`` ranks when initialised.
+    -> (precision_vec, recall_vec, counts int64[T,4])"""
+    import cv2
+    if edge_thresh_range is None:
+        edge_thresh_range = list(range(20, 241, 20))
+    rank, world = _dist_info()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    counts = torch.zeros((len(edge_thresh_range), 4), dtype=torch.int64, device=dev)
+    mine = list(range(rank, len(depths), world))
+    # group by GT shape and depth dtype so every launch is a dense batch; the quantisation runs in the
+    # array's own float type (edge.py:85-87), so float32 and float64 maps must not be mixed
+    by_shape = {}
+    for i in mine:
+        dt = np.float32 if np.asarray(depths[i]).dtype == np.float32 else np.float64
+        by_shape.setdefault((tuple(gts[i].shape[:2]), dt), []).append(i)
+    for ((H, W), dtype), idx in by_shape.items():
+        for s in range(0, len(idx), batch):
+            chunk = idx[s:s + batch]
+            dep = []
+            for i in chunk:
+                d = np.asarray(depths[i])
+                if d.shape != (H, W):
+                    d = cv2.resize(d, (W, H), interpolation=cv2.INTER_LINEAR)
+                dep.append(d)
+            d_dev = torch.from_numpy(np.stack([d.astype(dtype, copy=False) for d in dep])).to(dev, non_blocking=True)
+            # _pred_eval: value/255 > 0.5 -> edge (eval_depth_edges.py:202-205)
+            g_dev = torch.from_numpy(np.stack([(np.asarray(gts[i]) > 127).astype(np.uint8) for i in chunk])).to(
+                dev, non_blocking=True)
+            sweep_counts(d_dev, g_dev, edge_thresh_range, gt_crop, min_depth, max_depth, out=counts)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    c = counts.cpu().numpy().astype(np.float64)
+    rec, prec, _ = compute_rec_prec_f1(c[:, 0], c[:, 1], c[:, 2], c[:, 3])
+    return [float(p) for p in prec], [float(r) for r in rec], counts
+
+
+def pr_evaluation(edge_list, pred_list, edge_thresh_range=None, gt_crop=[44, 1197, 153, 371], min_depth=0.0,
+                  max_depth=80.0, save_folder="temp_output", num_workers=4):
+    """Drop-in for eval_depth_edges.py:232-348 -> (precision_vec, recall_vec).
+    ``save_folder`` and ``num_workers`` are accepted for signature compatibility; nothing is
+    written to disk and no process pool is forked."""
+    import cv2
+    depth_pred_list, edge_gt_list = list(pred_list), list(edge_list)
+    if len(edge_gt_list) > len(depth_pred_list):  # multiscale GT list: keep the first entry of each group (:255-258)
+        ratio = len(edge_gt_list) / len(depth_pred_list)
+        edge_gt_list = edge_gt_list[0:len(edge_gt_list):int(ratio)]
+    gts = [cv2.imread(p.split("\n")[0])[:, :, 0] for p in edge_gt_list]
+    depths = [read_depth_file(p.split("\n")[0]) for p in depth_pred_list]
+    prec, rec, _ = pr_evaluation_arrays(depths, gts, edge_thresh_range, gt_crop, min_depth, max_depth)
+    return prec, rec

@@ -1,0 +1,137 @@
+"""PR-count parity: the GPU matcher / counts against goldens produced by the reference
+``eval_depth_edges.py`` (run with the oracle stand-in for py-bsds500) and against the C oracle."""
+import os
+import tempfile
+
+import cv2
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from synth import random_boundary_maps, scene_with_gt
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("shape,max_dist", [((60, 90), 0.0075), ((218, 1153), 0.002), ((40, 40), 0.05),
+                                            ((100, 300), 0.0075), ((218, 1153), 0.0075), ((30, 200), 0.002),
+                                            ((1, 1), 0.5), ((3, 50), 0.1)])
+def test_matcher_vs_oracle(shape, max_dist):
+    from mindtheedge_b200.eval_depth_edges import correspond_pixels_batch
+    from oracle import pr_counts as opr
+    h, w = shape
+    preds, gts = zip(*[random_boundary_maps(h, w, 10 * h + k) for k in range(5)])
+    a = torch.from_numpy(np.stack(preds)).cuda()
+    b = torch.from_numpy(np.stack(gts)).cuda()
+    ma, mb, cnt = correspond_pixels_batch(a, b, max_dist)
+    ma, mb, cnt = ma.cpu().numpy(), mb.cpu().numpy(), cnt.cpu().numpy()
+    for k in range(5):
+        ref = opr.match_count(preds[k], gts[k], max_dist)
+        assert cnt[k] == ref, (k, cnt[k], ref)
+        assert ma[k].sum() == ref and mb[k].sum() == ref
+        assert not (ma[k] & ~(preds[k] != 0)).any() and not (mb[k] & ~(gts[k] != 0)).any()
+
+
+def test_matcher_worst_cases():
+    """Dense blobs (every pixel set) and a long two-chain component (long augmenting paths)."""
+    from mindtheedge_b200.eval_depth_edges import correspond_pixels_batch
+    from oracle import pr_counts as opr
+    h, w = 64, 256
+    a = np.zeros((3, h, w), np.uint8)
+    b = np.zeros((3, h, w), np.uint8)
+    a[0, 10:40, 20:120] = 1
+    b[0, 12:45, 30:100] = 1
+    a[1, 30, 5:250] = 1          # one pred chain, GT chain shifted so the greedy start is sub-optimal
+    b[1, 31, 4:249] = 1
+    b[1, 29, 100:140] = 1
+    r = np.random.default_rng(0)
+    a[2] = r.random((h, w)) < 0.3
+    b[2] = r.random((h, w)) < 0.3
+    _, _, cnt = correspond_pixels_batch(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), 0.008)
+    for k in range(3):
+        assert cnt[k].item() == opr.match_count(a[k], b[k], 0.008) == opr.match_count_scipy(a[k], b[k], 0.008)
+
+
+def test_golden_evaluate_boundaries():
+    from mindtheedge_b200.eval_depth_edges import evaluate_boundaries
+    z = np.load(os.path.join(GOLDEN, "pr.npz"))
+    for thin_flag in (0, 1):
+        c_r, s_r, c_p, s_p, thr = evaluate_boundaries(z["soft"], [z["soft_gt"].astype(np.float64)], thresholds=9,
+                                                      max_dist=0.0075, apply_thinning=bool(thin_flag))
+        got = np.stack([c_r, s_r, c_p, s_p], 1).astype(np.int64)
+        assert np.array_equal(got, z[f"soft_counts_thin{thin_flag}"]), thin_flag
+        assert np.array_equal(thr, z["soft_thr"])
+
+
+def test_golden_pr_evaluation_files():
+    """The file-level drop-in against precision/recall/AUC produced by the reference pr_evaluation."""
+    from mindtheedge_b200.eval_depth_edges import mean_recall_at_precision_range, pr_evaluation
+    z = np.load(os.path.join(GOLDEN, "pr.npz"))
+    H, W = z["pr_shape"]
+    with tempfile.TemporaryDirectory() as tmp:
+        gts, preds = [], []
+        for i in range(3):
+            g = np.unpackbits(z[f"pr_gt{i}"])[: H * W].reshape(H, W)
+            gp = os.path.join(tmp, f"gt{i}.png")
+            cv2.imwrite(gp, g.astype(np.uint8) * 255)
+            dp = os.path.join(tmp, f"pred{i}.npy")
+            np.save(dp, (z[f"pr_depth_u16_{i}"] / 256).astype(np.float32))
+            gts.append(gp)
+            preds.append(dp)
+        pv, rv = pr_evaluation(gts, preds, edge_thresh_range=[int(v) for v in z["pr_range"]],
+                               gt_crop=[int(v) for v in z["pr_crop"]], save_folder=os.path.join(tmp, "o"))
+    assert np.array_equal(np.array(pv), z["pr_precision"])
+    assert np.array_equal(np.array(rv), z["pr_recall"])
+    pr = np.vstack((pv, rv)).transpose()
+    assert mean_recall_at_precision_range(pr) == z["pr_auc_full"]
+    assert mean_recall_at_precision_range(pr, 0.12, 0.65) == z["pr_auc_part"]
+
+
+def test_kitti_size_sweep_vs_oracle():
+    """Config 2 shape: 384x1280 planes, 12 Canny settings, KITTI crop, max_dist 0.002 -- bit-exact counts."""
+    from mindtheedge_b200.eval_depth_edges import pr_evaluation_arrays
+    from oracle import pr_counts as opr
+    gts, depths = zip(*[scene_with_gt(384, 1280, 100 + k) for k in range(4)])
+    pv, rv, counts = pr_evaluation_arrays(depths, gts)
+    ref = opr.pr_sweep_counts(depths, gts)
+    assert np.array_equal(counts.cpu().numpy(), ref)
+    assert ref[:, 0].min() > 1000  # the matcher has real work
+
+
+def test_ddad_size_uncropped_property():
+    """Config 5 shape (1216x1936, no crop, radius 4.57 px).  Size-independent properties: counts are
+    bounded by both sides, monotone in the threshold, and an identical pred/GT pair matches fully."""
+    from mindtheedge_b200.eval_depth_edges import correspond_pixels_batch, sweep_counts
+    gt, depth = scene_with_gt(1216, 1936, 5, n_rect=120)
+    d = torch.from_numpy(depth)[None].cuda()
+    g = torch.from_numpy((gt > 127).astype(np.uint8))[None].cuda()
+    rng = list(range(20, 241, 20))
+    c = sweep_counts(d, g, rng, None, 0.0, 80.0, max_dist=0.002).cpu().numpy()
+    assert (c[:, 0] == c[:, 2]).all() and (c[:, 0] <= c[:, 1]).all() and (c[:, 0] <= c[:, 3]).all()
+    assert (np.diff(c[:, 3]) <= 0).all() and (np.diff(c[:, 0]) <= 0).all()  # higher threshold -> fewer edges
+    assert (c[:, 1] == int((gt > 127).sum())).all()
+    _, _, cnt = correspond_pixels_batch(g, g, 0.002, want_maps=False)
+    assert cnt.item() == int((gt > 127).sum())
+
+
+def test_thin_vs_oracle():
+    from mindtheedge_b200.bsds import thin
+    from oracle import thin as othin
+    r = np.random.default_rng(1)
+    for shape, dens in [((50, 80), 0.4), ((218, 1153), 0.1), ((7, 7), 0.9), ((1, 5), 1.0), ((64, 64), 1.0)]:
+        x = r.random(shape) < dens
+        x[: shape[0] // 2, : shape[1] // 3] = True  # a thick blob needs several iterations
+        assert np.array_equal(thin.binary_thin(x), othin.binary_thin(x)), shape
+        assert np.array_equal(thin.binary_thin(x, max_iter=1), othin.binary_thin(x, max_iter=1))
+
+
+def test_unmodified_reference_script_seam():
+    """The bsds stand-in has the module layout and call signatures eval_depth_edges.py:7,50,125 expect."""
+    from mindtheedge_b200 import bsds
+    bsds.install_as_bsds_metric()
+    from bsds_metric.bsds import correspond_pixels, thin  # noqa: F401  (the reference's import line)
+    pred, gt = random_boundary_maps(80, 120, 3)
+    m1, m2, cost, oc = correspond_pixels.correspond_pixels(pred.astype(bool), gt.astype(np.float64), max_dist=0.0075)
+    assert m1.shape == pred.shape and (m1 > 0).sum() == (m2 > 0).sum() > 0
+    assert thin.binary_thin(pred.astype(bool)).dtype == bool
