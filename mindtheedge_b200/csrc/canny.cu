@@ -239,6 +239,30 @@ static Layout layout(int N, int H, int W) {
     return L;
 }
 
+// Shared with the DEE post-process (dee.cu): relax E towards cl over 8-connected paths.
+int run_level_hysteresis(const unsigned char *cl, unsigned char *E, int N, int H, int W, unsigned char *active,
+                         unsigned int *counters, cudaStream_t st) {
+    HystP P;
+    P.cl = cl; P.E = E; P.N = N; P.H = H; P.W = W;
+    P.tilesX = ceil_div(W, TW); P.tilesY = ceil_div(H, TH); P.nTiles = P.tilesX * P.tilesY * N;
+    P.active = active;
+    P.counters = counters;
+    int dev = 0, sms = kNumSMs, perSm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, canny_hyst_kernel, kThreads, 0);
+    int grid = sms * (perSm < 1 ? 1 : perSm);
+    if (grid > P.nTiles) grid = P.nTiles;
+    cudaError_t e = cudaMemsetAsync(P.active, 0, (size_t)2 * P.nTiles, st);
+    if (e != cudaSuccess) return (int)e;
+    void *args[] = {&P};
+    e = cudaLaunchCooperativeKernel((const void *)canny_hyst_kernel, dim3(grid), dim3(kThreads), args, 0, st);
+    return e == cudaSuccess ? MTE_OK : (int)e;
+}
+size_t hysteresis_active_bytes(int N, int H, int W) {
+    return align_up((size_t)2 * ceil_div(W, TW) * ceil_div(H, TH) * N, 256);
+}
+
 static int run_pairs(const void *depth, int dtype, int N, int H, int W, double min_depth, double max_depth,
                      const Thresholds &thr, unsigned char *edges, unsigned char *levels, char *ws, const Layout &L,
                      cudaStream_t st) {
@@ -257,22 +281,10 @@ static int run_pairs(const void *depth, int dtype, int N, int H, int W, double m
                                                                    0, 0, 0, thr, cl, E);
     MTE_RETURN_IF_CUDA_ERROR();
 
-    HystP P;
-    P.cl = cl; P.E = E; P.N = N; P.H = H; P.W = W;
-    P.tilesX = L.tilesX; P.tilesY = L.tilesY; P.nTiles = L.nTiles;
-    P.active = reinterpret_cast<unsigned char *>(ws + L.offActive);
-    P.counters = reinterpret_cast<WsHeader *>(ws)->flag;
-    int dev = 0, sms = kNumSMs, perSm = 1;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, canny_hyst_kernel, kThreads, 0);
-    int grid2 = sms * (perSm < 1 ? 1 : perSm);
-    if (grid2 > L.nTiles) grid2 = L.nTiles;
-    cudaError_t e = cudaMemsetAsync(P.active, 0, (size_t)2 * L.nTiles, st);
-    if (e != cudaSuccess) return (int)e;
-    void *args[] = {&P};
-    e = cudaLaunchCooperativeKernel((const void *)canny_hyst_kernel, dim3(grid2), dim3(kThreads), args, 0, st);
-    if (e != cudaSuccess) return (int)e;
+    int rc = run_level_hysteresis(cl, E, N, H, W, reinterpret_cast<unsigned char *>(ws + L.offActive),
+                                  reinterpret_cast<WsHeader *>(ws)->flag, st);
+    if (rc) return rc;
+    int sms = kNumSMs;
     if (edges) {
         const size_t n = (size_t)N * H * W;
         const int g = (int)((n + 255) / 256 < (size_t)sms * 16 ? (n + 255) / 256 : (size_t)sms * 16);

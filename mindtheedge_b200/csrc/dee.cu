@@ -1,0 +1,277 @@
+// DEE annotation post-process for sm_100a: edge normals, non-maximum suppression, hysteresis.
+//
+// Replaces (reference root relative):
+//   normals block         infer_edge_estimation.py:193-199 (= :244-250)
+//   non_max_suppression   packnet_code/packnet_sfm/utils/tools.py:9-46
+//   hysteresis + DFS      packnet_code/packnet_sfm/utils/tools.py:49-92
+// and the third-party cv2.Sobel(img, CV_64F, dx, dy, ksize=5) they call: separable
+// [1,4,6,4,1] x [-1,-2,0,2,1], BORDER_REFLECT_101, row pass first, fp64 accumulation in tap order, the
+// column pass folded symmetrically / anti-symmetrically.  Every fp64 operation below is an explicit
+// __dmul_rn / __dadd_rn in exactly that order (no FMA contraction), so the Sobel responses are
+// bit-identical to OpenCV's and the orientation bins / uint8 normals follow.
+//
+// Kernels:  dee_front_kernel  (Sobel5 + normals + NMS + hysteresis labels, shared-memory halo tile)
+//           canny::run_level_hysteresis (shared 8-connected relaxation, one cooperative launch)
+//           dee_finish_kernel (img * labels / max(labels), the reference's normalisation quirk included)
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace mte {
+namespace dee {
+
+constexpr int TW = 64, TH = 16, kThreads = 256;
+
+struct ImgStat {
+    unsigned long long borderMaxKey;  // order-preserving key of the largest non-NaN border value
+    unsigned int anyStrong;           // a strong interior pixel exists (=> max(labels) >= 2)
+    unsigned int borderNaN;           // np.max propagates NaN
+};
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    const int period = 2 * (n - 1);
+    i %= period;
+    if (i < 0) i += period;
+    return i >= n ? period - i : i;
+}
+
+__device__ __forceinline__ unsigned long long dkey(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ inline double dkey_inv(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)b);
+#else
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+#endif
+}
+
+// T = type of the input map (the reference passes float32 network outputs; float64 accepted)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) dee_front_kernel(const T *__restrict__ img, int N, int H, int W, int doNms,
+                                                             int doHyst, double tLow, double tHigh,
+                                                             unsigned char *__restrict__ normals,
+                                                             T *__restrict__ nmsOut, unsigned char *__restrict__ cl,
+                                                             unsigned char *__restrict__ E, ImgStat *stats) {
+    __shared__ double s[TH + 4][TW + 4];
+    __shared__ double rowD[TH + 4][TW];  // row pass with the derivative taps  (-> sobel x)
+    __shared__ double rowS[TH + 4][TW];  // row pass with the smoothing taps   (-> sobel y)
+    const int tilesX = ceil_div(W, TW), tilesY = ceil_div(H, TH);
+    const int tile = blockIdx.x % (tilesX * tilesY), im = blockIdx.x / (tilesX * tilesY);
+    const int x0 = (tile % tilesX) * TW, y0 = (tile / tilesX) * TH;
+    const T *src = img + (size_t)im * H * W;
+    const bool needSobel = (normals != nullptr) || doNms;
+
+    for (int i = threadIdx.x; i < (TH + 4) * (TW + 4); i += kThreads) {
+        const int r = i / (TW + 4), c = i - r * (TW + 4);
+        const int y = reflect101(y0 + r - 2, H), x = reflect101(x0 + c - 2, W);
+        s[r][c] = (double)src[(size_t)y * W + x];
+    }
+    __syncthreads();
+    if (needSobel) {
+        for (int i = threadIdx.x; i < (TH + 4) * TW; i += kThreads) {
+            const int r = i / TW, c = i - r * TW;
+            const double a0 = s[r][c], a1 = s[r][c + 1], a2 = s[r][c + 2], a3 = s[r][c + 3], a4 = s[r][c + 4];
+            double d = __dmul_rn(-1.0, a0);
+            d = __dadd_rn(d, __dmul_rn(-2.0, a1));
+            d = __dadd_rn(d, __dmul_rn(0.0, a2));
+            d = __dadd_rn(d, __dmul_rn(2.0, a3));
+            d = __dadd_rn(d, __dmul_rn(1.0, a4));
+            double m = __dmul_rn(1.0, a0);
+            m = __dadd_rn(m, __dmul_rn(4.0, a1));
+            m = __dadd_rn(m, __dmul_rn(6.0, a2));
+            m = __dadd_rn(m, __dmul_rn(4.0, a3));
+            m = __dadd_rn(m, __dmul_rn(1.0, a4));
+            rowD[r][c] = d;
+            rowS[r][c] = m;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < TH * TW; i += kThreads) {
+        const int r = i / TW, c = i - r * TW;
+        const int y = y0 + r, x = x0 + c;
+        if (y >= H || x >= W) continue;
+        const size_t o = (size_t)im * H * W + (size_t)y * W + x;
+        const T v = src[(size_t)y * W + x];
+        double sx = 0.0, sy = 0.0;
+        if (needSobel) {
+            // symmetric column pass on the derivative rows, anti-symmetric on the smoothed rows
+            sx = __dmul_rn(6.0, rowD[r + 2][c]);
+            sx = __dadd_rn(sx, __dmul_rn(4.0, __dadd_rn(rowD[r + 3][c], rowD[r + 1][c])));
+            sx = __dadd_rn(sx, __dmul_rn(1.0, __dadd_rn(rowD[r + 4][c], rowD[r][c])));
+            sy = __dmul_rn(2.0, __dsub_rn(rowS[r + 3][c], rowS[r + 1][c]));
+            sy = __dadd_rn(sy, __dmul_rn(1.0, __dsub_rn(rowS[r + 4][c], rowS[r][c])));
+        }
+        if (normals) {
+            const double ang = atan2(-sy, sx);
+            const double u = __dmul_rn(__ddiv_rn(__dadd_rn(__dmul_rn(ang, 180.0 / M_PI), 180.0), 360.0), 255.0);
+            normals[o] = (unsigned char)(int)u;
+        }
+        const bool interior = y >= 1 && y < H - 1 && x >= 1 && x < W - 1;
+        T keep = v;
+        if (doNms) {
+            keep = (T)0;
+            if (interior) {
+                double a = __dmul_rn(atan2(sy, sx), 180.0 / M_PI);
+                if (a < 0.0) a = __dadd_rn(a, 180.0);
+                T q = (T)1, rr = (T)1;  // tools.py:22-23: no bin (NaN angle) compares against 1
+                const int cr = r + 2, cc = c + 2;
+                if ((0.0 <= a && a < 22.5) || (157.5 <= a && a <= 180.0)) {
+                    q = (T)s[cr][cc + 1]; rr = (T)s[cr][cc - 1];
+                } else if (22.5 <= a && a < 67.5) {
+                    q = (T)s[cr - 1][cc - 1]; rr = (T)s[cr + 1][cc + 1];
+                } else if (67.5 <= a && a < 112.5) {
+                    q = (T)s[cr + 1][cc]; rr = (T)s[cr - 1][cc];
+                } else if (112.5 <= a && a < 157.5) {
+                    q = (T)s[cr + 1][cc - 1]; rr = (T)s[cr - 1][cc + 1];
+                }
+                if (v >= q && v >= rr) keep = v;
+            }
+        }
+        if (nmsOut) nmsOut[o] = keep;
+        if (doHyst) {
+            unsigned char c_l = 255, e_l = 255;
+            const double kv = (double)keep;
+            if (interior) {
+                if (kv > tHigh) { c_l = 0; e_l = 0; }
+                else if (!(kv < tLow)) c_l = 0;
+                if (e_l == 0) atomicOr(&stats[im].anyStrong, 1u);
+            } else {
+                // border pixels keep their raw value as "label" (tools.py:54-55 never touches them)
+                if (kv != kv) atomicOr(&stats[im].borderNaN, 1u);
+                else atomicMax(&stats[im].borderMaxKey, dkey(kv));
+            }
+            cl[o] = c_l;
+            E[o] = e_l;
+        }
+    }
+}
+
+// out = img * (labels / max(labels))  in the dtype the reference computes in (C = float or double)
+template <typename T, typename C, typename O>
+__global__ void dee_finish_kernel(const T *__restrict__ val, const unsigned char *__restrict__ E, int N, int H, int W,
+                                  const ImgStat *__restrict__ stats, O *__restrict__ out) {
+    const size_t plane = (size_t)H * W, n = plane * N;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int im = (int)(i / plane);
+        const size_t j = i - (size_t)im * plane;
+        const int y = (int)(j / W), x = (int)(j - (size_t)y * W);
+        const ImgStat st = stats[im];
+        // np.max over {0, 2 at kept pixels, raw border values}; NaN wins
+        double mx = (H > 2 && W > 2) ? 0.0 : -INFINITY;
+        if (st.anyStrong) mx = 2.0;
+        if (st.borderMaxKey != 0ull) { const double b = dkey_inv(st.borderMaxKey); mx = b > mx ? b : mx; }
+        if (st.borderNaN) mx = NAN;
+        const bool interior = y >= 1 && y < H - 1 && x >= 1 && x < W - 1;
+        const C v = (C)val[i];
+        const C label = interior ? (E[i] == 0 ? (C)2 : (C)0) : v;
+        const C norm = label / (C)mx;
+        out[i] = (O)(v * norm);
+    }
+}
+
+template <typename T, typename O>
+__global__ void dee_convert_kernel(const T *__restrict__ in, O *__restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (O)in[i];
+}
+
+struct Layout {
+    size_t offStats, offVal, offCl, offE, offActive, total;
+};
+
+static Layout layout(int N, int H, int W) {
+    Layout L;
+    size_t off = MTE_WS_HEADER_BYTES;
+    L.offStats = off; off += align_up(sizeof(ImgStat) * (size_t)N, 256);
+    L.offVal = off; off += align_up((size_t)N * H * W * sizeof(double), 256);
+    L.offCl = off; off += align_up((size_t)N * H * W, 256);
+    L.offE = off; off += align_up((size_t)N * H * W, 256);
+    L.offActive = off; off += canny::hysteresis_active_bytes(N, H, W);
+    L.total = off;
+    return L;
+}
+
+template <typename T>
+static int run(const T *prob, int N, int H, int W, int do_nms, int do_hyst, double t_low, double t_high,
+               unsigned char *normals, void *out, int out_dtype, char *ws, const Layout &L, cudaStream_t st) {
+    ImgStat *stats = reinterpret_cast<ImgStat *>(ws + L.offStats);
+    T *val = reinterpret_cast<T *>(ws + L.offVal);
+    unsigned char *cl = reinterpret_cast<unsigned char *>(ws + L.offCl);
+    unsigned char *E = reinterpret_cast<unsigned char *>(ws + L.offE);
+    const int tiles = ceil_div(W, TW) * ceil_div(H, TH) * N;
+    cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(ImgStat) * (size_t)N, st);
+    if (e != cudaSuccess) return (int)e;
+    // fp32 inputs are compared against fp32-rounded thresholds when no NMS ran (NumPy weak-scalar promotion:
+    // tools.py:58-61 then sees a float32 array); after NMS the array is float64
+    double lo = t_low, hi = t_high;
+    if (!do_nms && sizeof(T) == 4) { lo = (double)(float)t_low; hi = (double)(float)t_high; }
+    const bool wantVal = out != nullptr;
+    T *nmsDst = wantVal ? val : nullptr;
+    // NMS only, fp32 out of fp32 in (or fp64/fp64): write straight to the output
+    if (wantVal && !do_hyst && ((out_dtype == MTE_F32 && sizeof(T) == 4) || (out_dtype == MTE_F64 && sizeof(T) == 8)))
+        nmsDst = static_cast<T *>(out);
+    dee_front_kernel<T><<<tiles, kThreads, 0, st>>>(prob, N, H, W, do_nms, do_hyst && wantVal, lo, hi, normals, nmsDst,
+                                                    cl, E, stats);
+    MTE_RETURN_IF_CUDA_ERROR();
+    if (!wantVal) return MTE_OK;
+    const size_t n = (size_t)N * H * W;
+    const int grid = (int)((n + 255) / 256 < (size_t)kNumSMs * 16 ? (n + 255) / 256 : (size_t)kNumSMs * 16);
+    if (do_hyst) {
+        int rc = canny::run_level_hysteresis(cl, E, N, H, W, reinterpret_cast<unsigned char *>(ws + L.offActive),
+                                             reinterpret_cast<WsHeader *>(ws)->flag + 2, st);
+        if (rc) return rc;
+        // the reference computes in float64 once NMS has run (its output array is float64), else in the input type
+        const bool c64 = do_nms || sizeof(T) == 8;
+        if (out_dtype == MTE_F64) {
+            if (c64) dee_finish_kernel<T, double, double><<<grid, 256, 0, st>>>(val, E, N, H, W, stats, (double *)out);
+            else dee_finish_kernel<T, float, double><<<grid, 256, 0, st>>>(val, E, N, H, W, stats, (double *)out);
+        } else {
+            if (c64) dee_finish_kernel<T, double, float><<<grid, 256, 0, st>>>(val, E, N, H, W, stats, (float *)out);
+            else dee_finish_kernel<T, float, float><<<grid, 256, 0, st>>>(val, E, N, H, W, stats, (float *)out);
+        }
+        MTE_RETURN_IF_CUDA_ERROR();
+    } else if (nmsDst == val) {
+        // NMS only: the reference returns float64 whatever the input type (tools.py:15 np.zeros((H, W)))
+        if (out_dtype == MTE_F64) dee_convert_kernel<T, double><<<grid, 256, 0, st>>>(val, (double *)out, n);
+        else dee_convert_kernel<T, float><<<grid, 256, 0, st>>>(val, (float *)out, n);
+        MTE_RETURN_IF_CUDA_ERROR();
+    }
+    return MTE_OK;
+}
+
+}  // namespace dee
+}  // namespace mte
+
+using namespace mte;
+
+extern "C" size_t mte_dee_workspace_bytes(int N, int H, int W) {
+    if (N < 1 || H < 1 || W < 1) return 0;
+    return dee::layout(N, H, W).total;
+}
+
+extern "C" int mte_dee_postprocess(const void *prob, int in_dtype, int N, int H, int W, int do_nms, int do_hyst,
+                                   double t_low, double t_high, uint8_t *normals_out, void *edges_out, int out_dtype,
+                                   void *workspace, size_t ws_bytes, mte_stream_t stream) {
+    if (!prob || !workspace) return MTE_ERR_NULL;
+    if (!normals_out && !edges_out) return MTE_ERR_NULL;
+    if (N < 1 || H < 1 || W < 1) return MTE_ERR_SHAPE;
+    if (in_dtype != MTE_F32 && in_dtype != MTE_F64) return MTE_ERR_ARG;
+    if (edges_out && out_dtype != MTE_F32 && out_dtype != MTE_F64) return MTE_ERR_ARG;
+    if (edges_out && !do_nms && !do_hyst) return MTE_ERR_ARG;
+    const dee::Layout L = dee::layout(N, H, W);
+    if (ws_bytes < L.total) return MTE_ERR_WORKSPACE;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    char *ws = static_cast<char *>(workspace);
+    if (in_dtype == MTE_F32)
+        return dee::run<float>(static_cast<const float *>(prob), N, H, W, do_nms, do_hyst, t_low, t_high, normals_out,
+                               edges_out, out_dtype, ws, L, st);
+    return dee::run<double>(static_cast<const double *>(prob), N, H, W, do_nms, do_hyst, t_low, t_high, normals_out,
+                            edges_out, out_dtype, ws, L, st);
+}
