@@ -1,0 +1,516 @@
+#!/usr/bin/env python
+"""Benchmark of the MindTheEdge depth-edge hot path on B200 (the driver's contract).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl mte|reference] [--workload loss|auc]
+
+One JSON line on stdout (rank 0).  Headline workload (BASELINE.json metric "edge-loss fwd+bwd ...
+Mpixel/s", config 3's loss shape): per GPU a batch of 8 images x the 4-scale pyramid
+(384x1280 ... 48x160, fp32, DEE normals, no mask, inv2depth fused) -> 5.22 Mpixel per step; a
+"step" is one forward + one backward of the edge loss.  The same line carries the second half of
+the metric, the KITTI-DE AUC evaluation (config 2 wiring: 102 images x 12 Canny settings x
+matcher), under "auc_eval".  `--workload auc` makes the AUC evaluation the headline instead.
+
+value      device-timed (CUDA events, max over ranks), inputs resident in HBM, steps rotate over
+           input sets larger than L2, each step replayed from a CUDA graph (the loss is 2 launches);
+e2e        the same metric through the public torch API with HOST buffers: pinned H2D of the
+           step's inputs and D2H of the loss inside the timed region;
+roofline   algorithmic bytes (32 B/px) / measured step time vs MEASURED_PEAKS.json;
+cpu_baseline  the oracle port (same op chain as the reference, torch CPU, all host threads) on a
+           bounded sample, timed in the same run.
+`--impl reference` times that CPU port alone (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+H0, W0, SCALES, B_PER_GPU = 384, 1280, 4, 8
+LOSS_BYTES_PER_PX = 32.0   # fwd 16 (depth+edge+normal in, grad map out) + bwd 16 (recompute in, grad out)
+AUC_BYTES_PER_PX = 7.0     # per (image, threshold): extraction 5 + counts 2
+KITTI_N, KITTI_T = 102, 12
+KITTI_CROP = [44, 1197, 153, 371]
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def recorded_traffic(kind):
+    """Per-launch DRAM bytes of the dominant kernels from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get(kind)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# synthetic inputs
+# ---------------------------------------------------------------------------
+def loss_inputs(B, seed, device, pinned=False):
+    """inverse depth, soft edges, u8-decoded normals at the 4 pyramid sizes."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    out = []
+    for s in range(SCALES):
+        h, w = H0 >> s, W0 >> s
+        depth = torch.rand(B, 1, h, w, generator=g) * 79 + 1
+        inv = 1.0 / depth
+        u = torch.rand(B, 1, h, w, generator=g)
+        edge = (u < 0.015).float() * torch.rand(B, 1, h, w, generator=g).clamp(min=0.3)
+        k = torch.randint(0, 256, (B, 1, h, w), generator=g).float()
+        normal = ((360 * k / 255 - 180) * np.pi / 180).float()
+        out.append((inv, edge, normal))
+    if device is not None:
+        return [tuple(t.to(device) for t in sc) for sc in out]
+    if pinned:
+        return [tuple(t.pin_memory() for t in sc) for sc in out]
+    return out
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(ms, world, device):
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return ms
+
+
+# ---------------------------------------------------------------------------
+# edge loss
+# ---------------------------------------------------------------------------
+def bench_loss(args, rank, world, device):
+    import ctypes as C
+    from mindtheedge_b200 import _lib, runtime
+    from mindtheedge_b200.losses import _attrs, _scales_struct, multiscale_edge_loss
+
+    px_per_step = sum(B_PER_GPU * (H0 >> s) * (W0 >> s) for s in range(SCALES))
+    set_bytes = px_per_step * 20  # 3 input planes + 2 output planes, fp32
+    n_sets = max(3, int(np.ceil(400e6 / set_bytes)))  # working set >= 400 MB > 126 MB of L2
+    sets = [loss_inputs(B_PER_GPU, 1000 * rank + i, device) for i in range(n_sets)]
+    weights = [1.0 / SCALES] * SCALES
+    at = _attrs(True, True, True, 4.0, 10.0, 1.0)
+    stream = torch.cuda.Stream(device)
+    graphs, keep = [], []
+    with torch.cuda.stream(stream):
+        st = stream.cuda_stream
+        for sc in sets:
+            pred = [t[0] for t in sc]; edge = [t[1] for t in sc]; normal = [t[2] for t in sc]
+            gmap = [torch.empty_like(e) for e in edge]
+            gpred = [torch.empty_like(p) for p in pred]
+            f = _scales_struct(pred, edge, normal, None, gmap, None, weights)
+            b = _scales_struct(pred, edge, normal, None, None, gpred, weights)
+            losses = torch.zeros(1 + SCALES, device=device)
+            ctx = torch.zeros(_lib.lib.mte_edge_loss_ctx_bytes(f, SCALES) // 4, device=device)
+            ws = torch.zeros(_lib.lib.mte_edge_loss_workspace_bytes(f, SCALES), dtype=torch.uint8, device=device)
+            gl = torch.zeros(1 + SCALES, device=device); gl[0] = 1.0
+            keep.append((f, b, gmap, gpred, losses, ctx, ws, gl))
+
+            def step(f=f, b=b, losses=losses, ctx=ctx, ws=ws, gl=gl):
+                _lib.check(_lib.lib.mte_edge_loss_fwd(f, SCALES, C.byref(at), losses.data_ptr(), ctx.data_ptr(),
+                                                      ws.data_ptr(), ws.numel(), st))
+                _lib.check(_lib.lib.mte_edge_loss_bwd(b, SCALES, C.byref(at), gl.data_ptr(), ctx.data_ptr(),
+                                                      ws.data_ptr(), ws.numel(), st))
+            step()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                step()
+            graphs.append(g)
+        for i in range(args.warmup):
+            graphs[i % n_sets].replay()
+        barrier(world)
+        sampler = ClockSampler(torch.cuda.current_device())
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.steps):
+            graphs[(args.warmup + i) % n_sets].replay()
+        e1.record(stream)
+        barrier(world)
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(ms, world, device)
+    ms_per_step = ms / args.steps
+    value = world * px_per_step / (ms_per_step * 1e-3) / 1e6
+
+    # per-kernel split (same stream, CUDA events around each launch of one replayed step, ungraphed)
+    with torch.cuda.stream(stream):
+        f, b, gmap, gpred, losses, ctx, ws, gl = keep[0]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        tf = tb = 0.0
+        reps = 10
+        for r in range(reps):
+            f, b, gmap, gpred, losses, ctx, ws, gl = keep[r % n_sets]
+            ev[0].record(stream)
+            _lib.check(_lib.lib.mte_edge_loss_fwd(f, SCALES, C.byref(at), losses.data_ptr(), ctx.data_ptr(),
+                                                  ws.data_ptr(), ws.numel(), stream.cuda_stream))
+            ev[1].record(stream)
+            _lib.check(_lib.lib.mte_edge_loss_bwd(b, SCALES, C.byref(at), gl.data_ptr(), ctx.data_ptr(),
+                                                  ws.data_ptr(), ws.numel(), stream.cuda_stream))
+            ev[2].record(stream)
+            torch.cuda.synchronize()
+            tf += ev[0].elapsed_time(ev[1]); tb += ev[1].elapsed_time(ev[2])
+        tf, tb = tf / reps, tb / reps
+
+    # end to end through the public API with host buffers
+    host = [loss_inputs(B_PER_GPU, 5000 + 1000 * rank + i, None, pinned=True) for i in range(2)]
+    h2d = sum(t.numel() * 4 for sc in host[0] for t in sc)
+    dev_bufs = [[tuple(torch.empty_like(t, device=device) for t in sc) for sc in host[0]] for _ in range(2)]
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        hb, db = host[i % 2], dev_bufs[i % 2]
+        for sc_h, sc_d in zip(hb, db):
+            for th, td in zip(sc_h, sc_d):
+                td.copy_(th, non_blocking=True)
+        inv = [sc[0].requires_grad_(True) for sc in db]
+        total, _, _ = multiscale_edge_loss(inv, [sc[1] for sc in db], None, [sc[2] for sc in db], weight=10.0,
+                                           pred_is_inverse=True)
+        total.backward()
+        loss_host.copy_(total.detach().reshape(1), non_blocking=True)
+        for t in inv:
+            t.grad = None
+            t.requires_grad_(False)
+
+    n_e2e = max(5, min(args.steps, 30))
+    for i in range(3):
+        e2e_step(i)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n_e2e):
+        e2e_step(i)
+    e1.record()
+    barrier(world)
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1), world, device) / n_e2e
+    e2e_value = world * px_per_step / (ms_e2e * 1e-3) / 1e6
+
+    peak, peak_src = measured_peak_gbs()
+    # roofline over the timed region itself: both kernels of a step, graph launch gaps included
+    achieved = LOSS_BYTES_PER_PX * px_per_step / (ms_per_step * 1e-3) / 1e9
+    out = {
+        "metric": "edge_loss_fwd_bwd_throughput", "value": round(value, 1), "unit": "Mpixel/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "edge loss fwd+bwd, batch 8/GPU x 4-scale pyramid 384x1280..48x160 fp32, DEE normals, "
+                               "no mask, inv2depth fused (BASELINE.json config 3 loss shape)",
+                   "pixels_per_step_per_gpu": px_per_step, "l2_policy": f"rotating {n_sets} input sets "
+                   f"({n_sets * set_bytes / 1e6:.0f} MB > L2)", "launch": "CUDA graph replay of 2 kernels/step",
+                   "parallelism": f"dp{world} (batch-sharded, no data-path collective in the loss)"},
+        "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": round(ms_e2e, 4), "api": "mindtheedge_b200.losses.multiscale_edge_loss + backward"},
+        "gpu_launches": 2 * args.steps,
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": recorded_traffic("edge_loss_fwd_bwd"),
+                     "kernel": "edge_loss_fwd_kernel + edge_loss_bwd_kernel",
+                     "fwd_us": round(tf * 1e3, 2), "bwd_us": round(tb * 1e3, 2),
+                     "algorithmic_bytes_per_px": LOSS_BYTES_PER_PX, "peak_source": peak_src},
+        "clocks": clocks,
+    }
+    return out
+
+
+def cpu_loss_baseline(B=4, scales=1, iters=5, warm=2):
+    """Oracle port of GradLoss fwd+bwd on the host cores (bounded sample)."""
+    from oracle.edge_loss import edge_loss_torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(0)
+    data = []
+    for s in range(scales):
+        h, w = H0 >> s, W0 >> s
+        inv = 1.0 / (torch.rand(B, 1, h, w, generator=g) * 79 + 1)
+        edge = (torch.rand(B, 1, h, w, generator=g) < 0.015).float() * torch.rand(B, 1, h, w, generator=g).clamp(min=0.3)
+        normal = ((360 * torch.randint(0, 256, (B, 1, h, w), generator=g).float() / 255 - 180) * np.pi / 180).float()
+        data.append((inv, edge, normal))
+    px = sum(B * (H0 >> s) * (W0 >> s) for s in range(scales))
+
+    def step():
+        total = 0
+        leaves = []
+        for inv, edge, normal in data:
+            x = inv.clone().requires_grad_(True)
+            leaves.append(x)
+            depth = 1.0 / x.clamp(min=1e-6)
+            l, _ = edge_loss_torch(depth, edge, None, True, True, 4, normal, weight=10.0)
+            total = total + l
+        (total / scales).backward()
+
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        step()
+    dt = (time.perf_counter() - t0) / iters
+    return px / dt / 1e6, dt, px
+
+
+# ---------------------------------------------------------------------------
+# AUC evaluation (KITTI-DE wiring)
+# ---------------------------------------------------------------------------
+def kitti_like_set(n, seed0):
+    from synth import scene_with_gt
+    gts, depths = zip(*[scene_with_gt(H0, W0, seed0 + i) for i in range(n)])
+    return np.stack(depths), np.stack([(g > 127).astype(np.uint8) for g in gts])
+
+
+def bench_auc(args, rank, world, device, steps=None, warmup=None):
+    from mindtheedge_b200.eval_depth_edges import compute_rec_prec_f1, mean_recall_at_precision_range, sweep_counts
+    steps = steps or args.steps
+    warmup = warmup if warmup is not None else args.warmup
+    rng = list(range(20, 241, 20))
+    # weak scaling: every rank evaluates its own shard of 102 images (image i of the job -> rank i mod R),
+    # counts are summed with one int64 all-reduce per evaluation
+    depths, gts = kitti_like_set(KITTI_N, 7000 + 1000 * rank)
+    d_dev, g_dev = torch.from_numpy(depths).to(device), torch.from_numpy(gts).to(device)
+    px_per_step = world * KITTI_N * KITTI_T * H0 * W0  # whole job
+
+    def step():
+        c = sweep_counts(d_dev, g_dev, rng, KITTI_CROP, 0.0, 80.0, max_dist=0.002)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        return c
+
+    for _ in range(warmup):
+        step()
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        c = step()
+    e1.record()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world, device) / steps
+    value = px_per_step / (ms * 1e-3) / 1e6
+
+    # e2e: host depth + GT in, P/R vectors + AUC out (the call a user of eval_depth_edges makes, minus file IO)
+    dh, gh = torch.from_numpy(depths).pin_memory(), torch.from_numpy(gts).pin_memory()
+    dd, gd = torch.empty_like(d_dev), torch.empty_like(g_dev)
+
+    def e2e_step():
+        dd.copy_(dh, non_blocking=True)
+        gd.copy_(gh, non_blocking=True)
+        cc = sweep_counts(dd, gd, rng, KITTI_CROP, 0.0, 80.0, max_dist=0.002)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(cc, op=dist.ReduceOp.SUM)
+        cn = cc.cpu().numpy().astype(np.float64)
+        rec, prec, _ = compute_rec_prec_f1(cn[:, 0], cn[:, 1], cn[:, 2], cn[:, 3])
+        return mean_recall_at_precision_range(np.vstack((prec, rec)).transpose())
+
+    e2e_step()
+    barrier(world)
+    n_e2e = max(2, min(steps, 5))
+    e0.record()
+    for _ in range(n_e2e):
+        auc = e2e_step()
+    e1.record()
+    barrier(world)
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1), world, device) / n_e2e
+    peak, peak_src = measured_peak_gbs()
+    achieved = AUC_BYTES_PER_PX * px_per_step / world / (ms * 1e-3) / 1e9
+    return {
+        "metric": "auc_eval_throughput", "value": round(value, 1), "unit": "Mpixel/s", "ms_per_step": round(ms, 4),
+        "steps": steps, "scaling": "weak",
+        "config": {"workload": "KITTI-DE depth-edge AUC eval (BASELINE.json config 2, shipped wiring): 102 synthetic images per GPU, "
+                               "384x1280 depth maps vs synthetic GT edges, 12 Canny settings (t/2,t) t=20..240, crop "
+                               "[153:371,44:1197], max_dist 0.002, exact matcher; pixel = image x threshold x H x W",
+                   "l2_policy": f"inputs {depths.nbytes / 1e6:.0f} MB + per-CTA matcher arenas > L2",
+                   "parallelism": f"images sharded over {world} rank(s) (102 each), one int64[12,4] all-reduce"},
+        "e2e": {"value": round(px_per_step / (ms_e2e * 1e-3) / 1e6, 1), "unit": "Mpixel/s",
+                "h2d_bytes_per_step": int(depths.nbytes + gts.nbytes), "d2h_bytes_per_step": 12 * 4 * 8,
+                "ms_per_step": round(ms_e2e, 3), "auc": round(float(auc), 6)},
+        "gpu_launches_per_step": 5,
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": recorded_traffic("auc_eval"),
+                     "kernel": "match_kernel (dominant) + canny_nms/hyst", "algorithmic_bytes_per_px": AUC_BYTES_PER_PX,
+                     "peak_source": peak_src,
+                     "note": "the matcher is latency-bound graph work in L2, not an HBM stream"},
+    }
+
+
+def cpu_auc_baseline(n_images=4):
+    from oracle import pr_counts as opr
+    depths, gts = kitti_like_set(n_images, 7000)
+    t0 = time.perf_counter()
+    opr.pr_sweep_counts(list(depths), [g * 255 for g in gts], gt_crop=tuple(KITTI_CROP))
+    dt = time.perf_counter() - t0
+    px = n_images * KITTI_T * H0 * W0
+    return px / dt / 1e6, dt, px
+
+
+# ---------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    if args.workload == "auc":
+        n = 2
+        vals = []
+        for _ in range(args.warmup and 1):
+            cpu_auc_baseline(1)
+        t0 = time.perf_counter()
+        for _ in range(max(1, min(args.steps, 5))):
+            v, dt, px = cpu_auc_baseline(n)
+            vals.append(v)
+        value = float(np.mean(vals))
+        line = {"metric": "auc_eval_throughput", "value": round(value, 3), "unit": "Mpixel/s", "impl": "reference",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 2),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": "KITTI-DE depth-edge AUC eval, oracle port on host cores"},
+                "cpu_baseline": {"value": round(value, 3), "unit": "Mpixel/s", "cores": 1, "kind": "port",
+                                 "sample": f"{n} images x 12 thresholds per step (NumPy/C oracle, single core)"},
+                "e2e": {"value": round(value, 3), "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+    # bounded sample of the config-3 loss shape: batch 2 x 4 scales per step
+    steps = max(1, min(args.steps, 40))
+    v, dt, px = cpu_loss_baseline(B=2, scales=SCALES, iters=steps, warm=max(1, min(args.warmup, 3)))
+    line = {"metric": "edge_loss_fwd_bwd_throughput", "value": round(v, 3), "unit": "Mpixel/s", "impl": "reference",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "edge loss fwd+bwd, 4-scale pyramid 384x1280..48x160 fp32 (BASELINE.json config 3 loss "
+                                   "shape), oracle port of GradLoss on host cores; each step a bounded sample of batch 2"},
+            "cpu_baseline": {"value": round(v, 3), "unit": "Mpixel/s", "cores": cores, "kind": "port",
+                             "sample": f"batch 2 x 4 scales ({px / 1e6:.2f} Mpx) per step, {steps} timed steps, "
+                                       f"torch CPU {torch.get_num_threads()} threads"},
+            "e2e": {"value": round(v, 3), "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="mte", choices=["mte", "reference"])
+    ap.add_argument("--workload", default="loss", choices=["loss", "auc"])
+    ap.add_argument("--no-secondary", action="store_true", help="skip the second workload and the CPU baselines")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: mindtheedge_b200 has no CPU path (use --impl reference for the CPU port)")
+    rank, world, local = dist_setup(args.gpus)
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    from mindtheedge_b200 import build
+    if rank == 0:
+        build.build()
+    barrier(world)
+
+    if args.workload == "loss":
+        line = bench_loss(args, rank, world, device)
+        if not args.no_secondary:
+            line["auc_eval"] = bench_auc(args, rank, world, device, steps=max(2, min(args.steps, 5)), warmup=3)
+    else:
+        a = bench_auc(args, rank, world, device)
+        line = {"metric": a["metric"], "value": a["value"], "unit": a["unit"], "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": a["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": a["config"], "e2e": a["e2e"],
+                "gpu_launches": a["gpu_launches_per_step"] * args.steps, "roofline": a["roofline"]}
+    if rank == 0 and not args.no_secondary:
+        v, dt, px = cpu_loss_baseline(B=4, scales=1, iters=5, warm=2)
+        cb = {"value": round(v, 3), "unit": "Mpixel/s", "cores": os.cpu_count(), "kind": "port",
+              "sample": f"oracle port of GradLoss fwd+bwd (torch CPU, {torch.get_num_threads()} threads), batch 4 x "
+                        f"384x1280 (BASELINE.json config 1), 5 timed iterations of {dt * 1e3:.0f} ms"}
+        va, dta, pxa = cpu_auc_baseline(3)
+        ca = {"value": round(va, 3), "unit": "Mpixel/s", "cores": 1, "kind": "port",
+              "sample": f"oracle port of pr_evaluation (NumPy Canny + C Hopcroft-Karp, 1 core), 3 images x 12 "
+                        f"thresholds in {dta:.1f} s"}
+        if args.workload == "loss":
+            line["cpu_baseline"] = cb
+            if "auc_eval" in line:
+                line["auc_eval"]["cpu_baseline"] = ca
+        else:
+            line["cpu_baseline"] = ca
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -8,6 +8,7 @@
 //   inv2depth (optional fuse)   packnet_code/packnet_sfm/utils/depth.py:104-121
 // and the autograd backward of that chain.  The hot kernels live in
 // edge_loss_kernels.cuh and are instantiated in edge_loss_{fwd,bwd}_v{4,1}.cu.
+#include <stdlib.h>
 #include <string.h>
 
 #include "edge_loss_kernels.cuh"
@@ -110,7 +111,7 @@ __global__ void resize_bwd_kernel(const float *__restrict__ gout, float *__restr
 // ---------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------
-constexpr int kCtaWaves = 4;
+constexpr int kFwdCtaWaves = 2, kBwdCtaWaves = 16;
 
 struct Plan {
     LossP P;
@@ -174,7 +175,11 @@ static int make_plan(Plan &pl, const mte_loss_scale_t *sc, int n, const mte_loss
     }
     // Cap the grid near kCtaWaves resident waves so the per-CTA epilogue (partials, ticket) is amortised over
     // several items per warp; every scale keeps at least one CTA per image.
-    const int cap = kNumSMs * 2 * kCtaWaves;
+    // measured on B200 (profiles/r01_notes.md): the forward (per-CTA reduction epilogue) likes ~2 resident waves,
+    // the backward (no epilogue) only needs enough CTAs for the hardware scheduler to balance the tail
+    int waves = bwd ? kBwdCtaWaves : kFwdCtaWaves;
+    if (const char *e = getenv("MTE_CTA_WAVES")) waves = atoi(e) > 0 ? atoi(e) : waves;  // tuning knob
+    const int cap = kNumSMs * 2 * waves;
     if (cta > cap) {
         const double shrink = (double)cap / (double)cta;
         cta = 0;
