@@ -34,6 +34,7 @@ from .edge import canny_from_depth, read_depth_file
 __all__ = [
     "pr_counts", "correspond_pixels_batch", "evaluate_boundaries", "evaluate_boundaries_bin",
     "compute_rec_prec_f1", "pr_evaluation", "pr_evaluation_arrays", "mean_recall_at_precision_range",
+    "shard_indices", "all_reduce_counts", "sweep_counts",
 ]
 
 _DT = {torch.float32: _lib.MTE_F32, torch.float64: _lib.MTE_F64, torch.uint8: _lib.MTE_U8}
@@ -187,6 +188,23 @@ def _dist_info():
     return 0, 1
 
 
+def shard_indices(n_items: int, rank: Optional[int] = None, world: Optional[int] = None) -> List[int]:
+    """Image i of the evaluation goes to rank i mod R."""
+    if rank is None or world is None:
+        rank, world = _dist_info()
+    return list(range(rank, n_items, world))
+
+
+def all_reduce_counts(counts: torch.Tensor) -> torch.Tensor:
+    """The ONE collective of the evaluation: integer sum of the int64[T,4] counts over ranks
+    (the distributed form of the Python ``sum`` at eval_depth_edges.py:298-301).  Exact, so the
+    result does not depend on the number of ranks."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    return counts
+
+
 def sweep_counts(depth: torch.Tensor, gt: torch.Tensor, edge_thresh_range, gt_crop, min_depth, max_depth,
                  max_dist=0.002, out=None) -> torch.Tensor:
     """Device part of ``pr_evaluation`` for a batch: depth [N,H,W] (already at GT size), gt [N,H,W]
@@ -216,7 +234,7 @@ def pr_evaluation_arrays(depths: Sequence[np.ndarray], gts: Sequence[np.ndarray]
     rank, world = _dist_info()
     dev = torch.device("cuda", torch.cuda.current_device())
     counts = torch.zeros((len(edge_thresh_range), 4), dtype=torch.int64, device=dev)
-    mine = list(range(rank, len(depths), world))
+    mine = shard_indices(len(depths), rank, world)
     # group by GT shape and depth dtype so every launch is a dense batch; the quantisation runs in the
     # array's own float type (edge.py:85-87), so float32 and float64 maps must not be mixed
     by_shape = {}
@@ -237,9 +255,7 @@ def pr_evaluation_arrays(depths: Sequence[np.ndarray], gts: Sequence[np.ndarray]
             g_dev = torch.from_numpy(np.stack([(np.asarray(gts[i]) > 127).astype(np.uint8) for i in chunk])).to(
                 dev, non_blocking=True)
             sweep_counts(d_dev, g_dev, edge_thresh_range, gt_crop, min_depth, max_depth, out=counts)
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    all_reduce_counts(counts)
     c = counts.cpu().numpy().astype(np.float64)
     rec, prec, _ = compute_rec_prec_f1(c[:, 0], c[:, 1], c[:, 2], c[:, 3])
     return [float(p) for p in prec], [float(r) for r in rec], counts

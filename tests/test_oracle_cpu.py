@@ -1,0 +1,135 @@
+"""CPU suite, part 1: the oracle against the golden vectors generated from the reference
+(tests/golden/make_golden.py) and against the third-party calls the reference makes."""
+import os
+
+import cv2
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, load_cases
+from synth import random_boundary_maps, scene_with_gt
+
+LOSS_CASES = load_cases("edge_loss.npz")
+
+
+def _t(a):
+    return None if a.size == 0 else torch.from_numpy(a)
+
+
+@pytest.mark.parametrize("name", sorted(LOSS_CASES))
+def test_edge_loss_oracle_vs_reference_golden(name):
+    from oracle.edge_loss import edge_loss_np64, edge_loss_torch
+    c = LOSS_CASES[name]
+    is_grad, is_sigmoid, thresh, weight, p2n = c["attrs"]
+    x = _t(c["depth"]).requires_grad_(True)
+    loss, gmap = edge_loss_torch(x, _t(c["edge"]), _t(c["mask"]), bool(is_grad), bool(is_sigmoid), float(thresh),
+                                 _t(c["normal"]), weight=float(weight), pos_to_neg=float(p2n))
+    loss.backward()
+    ref = float(c["loss"])
+    if np.isnan(ref):
+        assert np.isnan(loss.item())
+        return
+    assert abs(loss.item() - ref) <= 1e-6 * abs(ref)
+    assert np.abs(gmap.numpy() - c["grad_map"]).max() <= 1e-5 * max(np.abs(c["grad_map"]).max(), 1e-30)
+    assert np.abs(x.grad.numpy() - c["dgrad"]).max() <= 1e-5 * np.abs(c["dgrad"]).max()
+    # the independent fp64 restatement with the analytic backward agrees with both
+    l64, g64, dx64 = edge_loss_np64(c["depth"], c["edge"], None if c["mask"].size == 0 else c["mask"], bool(is_grad),
+                                    bool(is_sigmoid), float(thresh), None if c["normal"].size == 0 else c["normal"],
+                                    weight=float(weight), pos_to_neg=float(p2n))
+    assert abs(l64 - ref) <= 2e-6 * abs(ref)
+    assert np.abs(dx64 - c["dgrad"]).max() <= 5e-5 * np.abs(c["dgrad"]).max()
+
+
+def test_direction_bands_at_the_fp32_limits():
+    from oracle.edge_loss import DIR_H, DIR_LR, DIR_RL, DIR_V, direction_index
+    b = [np.float32(k * np.pi / 8) for k in range(9)]
+    up = lambda v: np.nextafter(np.float32(v), np.float32(10))
+    dn = lambda v: np.nextafter(np.float32(v), np.float32(-10))
+    th = np.array([0, b[1], dn(b[1]), b[3], dn(b[3]), b[5], dn(b[5]), b[7], dn(b[7]),
+                   -b[1], dn(-b[1]), -b[3], dn(-b[3]), -b[5], dn(-b[5]), -b[7], dn(-b[7]), np.nan, 4.0, -4.0],
+                  np.float32)
+    want = [DIR_H, DIR_RL, DIR_H, DIR_V, DIR_RL, DIR_LR, DIR_V, DIR_H, DIR_LR,
+            DIR_H, DIR_LR, DIR_LR, DIR_V, DIR_V, DIR_RL, DIR_RL, DIR_H, DIR_H, DIR_H, DIR_H]
+    assert direction_index(th).tolist() == want
+
+
+def test_canny_oracle_vs_golden_and_cv2():
+    from oracle.canny import canny_birth_levels, canny_np, edges_from_depth_np, quantise_depth
+    z = np.load(os.path.join(GOLDEN, "canny.npz"))
+    for i in range(6):
+        d = z[f"depth{i}"]
+        for t in (20, 60, 120, 240):
+            ref = np.unpackbits(z[f"edges{i}_t{t}"])[: d.size].reshape(d.shape) * 255
+            assert np.array_equal(edges_from_depth_np(d, 0.0, 80.0, t // 2, t), ref), (i, t)
+            assert np.array_equal(cv2.Canny(quantise_depth(d), t // 2, t), ref)
+    _, d = scene_with_gt(96, 200, 1)
+    q = quantise_depth(d)
+    pairs = [(t // 2, t) for t in range(240, 19, -20)]
+    lv = canny_birth_levels(q, pairs)
+    for k, (lo, hi) in enumerate(pairs):
+        assert np.array_equal((lv <= k) * 255, cv2.Canny(q, lo, hi))
+        assert np.array_equal(canny_np(q, lo, hi), cv2.Canny(q, lo, hi))
+
+
+def test_dee_oracle_vs_golden_and_cv2_sobel():
+    from oracle import dee
+    z = np.load(os.path.join(GOLDEN, "dee.npz"))
+    for i in range(5):
+        p = z[f"prob{i}"]
+        sx, sy = dee.sobel5(p)
+        assert np.array_equal(sx, cv2.Sobel(p, cv2.CV_64F, 1, 0, ksize=5))
+        assert np.array_equal(sy, cv2.Sobel(p, cv2.CV_64F, 0, 1, ksize=5))
+        nms = dee.non_max_suppression(p)
+        assert np.array_equal(nms, z[f"nms{i}"])
+        assert np.array_equal(dee.hysteresis(nms), z[f"hyst{i}"], equal_nan=True)
+        assert np.array_equal(dee.hysteresis(p), z[f"hyst_raw{i}"], equal_nan=True)
+        assert np.array_equal(dee.hysteresis(nms, 0.2, 0.5), z[f"hyst_custom{i}"], equal_nan=True)
+        assert np.array_equal(dee.normals_u8(p), z[f"normals{i}"])
+
+
+def test_matcher_oracle_vs_scipy():
+    from oracle import pr_counts as opr
+    for k, (shape, md) in enumerate([((60, 90), 0.0075), ((218, 1153), 0.002), ((40, 40), 0.05), ((100, 300), 0.01)]):
+        pred, gt = random_boundary_maps(*shape, seed=k)
+        c = opr.match_count(pred, gt, md)
+        assert c == opr.match_count_scipy(pred, gt, md)
+        m1, m2, _, _ = opr.correspond_pixels(pred, gt, md)
+        assert (m1 > 0).sum() == c == (m2 > 0).sum()
+    assert opr.match_count(np.zeros((5, 5)), np.ones((5, 5)), 0.1) == 0
+
+
+def test_pr_oracle_vs_reference_golden():
+    from oracle import pr_counts as opr
+    z = np.load(os.path.join(GOLDEN, "pr.npz"))
+    for flag in (0, 1):
+        c, thr = opr.evaluate_boundaries(z["soft"], [z["soft_gt"].astype(np.float64)], 9, 0.0075, bool(flag))
+        assert np.array_equal(c, z[f"soft_counts_thin{flag}"])
+        assert np.array_equal(thr, z["soft_thr"])
+    H, W = z["pr_shape"]
+    gts = [np.unpackbits(z[f"pr_gt{i}"])[: H * W].reshape(H, W).astype(np.uint8) * 255 for i in range(3)]
+    depths = [(z[f"pr_depth_u16_{i}"] / 256).astype(np.float32) for i in range(3)]
+    c = opr.pr_sweep_counts(depths, gts, [int(v) for v in z["pr_range"]], tuple(int(v) for v in z["pr_crop"]))
+    rec, prec, _ = opr.rec_prec_f1(c[:, 0], c[:, 1], c[:, 2], c[:, 3])
+    assert np.array_equal(prec, z["pr_precision"]) and np.array_equal(rec, z["pr_recall"])
+    pr = np.vstack((prec, rec)).transpose()
+    assert opr.mean_recall_at_precision_range(pr) == z["pr_auc_full"]
+    assert opr.mean_recall_at_precision_range(pr, 0.12, 0.65) == z["pr_auc_part"]
+
+
+def test_thin_oracle_properties():
+    from oracle import thin
+    r = np.random.default_rng(0)
+    x = r.random((60, 90)) < 0.5
+    x[10:40, 20:60] = True
+    t = thin.binary_thin(x)
+    assert not (t & ~x).any()                       # only deletes
+    assert np.array_equal(thin.binary_thin(t), t)   # idempotent
+    from scipy import ndimage
+    s8 = np.ones((3, 3), bool)
+    assert ndimage.label(t, s8)[1] == ndimage.label(x, s8)[1]  # 8-connectivity preserved
+    line = np.zeros((9, 30), bool)
+    line[4, 3:27] = True
+    assert np.array_equal(thin.binary_thin(line), line)  # a 1-px line is already thin
+    lut1, lut2 = thin.build_luts()
+    assert lut1.sum() == lut2.sum() and not lut1[0] and not lut1[255]
