@@ -6,17 +6,12 @@
 //  1. canny_nms_kernel   depth -> u8 (clamp, *255/max, trunc) -> Sobel3 (BORDER_REPLICATE) -> L1 magnitude ->
 //                        fixed-point NMS, staged through a shared-memory halo tile; emits per pixel the FIRST
 //                        threshold index at which it is a candidate (cl) and at which it is strong (sl).
-//  2. canny_hyst_kernel  multi-threshold hysteresis as one monotone relaxation
-//                            E(p) = max(cl(p), min(E(p), min_{n in N8(p)} E(n))),  E initialised to sl,
-//                        so E(p) <= t  <=>  p is an edge of cv2.Canny at pair t, for ALL nested pairs at once
-//                        (one u8 plane instead of T).  Tile-local fix-point in shared memory, tiles re-queued
-//                        through dirty flags, grid-wide iterations inside ONE cooperative launch (no host sync).
+//  2. canny_uf_hyst_kernel  multi-threshold hysteresis for ALL nested pairs at once: incremental union-find
+//                        over the candidate pixels in threshold order; result is one u8 "birth level" plane
+//                        E with  E(p) <= t  <=>  p is an edge of cv2.Canny at pair t  (instead of T planes).
 //  3. canny_expand_kernel  optional: the T {0,255} planes the reference API returns.
-#include <cooperative_groups.h>
 
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace mte {
 namespace canny {
@@ -114,101 +109,164 @@ __global__ void __launch_bounds__(kThreads) canny_nms_kernel(const T *__restrict
     }
 }
 
-struct HystP {
+// ---------------------------------------------------------------------------
+// Multi-threshold hysteresis as incremental connected components (Kruskal order).
+//
+// cl(p) = first threshold index at which p is a candidate, E(p) initialised to the first index at which p
+// is strong (255 = never).  Pair t's edge set is: candidates (cl <= t) 8-connected, through candidates, to a
+// strong pixel (sl <= t).  Candidate sets are nested in t, so components only ever merge as t grows: one
+// lock-free union-find per image, levels t = 0..T-1 processed in order:
+//   (i)   pixels with cl == t join their 8-neighbours with cl <= t         (atomicCAS link, smaller root wins)
+//   (ii)  every pixel already an edge (E <= t) flags its root
+//   (iii) every unassigned candidate whose root is flagged gets E = t
+// => E(p) <= t  <=>  p is an edge of cv2.Canny at pair t, for all pairs at once, with no data-dependent
+// iteration count (a relaxation needs one sweep per tile a weak chain crosses: 50-120 grid-wide
+// iterations on long object boundaries, profiles/r01_notes.md).  One CTA per image walks the compacted
+// candidate list (~2 % of the pixels); parents live in an L2-resident int32 plane.
+// ---------------------------------------------------------------------------
+constexpr int kUfThreads = 1024;
+
+struct UfP {
     const unsigned char *cl;
     unsigned char *E;
-    int N, H, W, tilesX, tilesY, nTiles;
-    unsigned char *active;   // [2][nTiles]
-    unsigned int *counters;  // [2] number of tiles queued for iteration parity
+    int N, H, W, T;
+    int *parent;          // [N,H,W]
+    int *list;            // [N,H,W] candidate pixels, sorted by cl
+    int *merged;          // [N,H,W] roots linked away during the current level
+    unsigned char *flag;  // [N,H,W] "component holds an edge pixel", valid at roots
 };
 
-__global__ void __launch_bounds__(kThreads) canny_hyst_kernel(const HystP P) {
-    cg::grid_group grid = cg::this_grid();
-    __shared__ unsigned char sE[TH + 2][TW + 2];
-    __shared__ unsigned char sC[TH][TW];
-    __shared__ int sChanged, sBorder, sGo;
-    const int perImg = P.tilesX * P.tilesY;
-    for (int it = 0;; it++) {
-        unsigned char *cur = P.active + (size_t)(it & 1) * P.nTiles;
-        unsigned char *nxt = P.active + (size_t)((it + 1) & 1) * P.nTiles;
-        for (int tile = blockIdx.x; tile < P.nTiles; tile += gridDim.x) {
-            if (threadIdx.x == 0) {
-                sGo = (it == 0) || cur[tile];
-                cur[tile] = 0;
-            }
-            __syncthreads();
-            if (!sGo) {
-                __syncthreads();
-                continue;
-            }
-            const int img = tile / perImg, tl = tile - img * perImg;
-            const int tx = tl % P.tilesX, ty = tl / P.tilesX;
-            const int x0 = tx * TW, y0 = ty * TH;
-            const size_t base = (size_t)img * P.H * P.W;
-            for (int i = threadIdx.x; i < (TH + 2) * (TW + 2); i += kThreads) {
-                const int r = i / (TW + 2), c = i - r * (TW + 2);
-                const int y = y0 + r - 1, x = x0 + c - 1;
-                const bool in = y >= 0 && y < P.H && x >= 0 && x < P.W;
-                sE[r][c] = in ? __ldcg(P.E + base + (size_t)y * P.W + x) : (unsigned char)kNever;
-            }
-            for (int i = threadIdx.x; i < TH * TW; i += kThreads) {
-                const int r = i / TW, c = i - r * TW;
-                const int y = y0 + r, x = x0 + c;
-                sC[r][c] = (y < P.H && x < P.W) ? P.cl[base + (size_t)y * P.W + x] : (unsigned char)kNever;
-            }
-            if (threadIdx.x == 0) sBorder = 0;
-            __syncthreads();
-            // tile-local fix-point (in place: any value read is a valid upper bound, the map is monotone)
-            bool anyChange = false;
-            for (;;) {
-                if (threadIdx.x == 0) sChanged = 0;
-                __syncthreads();
-                bool ch = false;
-                for (int i = threadIdx.x; i < TH * TW; i += kThreads) {
-                    const int r = i / TW, c = i - r * TW;
-                    const int cur_e = sE[r + 1][c + 1], lim = sC[r][c];
-                    if (cur_e <= lim) continue;  // already at its candidate level (or never a candidate)
-                    int m = min(min(sE[r][c], sE[r][c + 1]), sE[r][c + 2]);
-                    m = min(m, min(sE[r + 1][c], sE[r + 1][c + 2]));
-                    m = min(m, min(min(sE[r + 2][c], sE[r + 2][c + 1]), sE[r + 2][c + 2]));
-                    const int ne = max(lim, min(cur_e, m));
-                    if (ne < cur_e) {
-                        sE[r + 1][c + 1] = (unsigned char)ne;
-                        ch = true;
-                        if (r == 0 || c == 0 || r == TH - 1 || c == TW - 1) sBorder = 1;
-                    }
-                }
-                if (ch) sChanged = 1;
-                __syncthreads();
-                if (!sChanged) break;
-                anyChange = true;
-                __syncthreads();
-            }
-            if (anyChange) {
-                for (int i = threadIdx.x; i < TH * TW; i += kThreads) {
-                    const int r = i / TW, c = i - r * TW;
-                    const int y = y0 + r, x = x0 + c;
-                    if (y < P.H && x < P.W) __stcg(P.E + base + (size_t)y * P.W + x, sE[r + 1][c + 1]);
-                }
-                if (sBorder && threadIdx.x < 9 && threadIdx.x != 4) {
-                    const int nx = tx + (int)(threadIdx.x % 3) - 1, ny = ty + (int)(threadIdx.x / 3) - 1;
-                    if (nx >= 0 && nx < P.tilesX && ny >= 0 && ny < P.tilesY) {
-                        const int nt = img * perImg + ny * P.tilesX + nx;
-                        if (!nxt[nt]) {
-                            nxt[nt] = 1;
-                            atomicAdd(P.counters + ((it + 1) & 1), 1u);
-                        }
-                    }
-                }
-            }
-            __syncthreads();
+// find with path halving (every visited node is re-pointed to its grandparent; lock-free safe: a node only
+// ever moves to one of its ancestors, roots change only through the CAS in uf_unite)
+__device__ __forceinline__ int uf_find(int *parent, int x) {
+    int p = __ldcg(parent + x);
+    while (p != x) {
+        const int gp = __ldcg(parent + p);
+        if (gp == p) return p;
+        __stcg(parent + x, gp);
+        x = gp;
+        p = __ldcg(parent + x);
+    }
+    return x;
+}
+
+// 16 level bytes of one thread-step (128-bit load when the plane allows it)
+__device__ __forceinline__ void load16(unsigned char (&v)[16], const unsigned char *cl, int i0, int HW, bool vec) {
+    if (vec) {
+        *reinterpret_cast<uint4 *>(v) = __ldg(reinterpret_cast<const uint4 *>(cl + i0));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; k++) v[k] = (i0 + k < HW) ? cl[i0 + k] : (unsigned char)kNever;
+    }
+}
+
+__global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_kernel(const UfP P) {
+    __shared__ int sHist[256];   // candidates per level, then bucket write cursors
+    __shared__ int sEnd[256];    // sEnd[t] = number of candidates with cl <= t (list is sorted by cl)
+    __shared__ int sMerged;
+    const int img = blockIdx.x;
+    const int HW = P.H * P.W;
+    const size_t base = (size_t)img * HW;
+    const unsigned char *cl = P.cl + base;
+    unsigned char *E = P.E + base;
+    int *parent = P.parent + base;
+    int *list = P.list + base;
+    int *merged = P.merged + base;
+    unsigned char *flag = P.flag + base;
+    const int T = P.T;
+    for (int i = threadIdx.x; i < 256; i += kUfThreads) sHist[i] = 0;
+    __syncthreads();
+    // counting sort of the candidate pixels by their first-candidate level (two coalesced passes over cl)
+    const bool vec = (HW % 16) == 0 && (reinterpret_cast<uintptr_t>(cl) & 15) == 0;
+    for (int i0 = threadIdx.x * 16; i0 < HW; i0 += kUfThreads * 16) {
+        unsigned char v[16];
+        load16(v, cl, i0, HW, vec);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            // warp-aggregated: one shared atomic per distinct level in the warp (most candidates share 1-2 levels)
+            const unsigned grp = __match_any_sync(__activemask(), (int)v[k]);
+            if (v[k] != kNever && (int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sHist[v[k]], __popc(grp));
         }
-        __threadfence();
-        grid.sync();
-        const unsigned pending = *(volatile unsigned int *)(P.counters + ((it + 1) & 1));
-        grid.sync();
-        if (blockIdx.x == 0 && threadIdx.x == 0) P.counters[(it + 1) & 1] = 0;  // consumed; clean for reuse
-        if (pending == 0) break;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int t = 0; t < 255; t++) {
+            const int c = sHist[t];
+            sHist[t] = run;  // becomes the write cursor of bucket t
+            run += c;
+            sEnd[t] = run;
+        }
+    }
+    __syncthreads();
+    for (int i0 = threadIdx.x * 16; i0 < HW; i0 += kUfThreads * 16) {
+        unsigned char v[16];
+        load16(v, cl, i0, HW, vec);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const unsigned act = __activemask();
+            const unsigned grp = __match_any_sync(act, (int)v[k]);
+            const int leader = __ffs(grp) - 1, lane = threadIdx.x & 31;
+            int slot = 0;
+            if (v[k] != kNever && lane == leader) slot = atomicAdd(&sHist[v[k]], __popc(grp));
+            slot = __shfl_sync(act, slot, leader);
+            if (v[k] != kNever) {
+                list[slot + __popc(grp & ((1u << lane) - 1))] = i0 + k;
+                parent[i0 + k] = i0 + k;
+                flag[i0 + k] = 0;
+            }
+        }
+    }
+    __syncthreads();
+    const int W = P.W, H = P.H;
+    for (int t = 0; t < T; t++) {
+        const int begin = t ? sEnd[t - 1] : 0, end = sEnd[t];
+        if (threadIdx.x == 0) sMerged = 0;
+        __syncthreads();
+        // (i) the pixels that become candidates at this level join their neighbours that already are
+        for (int k = begin + threadIdx.x; k < end; k += kUfThreads) {
+            const int p = list[k];
+            const int y = p / W, x = p - y * W;
+#pragma unroll
+            for (int d = 0; d < 8; d++) {
+                const int dy = (d < 3) ? -1 : ((d < 5) ? 0 : 1);
+                const int dx = (d == 0 || d == 3 || d == 5) ? -1 : ((d == 1 || d == 6) ? 0 : 1);
+                const int yy = y + dy, xx = x + dx;
+                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                const int q = yy * W + xx;
+                if (cl[q] > t) continue;
+                // unite, remembering every root that loses its root status (its flag must follow it)
+                int a = p, b = q;
+                for (;;) {
+                    a = uf_find(parent, a);
+                    b = uf_find(parent, b);
+                    if (a == b) break;
+                    if (a < b) { const int tmp = a; a = b; b = tmp; }
+                    if (atomicCAS(parent + a, a, b) == a) {
+                        merged[atomicAdd(&sMerged, 1)] = a;
+                        break;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // (ii) flags: components that already held an edge keep it across merges; new strong pixels seed theirs
+        const int nMerged = sMerged;
+        for (int k = threadIdx.x; k < nMerged; k += kUfThreads) {
+            const int a = merged[k];
+            if (__ldcg(flag + a)) flag[uf_find(parent, a)] = 1;
+        }
+        for (int k = threadIdx.x; k < end; k += kUfThreads) {
+            const int p = list[k];
+            if (__ldcg(E + p) == t) flag[uf_find(parent, p)] = 1;  // unassigned pixels still carry their sl
+        }
+        __syncthreads();
+        // (iii) every unassigned candidate of a flagged component becomes an edge at this level
+        for (int k = threadIdx.x; k < end; k += kUfThreads) {
+            const int p = list[k];
+            if (__ldcg(E + p) > t && __ldcg(flag + uf_find(parent, p))) E[p] = (unsigned char)t;
+        }
+        __syncthreads();
     }
 }
 
@@ -234,33 +292,29 @@ static Layout layout(int N, int H, int W) {
     const size_t plane = align_up((size_t)N * H * W, 256);
     L.offCl = off; off += plane;
     L.offE = off; off += plane;
-    L.offActive = off; off += align_up((size_t)2 * L.nTiles, 256);
+    L.offActive = off; off += hysteresis_scratch_bytes(N, H, W);
     L.total = off;
     return L;
 }
 
-// Shared with the DEE post-process (dee.cu): relax E towards cl over 8-connected paths.
-int run_level_hysteresis(const unsigned char *cl, unsigned char *E, int N, int H, int W, unsigned char *active,
-                         unsigned int *counters, cudaStream_t st) {
-    HystP P;
-    P.cl = cl; P.E = E; P.N = N; P.H = H; P.W = W;
-    P.tilesX = ceil_div(W, TW); P.tilesY = ceil_div(H, TH); P.nTiles = P.tilesX * P.tilesY * N;
-    P.active = active;
-    P.counters = counters;
-    int dev = 0, sms = kNumSMs, perSm = 1;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, canny_hyst_kernel, kThreads, 0);
-    int grid = sms * (perSm < 1 ? 1 : perSm);
-    if (grid > P.nTiles) grid = P.nTiles;
-    cudaError_t e = cudaMemsetAsync(P.active, 0, (size_t)2 * P.nTiles, st);
-    if (e != cudaSuccess) return (int)e;
-    void *args[] = {&P};
-    e = cudaLaunchCooperativeKernel((const void *)canny_hyst_kernel, dim3(grid), dim3(kThreads), args, 0, st);
-    return e == cudaSuccess ? MTE_OK : (int)e;
+// Shared with the DEE post-process (dee.cu).  scratch needs hysteresis_scratch_bytes().
+int run_level_hysteresis(const unsigned char *cl, unsigned char *E, int N, int H, int W, int T, void *scratch,
+                         cudaStream_t st) {
+    UfP P;
+    const size_t px = (size_t)N * H * W;
+    char *w = static_cast<char *>(scratch);
+    P.cl = cl; P.E = E; P.N = N; P.H = H; P.W = W; P.T = T;
+    P.parent = reinterpret_cast<int *>(w);
+    P.list = reinterpret_cast<int *>(w + align_up(px * 4, 256));
+    P.merged = reinterpret_cast<int *>(w + 2 * align_up(px * 4, 256));
+    P.flag = reinterpret_cast<unsigned char *>(w + 3 * align_up(px * 4, 256));
+    canny_uf_hyst_kernel<<<N, kUfThreads, 0, st>>>(P);
+    MTE_RETURN_IF_CUDA_ERROR();
+    return MTE_OK;
 }
-size_t hysteresis_active_bytes(int N, int H, int W) {
-    return align_up((size_t)2 * ceil_div(W, TW) * ceil_div(H, TH) * N, 256);
+size_t hysteresis_scratch_bytes(int N, int H, int W) {
+    const size_t px = (size_t)N * H * W;
+    return 3 * align_up(px * 4, 256) + align_up(px, 256);
 }
 
 static int run_pairs(const void *depth, int dtype, int N, int H, int W, double min_depth, double max_depth,
@@ -270,6 +324,7 @@ static int run_pairs(const void *depth, int dtype, int N, int H, int W, double m
     unsigned char *E = levels ? levels : reinterpret_cast<unsigned char *>(ws + L.offE);
     const int grid1 = L.nTiles;
     const double factor = 255.0 / max_depth;
+
     if (dtype == MTE_F32)
         canny_nms_kernel<float><<<grid1, kThreads, 0, st>>>(static_cast<const float *>(depth), N, H, W, (float)min_depth,
                                                            (float)max_depth, (float)factor, thr, cl, E);
@@ -281,8 +336,7 @@ static int run_pairs(const void *depth, int dtype, int N, int H, int W, double m
                                                                    0, 0, 0, thr, cl, E);
     MTE_RETURN_IF_CUDA_ERROR();
 
-    int rc = run_level_hysteresis(cl, E, N, H, W, reinterpret_cast<unsigned char *>(ws + L.offActive),
-                                  reinterpret_cast<WsHeader *>(ws)->flag, st);
+    int rc = run_level_hysteresis(cl, E, N, H, W, thr.n, ws + L.offActive, st);
     if (rc) return rc;
     int sms = kNumSMs;
     if (edges) {

@@ -52,11 +52,11 @@ __device__ __forceinline__ void st_stream4(float *p, float4 v) { __stcs(reinterp
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 namespace canny {
-// canny.cu: multi-level 8-connected hysteresis  E <- max(cl, min(E, min_N8 E))  to its fix-point (one
-// cooperative launch).  `active` needs hysteresis_active_bytes(); `counters` = 2 zeroed uints (self-cleaning).
-int run_level_hysteresis(const unsigned char *cl, unsigned char *E, int N, int H, int W, unsigned char *active,
-                         unsigned int *counters, cudaStream_t st);
-size_t hysteresis_active_bytes(int N, int H, int W);
+// canny.cu: multi-level 8-connected hysteresis on (cl, E) level planes: afterwards E(p) = first level t >= cl(p)
+// at which p is connected, through pixels with cl <= t, to a pixel whose initial E <= t.
+int run_level_hysteresis(const unsigned char *cl, unsigned char *E, int N, int H, int W, int T, void *scratch,
+                         cudaStream_t st);
+size_t hysteresis_scratch_bytes(int N, int H, int W);
 }  // namespace canny
 
 }  // namespace mte

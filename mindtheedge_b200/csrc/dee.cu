@@ -11,7 +11,7 @@
 // bit-identical to OpenCV's and the orientation bins / uint8 normals follow.
 //
 // Kernels:  dee_front_kernel  (Sobel5 + normals + NMS + hysteresis labels, shared-memory halo tile)
-//           canny::run_level_hysteresis (shared 8-connected relaxation, one cooperative launch)
+//           canny::run_level_hysteresis (shared 8-connected union-find hysteresis)
 //           dee_finish_kernel (img * labels / max(labels), the reference's normalisation quirk included)
 #include <math.h>
 #include <string.h>
@@ -193,7 +193,7 @@ static Layout layout(int N, int H, int W) {
     L.offVal = off; off += align_up((size_t)N * H * W * sizeof(double), 256);
     L.offCl = off; off += align_up((size_t)N * H * W, 256);
     L.offE = off; off += align_up((size_t)N * H * W, 256);
-    L.offActive = off; off += canny::hysteresis_active_bytes(N, H, W);
+    L.offActive = off; off += canny::hysteresis_scratch_bytes(N, H, W);
     L.total = off;
     return L;
 }
@@ -224,8 +224,7 @@ static int run(const T *prob, int N, int H, int W, int do_nms, int do_hyst, doub
     const size_t n = (size_t)N * H * W;
     const int grid = (int)((n + 255) / 256 < (size_t)kNumSMs * 16 ? (n + 255) / 256 : (size_t)kNumSMs * 16);
     if (do_hyst) {
-        int rc = canny::run_level_hysteresis(cl, E, N, H, W, reinterpret_cast<unsigned char *>(ws + L.offActive),
-                                             reinterpret_cast<WsHeader *>(ws)->flag + 2, st);
+        int rc = canny::run_level_hysteresis(cl, E, N, H, W, 1, ws + L.offActive, st);
         if (rc) return rc;
         // the reference computes in float64 once NMS has run (its output array is float64), else in the input type
         const bool c64 = do_nms || sizeof(T) == 8;
