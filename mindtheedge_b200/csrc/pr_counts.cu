@@ -11,11 +11,13 @@
 // One persistent CTA per (image, threshold) problem, problems handed out through an atomic counter:
 //   scan   the cropped window once (the 2 B/px of algorithmic traffic), compact predicted pixels,
 //   greedy nearest-first proposals with 16-bit CAS on the GT side,
-//   then phases of { exhaustive alternating-forest BFS from all free predicted pixels, level-synchronous
-//   with warp-per-vertex expansion; one vertex-disjoint augmenting path per tree, claimed with CAS }
-//   until a phase finds no free GT pixel => no augmenting path exists => the matching is maximum.
+//   then phases of { alternating-forest BFS from all free predicted pixels, level-synchronous with
+//   warp-per-vertex expansion, stopped at the first level that reaches a free GT pixel; one
+//   vertex-disjoint augmenting path per tree, claimed with CAS }
+//   until an (exhaustive) phase finds no free GT pixel => no augmenting path exists => maximum.
 // Per-pixel state is 16-bit offset codes in an L2-resident per-CTA arena; nothing is allocated.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -48,6 +50,12 @@ struct MatchP {
     unsigned char *matchA, *matchB;  // optional outputs [nProblems,h,w]
     char *arena;               // kArenas * arenaBytes
     size_t arenaBytes;
+    const int *problemList;    // optional indirection: only these problems (the shared-memory kernel's overflow list)
+    const unsigned int *listCount;  // device count of problemList entries
+    unsigned int *overflowCount;    // written by the shared-memory kernel, reset by the dense kernel
+    int *overflowList;
+    int truncate;              // stop each BFS at the first level that reaches a free GT pixel
+    unsigned int *stats;       // optional profiling counters {phases, levels, expanded vertices, free roots}
     unsigned int *nextProblem; // dynamic scheduler (self-resetting)
     unsigned int *doneCtas;
 };
@@ -124,7 +132,11 @@ __global__ void __launch_bounds__(kThreads) match_kernel(const __grid_constant__
     __syncthreads();
 
     for (;;) {
-        if (threadIdx.x == 0) sProblem = (int)atomicAdd(P.nextProblem, 1u);
+        if (threadIdx.x == 0) {
+            int pr = (int)atomicAdd(P.nextProblem, 1u);
+            if (P.problemList) pr = (pr < (int)*P.listCount) ? P.problemList[pr] : P.nProblems;
+            sProblem = pr;
+        }
         __syncthreads();
         const int prob = sProblem;
         if (prob >= P.nProblems) break;
@@ -217,6 +229,7 @@ __global__ void __launch_bounds__(kThreads) match_kernel(const __grid_constant__
             int *cur = A.fa, *nxt = A.fb;
             int nCur = sCntA;
             if (nCur == 0) break;
+            if (P.stats && threadIdx.x == 0) { atomicAdd(P.stats + 0, 1u); atomicAdd(P.stats + 3, (unsigned)nCur); }
             // exhaustive alternating-forest BFS
             while (nCur > 0) {
                 if (threadIdx.x == 0) sCntB = 0;
@@ -246,7 +259,10 @@ __global__ void __launch_bounds__(kThreads) match_kernel(const __grid_constant__
                     }
                 }
                 __syncthreads();
-                nCur = sCntB;
+                // shortest augmenting paths first (Hopcroft-Karp layering): stop at the first level that reaches a
+                // free GT pixel; only the last phase, which finds none, explores the forest exhaustively
+                nCur = (P.truncate && sEnds > 0) ? 0 : sCntB;
+                if (P.stats && threadIdx.x == 0) { atomicAdd(P.stats + 1, 1u); atomicAdd(P.stats + 2, (unsigned)sCntB); }
                 int *tmp = cur; cur = nxt; nxt = tmp;
                 __syncthreads();
             }
@@ -326,6 +342,318 @@ __global__ void __launch_bounds__(kThreads) match_kernel(const __grid_constant__
         if (d == gridDim.x - 1) {
             *P.nextProblem = 0u;
             *P.doneCtas = 0u;
+            if (P.problemList) *P.overflowCount = 0u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Shared-memory matcher: the same algorithm with the whole problem resident on the SM.
+//
+// State is indexed by COMPACT vertex ids (16 bit): the GT side is a bitmap of the window plus a per-word
+// rank (pixel -> id by popcount), the predicted side a list of pixel positions.  A BFS level then costs a few
+// shared-memory round trips instead of L2 round trips (profiles/r01_notes.md: ~1000 levels per problem on long
+// contours, 15 us each in the L2 version).  Problems that do not fit (window bitmap or vertex counts beyond the
+// ~200 KB budget) are appended to an overflow list and solved by match_kernel above.
+// ---------------------------------------------------------------------------
+constexpr int kSmThreads = 512;
+constexpr int kSmWarps = kSmThreads / 32;
+constexpr int kSmemTableOff = 1024;  // offsets staged in static shared memory (radius <= 17 px)
+
+struct SmemLayout {
+    int nW;          // bitmap words of the window
+    int capP, capQ;  // vertex capacities
+    unsigned oBits, oRank, oPpix, oMateP, oClaimP, oFa, oFb, oMateQ, oParentQ, oStampQ, oEnds, total;
+};
+
+__global__ void __launch_bounds__(kSmThreads, 1) match_smem_kernel(const __grid_constant__ MatchP Pin,
+                                                                   const __grid_constant__ ParamTables tabs,
+                                                                   int tablesInParam, const SmemLayout SL) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ int sProblem, sNP, sNQ, sCntA, sEnds, sMatched, sHead, sTail, sPending;
+    __shared__ int sScan[kSmThreads];
+    __shared__ short2 sOff[kSmemTableOff];
+    __shared__ double sThr[MTE_MAX_THRESHOLDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    MatchP P = Pin;
+    const int w = P.w, h = P.h, hw = w * h;
+    unsigned *qbits = reinterpret_cast<unsigned *>(dyn + SL.oBits);
+    unsigned short *qrank = reinterpret_cast<unsigned short *>(dyn + SL.oRank);
+    unsigned *ppix = reinterpret_cast<unsigned *>(dyn + SL.oPpix);
+    unsigned short *mateP = reinterpret_cast<unsigned short *>(dyn + SL.oMateP);
+    unsigned short *claimP = reinterpret_cast<unsigned short *>(dyn + SL.oClaimP);
+    unsigned short *fa = reinterpret_cast<unsigned short *>(dyn + SL.oFa);
+    unsigned short *fb = reinterpret_cast<unsigned short *>(dyn + SL.oFb);
+    unsigned short *mateQ = reinterpret_cast<unsigned short *>(dyn + SL.oMateQ);
+    unsigned short *parentQ = reinterpret_cast<unsigned short *>(dyn + SL.oParentQ);
+    unsigned short *stampQ = reinterpret_cast<unsigned short *>(dyn + SL.oStampQ);
+    unsigned short *ends = reinterpret_cast<unsigned short *>(dyn + SL.oEnds);
+    for (int i = threadIdx.x; i < P.noff; i += kSmThreads) sOff[i] = tablesInParam ? tabs.off[i] : P.off[i];
+    if (P.inMode == IN_F32 || P.inMode == IN_F64)
+        for (int i = threadIdx.x; i < P.T; i += kSmThreads) sThr[i] = tablesInParam ? tabs.thr[i] : P.thr[i];
+    P.thr = sThr;
+    __syncthreads();
+    const int noff = P.noff;
+
+    // GT vertex id of window pixel q (caller has checked the bit)
+    auto qid = [&](int q) -> int {
+        const unsigned bits = qbits[q >> 5];
+        return (int)qrank[q >> 5] + __popc(bits & ((1u << (q & 31)) - 1u));
+    };
+
+    for (;;) {
+        if (threadIdx.x == 0) sProblem = (int)atomicAdd(P.nextProblem, 1u);
+        __syncthreads();
+        const int prob = sProblem;
+        if (prob >= P.nProblems) break;
+        const int img = (P.inMode == IN_BINARY) ? prob : prob / P.T;
+        const int t = (P.inMode == IN_BINARY) ? 0 : prob - img * P.T;
+        const unsigned char *gt = P.gt + (size_t)img * P.H * P.W;
+        if (threadIdx.x == 0) { sNP = 0; sNQ = 0; sMatched = 0; }
+        __syncthreads();
+
+        // ---- scan: GT bitmap (one ballot per 32 window pixels), predicted pixel list; 4 independent
+        //      steps per thread so 8 byte loads are in flight before the first ballot
+        for (int base = 0; base < SL.nW * 32; base += 4 * kSmThreads) {
+            bool isPk[4], isQk[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = base + u * kSmThreads + threadIdx.x;
+                isPk[u] = false; isQk[u] = false;
+                if (i < hw) {
+                    const int y = i / w, x = i - y * w;
+                    const int gy = P.y0 + y, gx = P.x0 + x;
+                    isPk[u] = is_pred(P, img, t, prob, gy, gx);
+                    isQk[u] = gt[(size_t)gy * P.W + gx] != 0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = base + u * kSmThreads + threadIdx.x;
+                if (base + u * kSmThreads >= SL.nW * 32) break;  // warp-uniform
+                const unsigned mq = __ballot_sync(MTE_FULL_MASK, isQk[u]);
+                const unsigned mp = __ballot_sync(MTE_FULL_MASK, isPk[u]);
+                int wbase = 0;
+                if (lane == 0) {
+                    qbits[i >> 5] = mq;
+                    if (mq) atomicAdd(&sNQ, __popc(mq));
+                    if (mp) wbase = atomicAdd(&sNP, __popc(mp));
+                }
+                wbase = __shfl_sync(MTE_FULL_MASK, wbase, 0);
+                if (isPk[u]) {
+                    const int slot = wbase + __popc(mp & ((1u << lane) - 1));
+                    if (slot < SL.capP) { ppix[slot] = (unsigned)i; mateP[slot] = kFree; claimP[slot] = 0; }
+                }
+            }
+        }
+        __syncthreads();
+        const int nP = sNP, nQ = sNQ;
+        if (nP > SL.capP || nQ > SL.capQ || nQ >= 0xFFF0 || nP >= 0xFFF0) {  // does not fit: leave it to the dense kernel
+            if (threadIdx.x == 0) P.overflowList[atomicAdd(P.overflowCount, 1u)] = prob;
+            __syncthreads();
+            continue;
+        }
+        // ---- rank: exclusive prefix popcount over the bitmap words
+        {
+            const int per = (SL.nW + kSmThreads - 1) / kSmThreads;
+            const int w0 = threadIdx.x * per, w1 = min(w0 + per, SL.nW);
+            int sum = 0;
+            for (int k = w0; k < w1; k++) sum += __popc(qbits[k]);
+            sScan[threadIdx.x] = sum;
+            __syncthreads();
+            if (warp == 0) {  // 512 partials: 16 per lane
+                int loc[kSmThreads / 32], run = 0;
+#pragma unroll
+                for (int k = 0; k < kSmThreads / 32; k++) { loc[k] = run; run += sScan[lane * (kSmThreads / 32) + k]; }
+                int incl = run;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(MTE_FULL_MASK, incl, o); if (lane >= o) incl += v; }
+                const int excl = incl - run;
+#pragma unroll
+                for (int k = 0; k < kSmThreads / 32; k++) sScan[lane * (kSmThreads / 32) + k] = excl + loc[k];
+            }
+            __syncthreads();
+            int run = sScan[threadIdx.x];
+            for (int k = w0; k < w1; k++) { qrank[k] = (unsigned short)run; run += __popc(qbits[k]); }
+        }
+        for (int k = threadIdx.x; k < nQ; k += kSmThreads) { mateQ[k] = kFree; stampQ[k] = 0; }
+        __syncthreads();
+
+        // ---- greedy start: nearest free GT pixel (warp per predicted pixel, lanes over offsets)
+        for (int pi = warp; pi < nP; pi += kSmWarps) {
+            const int p = (int)ppix[pi];
+            const int py = p / w, px = p - py * w;
+            bool done = false, anyQ = false;
+            for (int k0 = 0; k0 < noff && !done; k0 += 32) {
+                const int k = k0 + lane;
+                bool cand = false;
+                int q = 0;
+                if (k < noff) {
+                    const short2 o = sOff[k];
+                    const int qy = py + o.y, qx = px + o.x;
+                    if (qy >= 0 && qy < h && qx >= 0 && qx < w) {
+                        q = qy * w + qx;
+                        cand = (qbits[q >> 5] >> (q & 31)) & 1u;
+                    }
+                }
+                unsigned m = __ballot_sync(MTE_FULL_MASK, cand);
+                anyQ |= m != 0;
+                while (m && !done) {
+                    const int l = __ffs(m) - 1;
+                    m &= m - 1;
+                    int ok = 0;
+                    if (lane == l) {
+                        const int qi = qid(q);
+                        ok = cas16(&mateQ[qi], kFree, (unsigned short)pi) == kFree;
+                        if (ok) mateP[pi] = (unsigned short)qi;
+                    }
+                    done = __shfl_sync(MTE_FULL_MASK, ok, l) != 0;
+                }
+            }
+            if (done && lane == 0) atomicAdd(&sMatched, 1);
+            if (!done && !anyQ && lane == 0) mateP[pi] = kDead;
+        }
+        __syncthreads();
+
+        // ---- augmenting phases
+        for (unsigned short phase = 1;; phase++) {
+            if (threadIdx.x == 0) { sCntA = 0; sEnds = 0; }
+            __syncthreads();
+            for (int base = 0; base < nP; base += kSmThreads) {
+                const int pi = base + threadIdx.x;
+                const bool fr = pi < nP && mateP[pi] == kFree;
+                const unsigned m = __ballot_sync(MTE_FULL_MASK, fr);
+                int wbase = 0;
+                if (lane == 0 && m) wbase = atomicAdd(&sCntA, __popc(m));
+                wbase = __shfl_sync(MTE_FULL_MASK, wbase, 0);
+                if (fr) fa[wbase + __popc(m & ((1u << lane) - 1))] = (unsigned short)pi;
+            }
+            __syncthreads();
+            const int nRoots = sCntA;
+            if (nRoots == 0) break;
+            if (P.stats && threadIdx.x == 0) { atomicAdd(P.stats + 0, 1u); atomicAdd(P.stats + 3, (unsigned)nRoots); }
+            // Exhaustive alternating forest, explored ASYNCHRONOUSLY: the forest only has to be a forest (every GT
+            // vertex claimed once, parent = the predicted vertex that claimed it), not a BFS layering, so the warps
+            // drain one shared work queue of predicted vertices without any CTA barrier per level.  Every vertex
+            // enters the queue at most once per phase (its mate is claimed once), so the queue never wraps.
+            for (int i = nRoots + threadIdx.x; i < nP; i += kSmThreads) fa[i] = kFree;  // unpublished slots
+            if (threadIdx.x == 0) { sHead = 0; sTail = nRoots; sPending = nRoots; }
+            __syncthreads();
+            for (;;) {
+                int my = -1;
+                if (lane == 0) {
+                    for (;;) {
+                        const int hd = *(volatile int *)&sHead, tl = *(volatile int *)&sTail;
+                        if (hd < tl) {
+                            if (atomicCAS(&sHead, hd, hd + 1) == hd) { my = hd; break; }
+                        } else if (*(volatile int *)&sPending == 0) {
+                            my = -2;
+                            break;
+                        }
+                    }
+                    if (my >= 0) {
+                        int v;
+                        while ((v = ((volatile unsigned short *)fa)[my]) == kFree) {}
+                        my = v;
+                    }
+                }
+                my = __shfl_sync(MTE_FULL_MASK, my, 0);
+                if (my == -2) break;
+                const int pi = my;
+                const int p = (int)ppix[pi];
+                const int py = p / w, px = p - py * w;
+                for (int k = lane; k < noff; k += 32) {
+                    const short2 o = sOff[k];
+                    const int qy = py + o.y, qx = px + o.x;
+                    if (qy < 0 || qy >= h || qx < 0 || qx >= w) continue;
+                    const int q = qy * w + qx;
+                    if (!((qbits[q >> 5] >> (q & 31)) & 1u)) continue;
+                    const int qi = qid(q);
+                    const unsigned short s = stampQ[qi];
+                    if (s == phase) continue;
+                    if (cas16(&stampQ[qi], s, phase) != s) continue;
+                    parentQ[qi] = (unsigned short)pi;
+                    const unsigned short mq = mateQ[qi];
+                    if (mq == kFree) {
+                        ends[atomicAdd(&sEnds, 1)] = (unsigned short)qi;
+                    } else {
+                        atomicAdd(&sPending, 1);
+                        const int slot = atomicAdd(&sTail, 1);
+                        ((volatile unsigned short *)fa)[slot] = mq;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();
+                    atomicSub(&sPending, 1);
+                    if (P.stats) atomicAdd(P.stats + 2, 1u);
+                }
+            }
+            __syncthreads();
+            const int nEnds = sEnds;
+            if (nEnds == 0) break;
+            for (int ei = threadIdx.x; ei < nEnds; ei += kSmThreads) {
+                const int qEnd = ends[ei];
+                int q = qEnd;
+                bool ok = true;
+                for (;;) {  // claim walk
+                    const int pi = parentQ[q];
+                    const unsigned short c = claimP[pi];
+                    if (c == phase || cas16(&claimP[pi], c, phase) != c) { ok = false; break; }
+                    const unsigned short mp = mateP[pi];
+                    if (mp == kFree) break;
+                    q = mp;
+                }
+                if (!ok) continue;
+                q = qEnd;
+                for (;;) {  // flip walk
+                    const int pi = parentQ[q];
+                    const unsigned short prev = mateP[pi];
+                    mateP[pi] = (unsigned short)q;
+                    mateQ[q] = (unsigned short)pi;
+                    if (prev == kFree) break;
+                    q = prev;
+                }
+                atomicAdd(&sMatched, 1);
+            }
+            __syncthreads();
+            if (phase == 0xFFF0) break;
+        }
+        __syncthreads();
+
+        // ---- results
+        const int matched = sMatched;
+        if (threadIdx.x == 0) {
+            if (P.counts) {
+                unsigned long long *c = P.counts + (size_t)t * 4;
+                atomicAdd(c + 0, (unsigned long long)matched);
+                atomicAdd(c + 1, (unsigned long long)nQ);
+                atomicAdd(c + 2, (unsigned long long)matched);
+                atomicAdd(c + 3, (unsigned long long)nP);
+            }
+            if (P.countPerProblem) P.countPerProblem[prob] = matched;
+        }
+        if (P.matchA) {
+            unsigned char *ma = P.matchA + (size_t)prob * hw;
+            for (int i = threadIdx.x; i < hw; i += kSmThreads) ma[i] = 0;
+            __syncthreads();
+            for (int pi = threadIdx.x; pi < nP; pi += kSmThreads) ma[ppix[pi]] = mateP[pi] < kDead ? 1 : 0;
+        }
+        if (P.matchB) {
+            unsigned char *mb = P.matchB + (size_t)prob * hw;
+            for (int i = threadIdx.x; i < hw; i += kSmThreads) {
+                const bool isQ = (qbits[i >> 5] >> (i & 31)) & 1u;
+                mb[i] = (isQ && mateQ[qid(i)] != kFree) ? 1 : 0;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned d = atomicAdd(P.doneCtas, 1u);
+        if (d == gridDim.x - 1) {
+            *P.nextProblem = 0u;
+            *P.doneCtas = 0u;
         }
     }
 }
@@ -359,9 +687,36 @@ static int build_offsets(double radius, OffsetTable &tb) {
 }
 
 struct Layout {
-    size_t offTable, offNeg, offThr, offArena, arenaBytes, total;
+    size_t offTable, offNeg, offThr, offOverflow, offArena, arenaBytes, total;
     int nArenas;
 };
+
+// carve the dynamic shared memory of match_smem_kernel for a w x h window; capP = capQ = 0 if it cannot fit
+static SmemLayout smem_layout(int h, int w, int budget) {
+    SmemLayout S;
+    memset(&S, 0, sizeof(S));
+    const long long hw = (long long)h * w;
+    S.nW = (int)((hw + 31) / 32);
+    const long long fixed = (long long)S.nW * 4 + (((long long)S.nW * 2 + 15) / 16) * 16 + 256;
+    const long long cap = (budget - fixed) / 20;  // 12 B per predicted vertex + 8 B per GT vertex, equal capacities
+    if (cap < 512) return S;
+    S.capP = S.capQ = (int)(cap > 0xFFF0 ? 0xFFF0 : cap) & ~7;
+    unsigned o = 0;
+    auto take = [&](unsigned bytes) { const unsigned r = o; o += (bytes + 15u) & ~15u; return r; };
+    S.oBits = take(S.nW * 4);
+    S.oRank = take(S.nW * 2);
+    S.oPpix = take(S.capP * 4);
+    S.oMateP = take(S.capP * 2);
+    S.oClaimP = take(S.capP * 2);
+    S.oFa = take(S.capP * 2);
+    S.oFb = take(S.capP * 2);
+    S.oMateQ = take(S.capQ * 2);
+    S.oParentQ = take(S.capQ * 2);
+    S.oStampQ = take(S.capQ * 2);
+    S.oEnds = take(S.capQ * 2);
+    S.total = o;
+    return S;
+}
 
 static Layout layout(int nProblems, int h, int w, int T) {
     Layout L;
@@ -369,6 +724,7 @@ static Layout layout(int nProblems, int h, int w, int T) {
     L.offTable = off; off += align_up(sizeof(short2) * 4096, 256);
     L.offNeg = off; off += align_up(sizeof(unsigned short) * 4096, 256);
     L.offThr = off; off += align_up(sizeof(double) * (size_t)(T > 0 ? T : 1), 256);
+    L.offOverflow = off; off += align_up(sizeof(int) * (size_t)(nProblems > 0 ? nProblems : 1), 256);
     L.arenaBytes = align_up(arena_bytes(h, w), 256);
     int n = kNumSMs * kCtasPerSm;
     if (n > nProblems) n = nProblems;
@@ -423,8 +779,38 @@ static int launch(MatchP &P, const Layout &L, char *ws, double max_dist, const d
     P.arena = ws + L.offArena;
     P.arenaBytes = L.arenaBytes;
     WsHeader *hdr = reinterpret_cast<WsHeader *>(ws);
+    P.truncate = getenv("MTE_MATCH_TRUNCATE") ? 1 : 0;
+    P.stats = getenv("MTE_MATCH_STATS") ? hdr->pad : nullptr;
     P.nextProblem = hdr->ticket + 4;
     P.doneCtas = hdr->ticket + 5;
+    P.overflowCount = hdr->ticket + 6;
+    P.overflowList = reinterpret_cast<int *>(ws + L.offOverflow);
+    P.problemList = nullptr;
+    P.listCount = nullptr;
+    // shared-memory kernel first (one CTA per SM, ~200 KB of state), the dense L2 kernel mops up what did not fit
+    static int smemBudget = -1;
+    if (smemBudget < 0) {
+        int dev = 0, optin = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, match_smem_kernel);
+        smemBudget = optin - (int)fa.sharedSizeBytes - 1024;
+        if (smemBudget > 0 &&
+            cudaFuncSetAttribute(match_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBudget) != cudaSuccess)
+            smemBudget = 0;
+        cudaGetLastError();
+    }
+    const SmemLayout SL = smem_layout(P.h, P.w, smemBudget);
+    const bool useSmem = SL.capP > 0 && tb.n <= kSmemTableOff && !getenv("MTE_MATCH_DENSE");
+    if (useSmem) {
+        int grid = kNumSMs;
+        if (grid > P.nProblems) grid = P.nProblems;
+        match_smem_kernel<<<grid, kSmThreads, SL.total, st>>>(P, pt, inParam ? 1 : 0, SL);
+        MTE_RETURN_IF_CUDA_ERROR();
+        P.problemList = P.overflowList;
+        P.listCount = P.overflowCount;
+    }
     match_kernel<<<L.nArenas, kThreads, 0, st>>>(P, pt, inParam ? 1 : 0);
     MTE_RETURN_IF_CUDA_ERROR();
     return MTE_OK;
