@@ -161,7 +161,7 @@ def bench_loss(args, rank, world, device):
     from mindtheedge_b200.losses import _attrs, _scales_struct, multiscale_edge_loss
 
     px_per_step = sum(B_PER_GPU * (H0 >> s) * (W0 >> s) for s in range(SCALES))
-    set_bytes = px_per_step * 20  # 3 input planes + 2 output planes, fp32
+    set_bytes = px_per_step * 21  # 3 input planes + 2 output planes fp32 + the 1-byte stash
     n_sets = max(3, int(np.ceil(400e6 / set_bytes)))  # working set >= 400 MB > 126 MB of L2
     sets = [loss_inputs(B_PER_GPU, 1000 * rank + i, device) for i in range(n_sets)]
     weights = [1.0 / SCALES] * SCALES
@@ -174,13 +174,14 @@ def bench_loss(args, rank, world, device):
             pred = [t[0] for t in sc]; edge = [t[1] for t in sc]; normal = [t[2] for t in sc]
             gmap = [torch.empty_like(e) for e in edge]
             gpred = [torch.empty_like(p) for p in pred]
-            f = _scales_struct(pred, edge, normal, None, gmap, None, weights)
-            b = _scales_struct(pred, edge, normal, None, None, gpred, weights)
+            stash = [torch.empty(e.shape, dtype=torch.uint8, device=device) for e in edge]
+            f = _scales_struct(pred, edge, normal, None, gmap, None, weights, stash)
+            b = _scales_struct(pred, edge, normal, None, gmap, gpred, weights, stash)
             losses = torch.zeros(1 + SCALES, device=device)
             ctx = torch.zeros(_lib.lib.mte_edge_loss_ctx_bytes(f, SCALES) // 4, device=device)
             ws = torch.zeros(_lib.lib.mte_edge_loss_workspace_bytes(f, SCALES), dtype=torch.uint8, device=device)
             gl = torch.zeros(1 + SCALES, device=device); gl[0] = 1.0
-            keep.append((f, b, gmap, gpred, losses, ctx, ws, gl))
+            keep.append((f, b, gmap, gpred, losses, ctx, ws, gl, stash))
 
             def step(f=f, b=b, losses=losses, ctx=ctx, ws=ws, gl=gl):
                 _lib.check(_lib.lib.mte_edge_loss_fwd(f, SCALES, C.byref(at), losses.data_ptr(), ctx.data_ptr(),
@@ -213,12 +214,12 @@ def bench_loss(args, rank, world, device):
 
     # per-kernel split (same stream, CUDA events around each launch of one replayed step, ungraphed)
     with torch.cuda.stream(stream):
-        f, b, gmap, gpred, losses, ctx, ws, gl = keep[0]
+        f, b, gmap, gpred, losses, ctx, ws, gl, _stash = keep[0]
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         tf = tb = 0.0
         reps = 10
         for r in range(reps):
-            f, b, gmap, gpred, losses, ctx, ws, gl = keep[r % n_sets]
+            f, b, gmap, gpred, losses, ctx, ws, gl, _stash = keep[r % n_sets]
             ev[0].record(stream)
             _lib.check(_lib.lib.mte_edge_loss_fwd(f, SCALES, C.byref(at), losses.data_ptr(), ctx.data_ptr(),
                                                   ws.data_ptr(), ws.numel(), stream.cuda_stream))

@@ -15,8 +15,9 @@
  *     synchronises, no global mutable state (re-entrant; one workspace per
  *     in-flight call)
  *   - `workspace` must hold at least the matching *_workspace_bytes() and its
- *     first MTE_WS_HEADER_BYTES must be zero before the FIRST use (kernels leave
- *     them zero again), see mte_workspace_init
+ *     first MTE_WS_HEADER_BYTES (64 KB: tickets, queues, the loss accumulators)
+ *     must be zero before the FIRST use (kernels leave them zero again), see
+ *     mte_workspace_init
  *   - return value: 0 = OK, < 0 = argument error (mte_error_string), > 0 =
  *     cudaError_t of the launch
  */
@@ -33,7 +34,7 @@ extern "C" {
 #define MTE_VERSION 100
 #define MTE_MAX_SCALES 4
 #define MTE_MAX_THRESHOLDS 254
-#define MTE_WS_HEADER_BYTES 256
+#define MTE_WS_HEADER_BYTES 65536
 
 typedef struct CUstream_st *mte_stream_t; /* == cudaStream_t */
 
@@ -69,6 +70,9 @@ typedef struct {
     const float *mask;   /* [B,1,H,W] validity mask, or NULL                   */
     float *grad_map;     /* out [B,1,H,W] |directional gradient| (NULL = skip) */
     float *grad_pred;    /* bwd out [B,1,h,w] d loss / d pred                  */
+    uint8_t *stash;      /* optional [B,1,H,W]: the forward records 1 byte/px (picked
+                            direction + sign of the response); a backward that is given
+                            the same stash and grad_map skips the stencil recompute   */
     int32_t B, h, w, H, W;
     float scale_weight;  /* this scale's share of the total (e.g. 0.25)        */
 } mte_loss_scale_t;

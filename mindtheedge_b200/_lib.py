@@ -9,10 +9,10 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmte.so")
+LIB_PATH = os.environ.get("MTE_LIB", os.path.join(_HERE, "libmte.so"))  # MTE_LIB: A/B builds while tuning
 
 MTE_MAX_SCALES = 4
-MTE_WS_HEADER_BYTES = 256
+MTE_WS_HEADER_BYTES = 65536
 MTE_F32, MTE_F64, MTE_U8 = 0, 1, 2
 
 
@@ -23,7 +23,7 @@ class MteError(RuntimeError):
 class LossScale(C.Structure):
     _fields_ = [
         ("pred", C.c_void_p), ("edge", C.c_void_p), ("normal", C.c_void_p), ("mask", C.c_void_p),
-        ("grad_map", C.c_void_p), ("grad_pred", C.c_void_p),
+        ("grad_map", C.c_void_p), ("grad_pred", C.c_void_p), ("stash", C.c_void_p),
         ("B", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
         ("scale_weight", C.c_float),
     ]

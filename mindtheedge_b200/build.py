@@ -17,12 +17,13 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
-LIB = os.path.join(HERE, "libmte.so")
+LIB = os.environ.get("MTE_LIB_OUT", os.path.join(HERE, "libmte.so"))  # alternate output for A/B experiments
+OBJ = OBJ if "MTE_LIB_OUT" not in os.environ else OBJ + "_alt"
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
-]
+] + os.environ.get("MTE_NVCC_DEFS", "").split()
 
 
 def sources():

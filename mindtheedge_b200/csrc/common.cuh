@@ -17,13 +17,16 @@ namespace mte {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
-// First 256 bytes of every workspace: self-resetting tickets / flags.
+// Start of every workspace: self-resetting tickets / flags (256 B), then, inside the zero-initialised 64 KB
+// header, the per-image accumulators of the edge-loss forward at kWsAccumOffset.
 struct WsHeader {
     unsigned int ticket[16];
     unsigned int flag[16];
     unsigned int pad[32];
 };
-static_assert(sizeof(WsHeader) == MTE_WS_HEADER_BYTES, "workspace header size");
+static_assert(sizeof(WsHeader) == 256, "workspace header layout");
+constexpr size_t kWsAccumOffset = 4096;
+constexpr int kWsMaxLossImages = (MTE_WS_HEADER_BYTES - 4096) / 64;  // 960 images (all scales together)
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -116,7 +116,8 @@ constexpr int kFwdCtaWaves = 2, kBwdCtaWaves = 16;
 struct Plan {
     LossP P;
     bool vec, hasNormal, hasMask, isGrad;
-    size_t offPartials, offSegsums, offResize[MTE_MAX_SCALES], offResizeDx[MTE_MAX_SCALES], total;
+    size_t offAccum, accumBytes, offResize[MTE_MAX_SCALES], offResizeDx[MTE_MAX_SCALES], total;
+    int fwdGrid;
     bool resized[MTE_MAX_SCALES];
 };
 
@@ -136,6 +137,15 @@ static int validate(const mte_loss_scale_t *sc, int n) {
 }
 
 // Lay out CTAs / workspace.  bwd == true uses the overlapped 30-lane strips.
+static bool can_use_stash(const mte_loss_scale_t *sc, int n, const mte_loss_attrs_t *at) {
+    if (!at || !at->is_grad || getenv("MTE_LOSS_NO_STASH")) return false;
+    for (int i = 0; i < n; i++) {
+        if (!sc[i].stash || !sc[i].grad_map || !sc[i].normal) return false;
+        if (sc[i].h != sc[i].H || sc[i].w != sc[i].W) return false;
+    }
+    return true;
+}
+
 static int make_plan(Plan &pl, const mte_loss_scale_t *sc, int n, const mte_loss_attrs_t *at, bool bwd) {
     int rc = validate(sc, n);
     if (rc) return rc;
@@ -151,23 +161,28 @@ static int make_plan(Plan &pl, const mte_loss_scale_t *sc, int n, const mte_loss
         const void *ptrs[] = {sc[i].edge, sc[i].normal, sc[i].mask, sc[i].grad_map};
         for (const void *p : ptrs)
             if (!aligned16(p)) pl.vec = false;
+        if (reinterpret_cast<uintptr_t>(sc[i].stash) & 3u) pl.vec = false;
         const bool rs = sc[i].h != sc[i].H || sc[i].w != sc[i].W;
         if (!rs && (!aligned16(sc[i].pred) || (bwd && !aligned16(sc[i].grad_pred)))) pl.vec = false;
     }
     const int VEC = pl.vec ? 4 : 1;
     const int RH = bwd ? kBwdRH : kFwdRH;
-    const int lanesOut = !pl.isGrad ? 32 : (bwd ? bwd_lanes(VEC) : kHaloLanes);
-    int cta = 0, img = 0;
+    const bool stashBwd = bwd && can_use_stash(sc, n, at);
+    const int lanesOut = !pl.isGrad ? 32 : ((bwd && !stashBwd) ? bwd_lanes(VEC) : kHaloLanes);
+    int cta = 0, img = 0, itemBase = 0;
     for (int i = 0; i < n; i++) {
         ScaleP &S = P.s[i];
         S.B = sc[i].B; S.H = sc[i].H; S.W = sc[i].W;
         S.e = sc[i].edge; S.n = sc[i].normal; S.m = sc[i].mask; S.g = sc[i].grad_map; S.dx = sc[i].grad_pred;
+        S.stash = sc[i].stash;
         S.x = sc[i].pred;
         S.strips = ceil_div(S.W, lanesOut * VEC);
         S.rowBlocks = ceil_div(S.H, RH);
         S.items = S.strips * S.rowBlocks;
         S.ctasPerImage = ceil_div(S.items, kWarps);  // capped below: warps loop over several items
         S.ctaBase = cta; S.imgBase = img;
+        S.itemBase = itemBase;
+        itemBase += S.items * S.B;
         S.scaleWeight = sc[i].scale_weight;
         cta += S.ctasPerImage * S.B;
         img += S.B;
@@ -192,18 +207,19 @@ static int make_plan(Plan &pl, const mte_loss_scale_t *sc, int n, const mte_loss
         }
     }
     P.nScales = n; P.totalCtas = cta; P.totalImages = img;
+    P.totalItems = itemBase;
+    // forward: persistent CTAs (2 per SM) pulling items from the atomic queue; never more warps than items
+    pl.fwdGrid = kNumSMs * 2;
+    if (pl.fwdGrid * kWarps > itemBase) pl.fwdGrid = ceil_div(itemBase, kWarps);
     if (at) {
         P.T = at->sigmoid_thresh; P.weight = at->weight; P.p2n = at->pos_to_neg;
     }
     size_t off = MTE_WS_HEADER_BYTES;
-    // forward partial layout is what sizes the workspace (bwd uses none of it)
-    int fwdCtas = 0;
-    for (int i = 0; i < n; i++) {
-        const int items = ceil_div(sc[i].W, kHaloLanes) * ceil_div(sc[i].H, kFwdRH);  // upper bound (VEC=1)
-        fwdCtas += ceil_div(items, kWarps) * sc[i].B;
-    }
-    pl.offPartials = off; off += align_up((size_t)fwdCtas * kAcc * sizeof(double), 256);
-    pl.offSegsums = off; off += align_up((size_t)img * kAcc * sizeof(double), 256);
+    // forward: the per-image fixed-point accumulators live in the zero-initialised workspace header and are left
+    // zero by the kernel (no memset node per launch)
+    pl.offAccum = kWsAccumOffset;
+    pl.accumBytes = (size_t)img * kAcc * sizeof(unsigned long long);
+    if (img > kWsMaxLossImages) return MTE_ERR_SHAPE;
     for (int i = 0; i < n; i++) {
         const size_t planeBytes = align_up((size_t)sc[i].B * sc[i].H * sc[i].W * sizeof(float), 256);
         pl.offResize[i] = off;
@@ -244,9 +260,9 @@ extern "C" int mte_edge_loss_fwd(const mte_loss_scale_t *sc, int n, const mte_lo
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     char *w = static_cast<char *>(ws);
     LossP &P = pl.P;
-    P.partials = reinterpret_cast<double *>(w + pl.offPartials);
-    P.segsums = reinterpret_cast<double *>(w + pl.offSegsums);
+    P.accum = reinterpret_cast<unsigned long long *>(w + pl.offAccum);
     P.ticket = reinterpret_cast<WsHeader *>(w)->ticket;
+    P.totalCtas = pl.fwdGrid;
     P.lossOut = loss_out;
     P.ctx = static_cast<float *>(ctx);
     for (int i = 0; i < n; i++) {
@@ -306,7 +322,10 @@ extern "C" int mte_edge_loss_bwd(const mte_loss_scale_t *sc, int n, const mte_lo
             edge_loss_bwd_pointwise_kernel<false><<<kNumSMs * 8, kThreads, 0, st>>>(P, at->is_sigmoid, at->pred_is_inverse);
     } else {
         const int mode = pl.hasNormal ? MODE_DIR : MODE_MAG;
-        if (pl.vec) launch_bwd_v4(P, mode, pl.hasMask, at->pred_is_inverse != 0, at->is_sigmoid != 0, st);
+        if (can_use_stash(sc, n, at)) {
+            if (pl.vec) launch_bwd_stash_v4(P, pl.hasMask, at->pred_is_inverse != 0, at->is_sigmoid != 0, st);
+            else launch_bwd_stash_v1(P, pl.hasMask, at->pred_is_inverse != 0, at->is_sigmoid != 0, st);
+        } else if (pl.vec) launch_bwd_v4(P, mode, pl.hasMask, at->pred_is_inverse != 0, at->is_sigmoid != 0, st);
         else launch_bwd_v1(P, mode, pl.hasMask, at->pred_is_inverse != 0, at->is_sigmoid != 0, st);
     }
     MTE_RETURN_IF_CUDA_ERROR();

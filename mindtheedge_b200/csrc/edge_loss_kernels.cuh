@@ -27,7 +27,13 @@ enum { A_WP = 0, A_WN, A_SPU, A_SNU, A_SPM, A_SNM, A_SUMM, A_FLAGS };
 enum { F_HAS0 = 1u, F_HAS1 = 2u, F_OTHER = 4u };
 enum { MODE_NONE = 0, MODE_MAG = 1, MODE_DIR = 2 };
 
-constexpr int kFwdRH = 4;   // output rows per forward work item
+#ifndef MTE_FWD_MINB
+#define MTE_FWD_MINB 2
+#endif
+#ifndef MTE_FWD_RH
+#define MTE_FWD_RH 6
+#endif
+constexpr int kFwdRH = MTE_FWD_RH;   // output rows per forward work item
 constexpr int kBwdRH = 8;   // output rows per backward work item
 constexpr int kHaloLanes = 30;  // writing lanes of an overlapped strip (one halo lane per side)
 // The backward needs the coefficient of the neighbouring pixel, i.e. depth two columns out: with
@@ -41,9 +47,11 @@ constexpr float kLn2 = 0.6931471805599453f;
 struct ScaleP {
     const float *x, *e, *n, *m;
     float *g, *dx;
+    unsigned char *stash;  // 1 B/px: bits 0-1 picked direction, bits 2-3 sign of the response (1:+ 2:- 0:zero)
     int B, H, W;
     int strips, rowBlocks, items, ctasPerImage;
     int ctaBase, imgBase;
+    int itemBase;  // forward: first work item of this scale in the global (dynamically scheduled) item queue
     float scaleWeight;
 };
 
@@ -51,9 +59,9 @@ struct LossP {
     ScaleP s[MTE_MAX_SCALES];
     int nScales, totalCtas, totalImages;
     float T, weight, p2n;
-    double *partials;       // [totalCtas][kAcc]
-    double *segsums;        // [totalImages][kAcc]
-    unsigned *ticket;
+    int totalItems;                // forward work items over all scales and images
+    unsigned long long *accum;     // forward: [totalImages][kAcc] fixed-point (2^32) per-image sums, zero at launch
+    unsigned *ticket;              // forward: dynamic item counter; [1]: finished-warp counter (both self-resetting)
     float *lossOut;         // [1+nScales]
     float *ctx;             // [totalImages] alpha, then per scale {coef, maskBinary}
     const float *gradLoss;  // bwd: [1+nScales]
@@ -114,6 +122,18 @@ struct Row {
     __device__ __forceinline__ float at(int v) const { return v < 0 ? l : (v >= VEC ? r : c[v]); }
 };
 
+// Unchecked flavour for work items that lie completely inside the image (the common case): no predicates.
+template <int VEC>
+__device__ __forceinline__ void load_vec_in(float (&out)[VEC], const float *img, int row, int W, int col0, bool cached) {
+    const float *p = img + (size_t)row * W + col0;
+    if (VEC == 4) {
+        const float4 v = cached ? ld_cached4(p) : ld_stream4(p);
+        out[0] = v.x; out[1 % VEC] = v.y; out[2 % VEC] = v.z; out[3 % VEC] = v.w;
+    } else {
+        out[0] = cached ? __ldg(p) : __ldcs(p);
+    }
+}
+
 template <int VEC>
 __device__ __forceinline__ void load_vec(float (&out)[VEC], const float *img, int row, int H, int W, int col0,
                                          bool cached) {
@@ -138,6 +158,14 @@ __device__ __forceinline__ void load_row(Row<VEC> &R, const float *img, int row,
         const bool ok = (row >= 0) && (row < H) && (col0 >= 0) && (col0 < W);
 #pragma unroll
         for (int v = 0; v < VEC; v++) R.c[v] = ok ? inv_to_depth(R.c[v]) : 0.f;
+    }
+}
+template <int VEC, bool INV>
+__device__ __forceinline__ void load_row_in(Row<VEC> &R, const float *img, int row, int W, int col0) {
+    load_vec_in<VEC>(R.c, img, row, W, col0, true);
+    if (INV) {
+#pragma unroll
+        for (int v = 0; v < VEC; v++) R.c[v] = inv_to_depth(R.c[v]);
     }
 }
 // Horizontal neighbours across the lane boundary (lanes 0 / 31 get don't-care values: they are halo lanes).
@@ -170,205 +198,257 @@ __device__ __forceinline__ float pick_response(int k, float P, float R, float Dm
 // ---------------------------------------------------------------------------
 // Forward
 // ---------------------------------------------------------------------------
+// Persistent warps pull work items (a 32-lane strip x RH rows of one image) from one global atomic queue, biggest
+// scale first, so the tail is one item long whatever the shape.  An item streams its rows through a 3-row register
+// window with a PD-row prefetch ring.  Its partial sums are reduced in the warp (fixed order) and added to
+// per-image 2^32 fixed-point int64 accumulators with integer atomics: the result does not depend on the order in
+// which items finish, so the loss is bit-reproducible without any per-CTA partial buffer or barrier.  The last warp
+// to finish (atomic counter) folds the per-image sums into alpha and the loss.
+constexpr double kFix = 4294967296.0;  // 2^32
+
 static __device__ __noinline__ void finalize_loss(const LossP &P, bool hasMask) {
-    // Run by every thread of the LAST CTA.  Fixed summation order => reproducible.
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Run by ONE warp (the last to finish).  lane <-> image (strided); fixed shuffle order => reproducible.
+    const int lane = threadIdx.x & 31;
+    double total = 0.0;
     for (int si = 0; si < P.nScales; si++) {
         const ScaleP &S = P.s[si];
-        for (int b = warp; b < S.B; b += kWarps) {
-            double a[kAcc];
-            unsigned fl = 0;
+        const double npix = (double)S.H * (double)S.W;
+        unsigned fl = 0;
+        double wnAll = 0.0, sumM = 0.0;
+        for (int b = lane; b < S.B; b += 32) {
+            const unsigned long long *o = P.accum + (size_t)(S.imgBase + b) * kAcc;
+            unsigned long long v[kAcc];
 #pragma unroll
-            for (int k = 0; k < kAcc; k++) a[k] = 0.0;
-            const double *base = P.partials + (size_t)(S.ctaBase + b * S.ctasPerImage) * kAcc;
-            for (int c = lane; c < S.ctasPerImage; c += 32) {
-                const double *q = base + (size_t)c * kAcc;
-#pragma unroll
-                for (int k = 0; k < kAcc - 1; k++) a[k] += __ldcg(q + k);
-                fl |= (unsigned)__ldcg(q + A_FLAGS);
-            }
-#pragma unroll
-            for (int k = 0; k < kAcc - 1; k++) a[k] = warp_sum(a[k]);
-            fl = warp_or(fl);
-            if (lane == 0) {
-                double *o = P.segsums + (size_t)(S.imgBase + b) * kAcc;
-#pragma unroll
-                for (int k = 0; k < kAcc - 1; k++) o[k] = a[k];
-                o[A_FLAGS] = (double)fl;
-            }
+            for (int k = 0; k < kAcc; k++) v[k] = __ldcg(o + k);  // one round trip
+            fl |= (unsigned)v[A_FLAGS];
+            const double wp = (double)(long long)v[A_WP] / kFix;
+            wnAll += hasMask ? (double)(long long)v[A_WN] / kFix : (npix - wp);
+            sumM += (double)(long long)v[A_SUMM] / kFix;
         }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double total = 0.0;
-        for (int si = 0; si < P.nScales; si++) {
-            const ScaleP &S = P.s[si];
-            const double npix = (double)S.H * (double)S.W;
-            unsigned fl = 0;
-            double wnAll = 0.0, sumM = 0.0;
-            for (int b = 0; b < S.B; b++) {
-                const double *o = P.segsums + (size_t)(S.imgBase + b) * kAcc;
-                fl |= (unsigned)o[A_FLAGS];
-                wnAll += hasMask ? o[A_WN] : (npix - o[A_WP]);
-                sumM += o[A_SUMM];
-            }
-            // grad_loss.py:183-187: the mask only masks when its value set is exactly {0,1}
-            const bool binary = hasMask && fl == (F_HAS0 | F_HAS1);
-            const double valid = binary ? sumM : npix * (double)S.B;
-            double acc = 0.0;
-            for (int b = 0; b < S.B; b++) {
-                const double *o = P.segsums + (size_t)(S.imgBase + b) * kAcc;
-                const double wp = o[A_WP];
-                const double wn = hasMask ? o[A_WN] : (npix - wp);
-                const float alpha = (wnAll == 0.0) ? 1.0f : (float)(wn / (wp + wn));  // grad_loss.py:175-178
-                const double sp = (double)kLn2 * (binary ? o[A_SPM] : o[A_SPU]);
-                const double sn = (double)kLn2 * (binary ? o[A_SNM] : o[A_SNU]);
-                acc += -(double)P.p2n * (double)alpha * sp - (1.0 - (double)alpha) * sn;
-                P.ctx[S.imgBase + b] = alpha;
-            }
-            const double lossS = (double)P.weight * (acc / valid);
+        fl = warp_or(fl);
+        wnAll = warp_sum(wnAll);
+        sumM = warp_sum(sumM);
+        // grad_loss.py:183-187: the mask only masks when its value set is exactly {0,1}
+        const bool binary = hasMask && fl == (F_HAS0 | F_HAS1);
+        const double valid = binary ? sumM : npix * (double)S.B;
+        double acc = 0.0;
+        for (int b = lane; b < S.B; b += 32) {
+            unsigned long long *o = P.accum + (size_t)(S.imgBase + b) * kAcc;
+            unsigned long long v[kAcc];
+#pragma unroll
+            for (int k = 0; k < kAcc; k++) v[k] = __ldcg(o + k);
+            const double wp = (double)(long long)v[A_WP] / kFix;
+            const double wn = hasMask ? (double)(long long)v[A_WN] / kFix : (npix - wp);
+            const float alpha = (wnAll == 0.0) ? 1.0f : (float)(wn / (wp + wn));  // grad_loss.py:175-178
+            const double sp = (double)kLn2 * ((double)(long long)(binary ? v[A_SPM] : v[A_SPU]) / kFix);
+            const double sn = (double)kLn2 * ((double)(long long)(binary ? v[A_SNM] : v[A_SNU]) / kFix);
+            acc += -(double)P.p2n * (double)alpha * sp - (1.0 - (double)alpha) * sn;
+            P.ctx[S.imgBase + b] = alpha;
+#pragma unroll
+            for (int k = 0; k < kAcc; k++) o[k] = 0ull;  // leave the accumulators clean
+        }
+        acc = warp_sum(acc);
+        const double lossS = (double)P.weight * (acc / valid);
+        if (lane == 0) {
             P.lossOut[1 + si] = (float)lossS;
             P.ctx[P.totalImages + 2 * si] = (float)((double)P.weight / valid);
             P.ctx[P.totalImages + 2 * si + 1] = binary ? 1.0f : 0.0f;
-            total += (double)S.scaleWeight * lossS;
         }
+        total += (double)S.scaleWeight * lossS;
+    }
+    if (lane == 0) {
         P.lossOut[0] = (float)total;
-        *P.ticket = 0u;  // leave the workspace header clean for the next launch
+        P.ticket[0] = 0u;  // leave the workspace header clean for the next launch
+        P.ticket[1] = 0u;
+    }
+}
+
+// per-pixel loss terms of one output row.  okf = 1 inside the image, 0 outside (edge and mask planes are loaded as 0
+// there, so only the "1 - e" term needs it); halo lanes are discarded once per item by the caller.
+template <int VEC, int MODE, bool MASK, bool SIG>
+__device__ __forceinline__ void fwd_row(const LossP &P, const ScaleP &S, size_t plane, int row, int col0, bool ok,
+                                        const Row<VEC> &up, const Row<VEC> &mid, const Row<VEC> &dn,
+                                        const float (&e)[VEC], const float (&th)[VEC], const float (&m)[VEC],
+                                        float (&la)[kAcc - 1], unsigned &lflags) {
+    const float okf = ok ? 1.f : 0.f;
+    float g[VEC];
+    unsigned code[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; v++) {
+        code[v] = 0u;
+        if (MODE == MODE_NONE) {
+            g[v] = mid.c[v];
+        } else {
+            float sP, sR, sDm, sdv;
+            stencil_parts<VEC>(up, mid, dn, v, sP, sR, sDm, sdv);
+            if (MODE == MODE_MAG) {
+                const float cv = sP + sdv, ch = sR + sDm;
+                g[v] = sqrtf(cv * cv + ch * ch + 1e-6f);
+            } else {
+                const int di = dir_index(th[v]);
+                const float c = pick_response(di, sP, sR, sDm, sdv);
+                g[v] = fabsf(c);
+                code[v] = (unsigned)di | (c > 0.f ? 4u : 0u) | (c < 0.f ? 8u : 0u);
+            }
+        }
+        const float p = SIG ? sigmoid_fast(g[v] - P.T) : g[v];
+        const float ee = e[v];
+        const float ne = okf - ee;
+        const float lp = __log2f(p + kEps);
+        const float ln = __log2f((1.0f - p) + kEps);
+        la[A_SPU] = fmaf(ee, lp, la[A_SPU]);
+        la[A_SNU] = fmaf(ne, ln, la[A_SNU]);
+        if (MASK) {
+            const float mm = m[v];
+            la[A_WP] = fmaf(ee, mm, la[A_WP]);
+            la[A_WN] = fmaf(ne, mm, la[A_WN]);
+            la[A_SUMM] += mm;
+            const bool keep = mm != 0.f;
+            la[A_SPM] += keep ? ee * lp : 0.f;
+            la[A_SNM] += keep ? ne * ln : 0.f;
+            const unsigned f = (mm == 0.f) ? F_HAS0 : ((mm == 1.f) ? F_HAS1 : F_OTHER);
+            lflags |= ok ? f : 0u;
+        } else {
+            la[A_WP] += ee;
+        }
+    }
+    if (ok) {
+        const size_t o = plane + (size_t)row * S.W + col0;
+        if (S.g != nullptr) {
+            if (VEC == 4) st_stream4(S.g + o, make_float4(g[0], g[1 % VEC], g[2 % VEC], g[3 % VEC]));
+            else __stcs(S.g + o, g[0]);
+        }
+        if (MODE == MODE_DIR && S.stash != nullptr) {
+            if (VEC == 4)
+                __stcs(reinterpret_cast<unsigned *>(S.stash + o),
+                       code[0] | (code[1 % VEC] << 8) | (code[2 % VEC] << 16) | (code[3 % VEC] << 24));
+            else
+                __stcs(S.stash + o, (unsigned char)code[0]);
+        }
+    }
+}
+
+// One forward work item: RH output rows of a 32-lane strip, streamed through a 3-row register window with a 3-row
+// prefetch ring.  The row loop is unrolled by 3 only (window and ring indices become static); unrolling all RH rows
+// made the kernel ~100 KB of SASS and instruction-cache misses its top stall (profiles/r01_notes.md).
+template <int VEC, int MODE, bool MASK, bool INV, bool SIG>
+__device__ __forceinline__ void fwd_item(const LossP &P, const ScaleP &S, int img, int row0, int colFirst, int lane,
+                                         float (&la)[kAcc - 1], unsigned &lflags) {
+    constexpr int RH = kFwdRH;
+    constexpr int PD = 3;
+    static_assert(RH % 3 == 0, "row loop is unrolled by the window size");
+    constexpr int OFF = (MODE == MODE_NONE) ? 0 : 1;
+    const int H = S.H, W = S.W;
+    const int col0 = colFirst + lane * VEC;
+    const size_t plane = (size_t)img * H * W;
+    const float *x = S.x + plane;
+    const bool writer = (MODE == MODE_NONE) || (lane >= 1 && lane <= kHaloLanes);
+    const bool colOk = writer && col0 >= 0 && col0 < W;
+
+    Row<VEC> xr[3];   // depth window: xr[d % 3] holds depth row index d (image row row0 - OFF + d)
+    Row<VEC> pfx[PD];
+    float pfe[PD][VEC], pft[PD][VEC], pfm[PD][VEC];
+    auto fetch = [&](int slot, int j) {  // everything output row j needs that is not in the window yet
+        load_row<VEC, INV>(pfx[slot], x, row0 + j + OFF, H, W, col0);
+        load_vec<VEC>(pfe[slot], S.e + plane, row0 + j, H, W, col0, false);
+        if (MODE == MODE_DIR) load_vec<VEC>(pft[slot], S.n + plane, row0 + j, H, W, col0, false);
+        if (MASK) load_vec<VEC>(pfm[slot], S.m + plane, row0 + j, H, W, col0, false);
+    };
+    if (MODE != MODE_NONE) {
+        load_row<VEC, INV>(xr[0], x, row0 - 1, H, W, col0);
+        load_row<VEC, INV>(xr[1], x, row0, H, W, col0);
+    }
+#pragma unroll
+    for (int k = 0; k < PD; k++) fetch(k, k);
+    if (MODE != MODE_NONE) {
+        exchange_row<VEC>(xr[0]);
+        exchange_row<VEC>(xr[1]);
+    }
+#pragma unroll 1
+    for (int jj = 0; jj < RH; jj += 3) {
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const int j = jj + u;
+            float e[VEC], th[VEC], m[VEC];
+            Row<VEC> &newest = xr[(MODE == MODE_NONE) ? 0 : (u + 2) % 3];
+            newest = pfx[u];
+#pragma unroll
+            for (int v = 0; v < VEC; v++) {
+                e[v] = pfe[u][v];
+                th[v] = (MODE == MODE_DIR) ? pft[u][v] : 0.f;
+                m[v] = MASK ? pfm[u][v] : 1.f;
+            }
+            if (j + PD < RH) fetch(u, j + PD);
+            if (MODE != MODE_NONE) exchange_row<VEC>(newest);
+            const int row = row0 + j;
+            const bool ok = colOk && row < H;
+            if (MODE == MODE_NONE)
+                fwd_row<VEC, MODE, MASK, SIG>(P, S, plane, row, col0, ok, xr[0], xr[0], xr[0], e, th, m, la, lflags);
+            else
+                fwd_row<VEC, MODE, MASK, SIG>(P, S, plane, row, col0, ok, xr[u % 3], xr[(u + 1) % 3], xr[(u + 2) % 3], e,
+                                              th, m, la, lflags);
+        }
+    }
+    if (!writer) {  // halo lanes: discard (select, no NaN propagation)
+#pragma unroll
+        for (int k = 0; k < kAcc - 1; k++) la[k] = 0.f;
     }
 }
 
 template <int VEC, int MODE, bool MASK, bool INV, bool SIG>
-__global__ void __launch_bounds__(kThreads, 2) edge_loss_fwd_kernel(const __grid_constant__ LossP P) {
+__global__ void __launch_bounds__(kThreads, MTE_FWD_MINB) edge_loss_fwd_kernel(const __grid_constant__ LossP P) {
     constexpr int RH = kFwdRH;
     constexpr int LANES = (MODE == MODE_NONE) ? 32 : kHaloLanes;
     constexpr int OFF = (MODE == MODE_NONE) ? 0 : 1;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int si = 0;
+    const int lane = threadIdx.x & 31;
+    int item = 0;
+    if (lane == 0) item = (int)atomicAdd(P.ticket, 1u);
+    item = __shfl_sync(MTE_FULL_MASK, item, 0);
+    while (item < P.totalItems) {
+        // claim the next item now: the atomic's round trip hides behind this item's work
+        int next = 0;
+        if (lane == 0) next = (int)atomicAdd(P.ticket, 1u);
+        int si = 0;
 #pragma unroll
-    for (int k = 1; k < MTE_MAX_SCALES; k++)
-        if (k < P.nScales && (int)blockIdx.x >= P.s[k].ctaBase) si = k;
-    const ScaleP &S = P.s[si];
-    const int local = blockIdx.x - S.ctaBase;
-    const int img = local / S.ctasPerImage;
-    const int item0 = (local - img * S.ctasPerImage) * kWarps + warp;
-
-    float acc[kAcc - 1];
-#pragma unroll
-    for (int k = 0; k < kAcc - 1; k++) acc[k] = 0.f;
-    unsigned flags = 0;
-
-    // a warp walks the items of its image with stride ctasPerImage*kWarps (warp-uniform trip count)
-    for (int item = item0; item < S.items; item += S.ctasPerImage * kWarps) {
-        const int H = S.H, W = S.W;
-        const int strip = item / S.rowBlocks;  // vertically adjacent row blocks share a CTA (L1 halo reuse)
-        const int rb = item - strip * S.rowBlocks;
+        for (int k = 1; k < MTE_MAX_SCALES; k++)
+            if (k < P.nScales && item >= P.s[k].itemBase) si = k;
+        const ScaleP &S = P.s[si];
+        const int local = item - S.itemBase;
+        const int img = local / S.items;
+        const int it = local - img * S.items;
+        const int strip = it / S.rowBlocks;
+        const int rb = it - strip * S.rowBlocks;
         const int row0 = rb * RH;
-        const int col0 = (strip * LANES + lane - OFF) * VEC;
-        const size_t plane = (size_t)img * H * W;
-        const float *x = S.x + plane;
-        const bool writer = (MODE == MODE_NONE) || (lane >= 1 && lane <= kHaloLanes);
-        const bool colOk = writer && col0 >= 0 && col0 < W;
-
-        constexpr int NR = (MODE == MODE_NONE) ? RH : RH + 2;
-        Row<VEC> rows[NR];
-        float e[RH][VEC], th[RH][VEC], m[RH][VEC];
-        // every load of the item is issued before the first use
+        const int colFirst = (strip * LANES - OFF) * VEC;  // column of lane 0
+        float la[kAcc - 1];
 #pragma unroll
-        for (int r = 0; r < NR; r++) load_row<VEC, INV>(rows[r], x, row0 - OFF + r, H, W, col0);
+        for (int k = 0; k < kAcc - 1; k++) la[k] = 0.f;
+        unsigned lflags = 0;
+        fwd_item<VEC, MODE, MASK, INV, SIG>(P, S, img, row0, colFirst, lane, la, lflags);
+        // order-independent accumulation: warp tree (fixed) -> 2^32 fixed point -> integer atomics
+        unsigned long long *acc = P.accum + (size_t)(S.imgBase + img) * kAcc;
 #pragma unroll
-        for (int r = 0; r < RH; r++) {
-            load_vec<VEC>(e[r], S.e + plane, row0 + r, H, W, col0, false);
-            if (MODE == MODE_DIR) load_vec<VEC>(th[r], S.n + plane, row0 + r, H, W, col0, false);
-            if (MASK) load_vec<VEC>(m[r], S.m + plane, row0 + r, H, W, col0, false);
-        }
-        if (MODE != MODE_NONE) {
-#pragma unroll
-            for (int r = 0; r < NR; r++) exchange_row<VEC>(rows[r]);
-        }
-#pragma unroll
-        for (int r = 0; r < RH; r++) {
-            const int row = row0 + r;
-            const bool ok = colOk && row < H;
-            const float okf = ok ? 1.f : 0.f;
-            float g[VEC];
-#pragma unroll
-            for (int v = 0; v < VEC; v++) {
-                if (MODE == MODE_NONE) {
-                    g[v] = rows[r].c[v];
-                } else {
-                    float sP, sR, sDm, sdv;
-                    stencil_parts<VEC>(rows[r], rows[r + 1], rows[r + 2], v, sP, sR, sDm, sdv);
-                    if (MODE == MODE_MAG) {
-                        const float cv = sP + sdv, ch = sR + sDm;
-                        g[v] = sqrtf(cv * cv + ch * ch + 1e-6f);
-                    } else {
-                        g[v] = fabsf(pick_response(dir_index(th[r][v]), sP, sR, sDm, sdv));
-                    }
-                }
-                const float p = SIG ? sigmoid_fast(g[v] - P.T) : g[v];
-                const float ee = okf * e[r][v];
-                const float ne = okf - ee;
-                float lp = __log2f(p + kEps);
-                float ln = __log2f((1.0f - p) + kEps);
-                if (!ok) { lp = 0.f; ln = 0.f; }  // select: halo lanes may hold garbage neighbours
-                acc[A_SPU] = fmaf(ee, lp, acc[A_SPU]);
-                acc[A_SNU] = fmaf(ne, ln, acc[A_SNU]);
-                if (MASK) {
-                    const float mm = okf * m[r][v];
-                    acc[A_WP] = fmaf(ee, mm, acc[A_WP]);
-                    acc[A_WN] = fmaf(ne, mm, acc[A_WN]);
-                    acc[A_SUMM] += mm;
-                    const bool keep = m[r][v] != 0.f;
-                    acc[A_SPM] += keep ? ee * lp : 0.f;
-                    acc[A_SNM] += keep ? ne * ln : 0.f;
-                    const unsigned f = (m[r][v] == 0.f) ? F_HAS0 : ((m[r][v] == 1.f) ? F_HAS1 : F_OTHER);
-                    flags |= ok ? f : 0u;
-                } else {
-                    acc[A_WP] += ee;
-                }
-            }
-            if (S.g != nullptr && ok) {
-                float *gp = S.g + plane + (size_t)row * W + col0;
-                if (VEC == 4) st_stream4(gp, make_float4(g[0], g[1 % VEC], g[2 % VEC], g[3 % VEC]));
-                else __stcs(gp, g[0]);
+        for (int k = 0; k < kAcc - 1; k++) {
+            if (MASK || k == A_WP || k == A_SPU || k == A_SNU) {
+                const float v = warp_sum(la[k]);
+                if (lane == 0) atomicAdd(acc + k, (unsigned long long)__double2ll_rn((double)v * kFix));
             }
         }
+        if (MASK) {
+            lflags = warp_or(lflags);
+            if (lane == 0 && lflags) atomicOr(acc + A_FLAGS, (unsigned long long)lflags);
+        }
+        item = __shfl_sync(MTE_FULL_MASK, next, 0);
     }
-
-    // warp -> CTA -> one fp64 partial row per CTA
-    __shared__ float sAcc[kWarps][kAcc];
-#pragma unroll
-    for (int k = 0; k < kAcc - 1; k++)
-        if (MASK || k == A_WP || k == A_SPU || k == A_SNU) acc[k] = warp_sum(acc[k]);
-    if (MASK) flags = warp_or(flags);
+    // the last warp to leave finalises
+    int last = 0;
     if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < kAcc - 1; k++) sAcc[warp][k] = acc[k];
-        sAcc[warp][A_FLAGS] = __uint_as_float(flags);
+        __threadfence();
+        const unsigned t = atomicAdd(P.ticket + 1, 1u);
+        last = (t == gridDim.x * kWarps - 1u);
     }
-    __syncthreads();
-    __shared__ bool sLast;
-    if (threadIdx.x < kAcc) {
-        const int k = threadIdx.x;
-        double v;
-        if (k == A_FLAGS) {
-            unsigned f = 0;
-            for (int w = 0; w < kWarps; w++) f |= __float_as_uint(sAcc[w][k]);
-            v = (double)f;
-        } else {
-            v = 0.0;
-            for (int w = 0; w < kWarps; w++) v += (double)sAcc[w][k];
-        }
-        __stcg(P.partials + (size_t)blockIdx.x * kAcc + k, v);
-        __threadfence();  // only the writers fence; the ticket below is taken after the barrier
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned t = atomicAdd(P.ticket, 1u);
-        sLast = (t == (unsigned)P.totalCtas - 1u);
-    }
-    __syncthreads();
-    if (sLast) {
+    last = __shfl_sync(MTE_FULL_MASK, last, 0);
+    if (last) {
         __threadfence();
         finalize_loss(P, MASK);
     }
@@ -558,11 +638,150 @@ __global__ void __launch_bounds__(kThreads, 2) edge_loss_bwd_kernel(const __grid
     }  // item loop
 }
 
+// ---------------------------------------------------------------------------
+// Backward from the stash (MODE_DIR only): the forward left |c| (the grad map, an output anyway) and one byte
+// per pixel (direction + sign), so the backward needs neither the 3x3 stencil nor the normals: per pixel it
+// recomputes p = sigmoid(g - T) the reference-faithful way, d loss/d g, looks the four adjoint coefficients up
+// in a 16-entry shared-memory table and scatters them into three rolling output rows.
+// Traffic: g 4 + edge 4 + stash 1 (+ inverse depth 4 when fused) in, gradient 4 out.
+// ---------------------------------------------------------------------------
+template <int VEC, bool MASK, bool INV, bool SIG>
+__global__ void __launch_bounds__(kThreads, 2) edge_loss_bwd_stash_kernel(const __grid_constant__ LossP P) {
+    constexpr int RH = kBwdRH;
+    constexpr int PD = 3;
+    __shared__ float4 sLut[16];  // per code: (A, C, A2, C2) for s = 1
+    if (threadIdx.x < 16) {
+        const int di = threadIdx.x & 3, sg = threadIdx.x >> 2;
+        const float sgn = sg == 1 ? 1.f : (sg == 2 ? -1.f : 0.f);
+        const float a = (di == 2 || di == 3) ? 1.f : (di == 1 ? -1.f : 0.f);  // h:0 rl:-1 v:1 lr:1
+        const float c = (di == 2) ? 0.f : 1.f;                                // h:1 rl:1 v:0 lr:1
+        const float bb = (di & 1) ? 1.f : 2.f;                                // axis stencils weigh the centre twice
+        sLut[threadIdx.x] = make_float4(sgn * a, sgn * c, sgn * a * bb, sgn * c * bb);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int si = 0;
+#pragma unroll
+    for (int k = 1; k < MTE_MAX_SCALES; k++)
+        if (k < P.nScales && (int)blockIdx.x >= P.s[k].ctaBase) si = k;
+    const ScaleP &S = P.s[si];
+    const int local = blockIdx.x - S.ctaBase;
+    const int img = local / S.ctasPerImage;
+    const int item0 = (local - img * S.ctasPerImage) * kWarps + warp;
+    const int H = S.H, W = S.W;
+    constexpr int HALO = bwd_halo(VEC), LANES = bwd_lanes(VEC);
+    (void)HALO;
+
+    BwdImg I;
+    {
+        const float G = __ldg(P.gradLoss) * S.scaleWeight + __ldg(P.gradLoss + 1 + si);
+        const float coef = __ldg(P.ctx + P.totalImages + 2 * si) * G;
+        const float alpha = __ldg(P.ctx + S.imgBase + img);
+        I.cp = -coef * P.p2n * alpha;
+        I.cn = coef * (1.0f - alpha);
+        I.maskBinary = MASK && (__ldg(P.ctx + P.totalImages + 2 * si + 1) != 0.f);
+    }
+    const size_t plane = (size_t)img * H * W;
+
+    for (int item = item0; item < S.items; item += S.ctasPerImage * kWarps) {  // warp-uniform
+        const int strip = item / S.rowBlocks;
+        const int rb = item - strip * S.rowBlocks;
+        const int row0 = rb * RH;
+        // one halo lane per side is enough here (coefficients are pointwise): lanes 1..30 write
+        const int col0 = (strip * kHaloLanes + lane - 1) * VEC;
+        const bool colOk = col0 >= 0 && col0 < W;
+        const bool writer = lane >= 1 && lane <= kHaloLanes && colOk;
+
+        float pfg[PD][VEC], pfe[PD][VEC], pfm[PD][VEC], pfx[PD][VEC];
+        unsigned pfc[PD];
+        auto fetch = [&](int slot, int row) {
+            load_vec<VEC>(pfg[slot], S.g + plane, row, H, W, col0, false);
+            load_vec<VEC>(pfe[slot], S.e + plane, row, H, W, col0, false);
+            if (MASK) load_vec<VEC>(pfm[slot], S.m + plane, row, H, W, col0, false);
+            if (INV) load_vec<VEC>(pfx[slot], S.x + plane, row, H, W, col0, false);
+            const bool ok = row >= 0 && row < H && colOk;
+            unsigned c = 0;
+            if (ok) {
+                const unsigned char *sp = S.stash + plane + (size_t)row * W + col0;
+                c = (VEC == 4) ? __ldcs(reinterpret_cast<const unsigned *>(sp)) : (unsigned)__ldcs(sp);
+            }
+            pfc[slot] = c;
+        };
+#pragma unroll
+        for (int k = 0; k < PD; k++) fetch(k, row0 - 1 + k);
+        float oacc[3][VEC], xrow[3][VEC];
+#pragma unroll
+        for (int o = 0; o < 3; o++)
+#pragma unroll
+            for (int v = 0; v < VEC; v++) { oacc[o][v] = 0.f; xrow[o][v] = 0.f; }
+
+#pragma unroll
+        for (int j = 0; j < RH + 2; j++) {
+            const int row = row0 - 1 + j;
+            float g[VEC], e[VEC], m[VEC];
+            const unsigned codes = pfc[j % PD];
+#pragma unroll
+            for (int v = 0; v < VEC; v++) {
+                g[v] = pfg[j % PD][v];
+                e[v] = pfe[j % PD][v];
+                m[v] = MASK ? pfm[j % PD][v] : 1.f;
+                if (INV) xrow[j % 3][v] = pfx[j % PD][v];
+            }
+            if (j + PD < RH + 2) fetch(j % PD, row + PD);
+            const bool live = colOk && row >= 0 && row < H;
+            float A[VEC], C[VEC], A2[VEC], C2[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; v++) {
+                float d = dloss_dg<MASK, SIG>(g[v], e[v], m[v], I, P.T);
+                d = live ? d : 0.f;
+                const float4 k = sLut[(codes >> (8 * v)) & 15u];
+                A[v] = d * k.x; C[v] = d * k.y; A2[v] = d * k.z; C2[v] = d * k.w;
+            }
+            const float Al = __shfl_up_sync(MTE_FULL_MASK, A[VEC - 1], 1), Ar = __shfl_down_sync(MTE_FULL_MASK, A[0], 1);
+            const float Cl = __shfl_up_sync(MTE_FULL_MASK, C[VEC - 1], 1), Cr = __shfl_down_sync(MTE_FULL_MASK, C[0], 1);
+            const float C2l = __shfl_up_sync(MTE_FULL_MASK, C2[VEC - 1], 1), C2r = __shfl_down_sync(MTE_FULL_MASK, C2[0], 1);
+#pragma unroll
+            for (int v = 0; v < VEC; v++) {
+                const float a_l = v == 0 ? Al : A[v - 1], a_r = v == VEC - 1 ? Ar : A[(v + 1) % VEC];
+                const float c_l = v == 0 ? Cl : C[v - 1], c_r = v == VEC - 1 ? Cr : C[(v + 1) % VEC];
+                const float c2_l = v == 0 ? C2l : C2[v - 1], c2_r = v == VEC - 1 ? C2r : C2[(v + 1) % VEC];
+                const float SA = (a_l + a_r) + A2[v], DC = c_l - c_r;
+                oacc[j % 3][v] = SA + DC;                           // output row j   (this row acts as "up")
+                if (j >= 1) oacc[(j + 2) % 3][v] += c2_l - c2_r;    // output row j-1 ("mid")
+                if (j >= 2) oacc[(j + 1) % 3][v] -= SA - DC;        // output row j-2 ("down"), now complete
+            }
+            if (j >= 2) {
+                const int o = j - 2, orow = row0 + o;
+                float out[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; v++) {
+                    float d = oacc[o % 3][v];
+                    if (INV) {
+                        // pred was an inverse depth: chain through depth = 1/clamp(inv, 1e-6); coefficient row j-1
+                        // carried the inverse depth of image row orow
+                        const float inv = xrow[(j + 2) % 3][v];
+                        const float dep = inv_to_depth(inv);
+                        d = (dep < 1e6f) ? -d * dep * dep : 0.f;
+                    }
+                    out[v] = d;
+                }
+                if (writer && orow < H) {
+                    float *op = S.dx + plane + (size_t)orow * W + col0;
+                    if (VEC == 4) st_stream4(op, make_float4(out[0], out[1 % VEC], out[2 % VEC], out[3 % VEC]));
+                    else __stcs(op, out[0]);
+                }
+            }
+        }
+    }
+}
+
 // launchers implemented one translation unit per (direction, VEC) so they compile in parallel
 void launch_fwd_v4(const LossP &P, int mode, bool mask, bool inv, bool sig, cudaStream_t st);
 void launch_fwd_v1(const LossP &P, int mode, bool mask, bool inv, bool sig, cudaStream_t st);
 void launch_bwd_v4(const LossP &P, int mode, bool mask, bool inv, bool sig, cudaStream_t st);
 void launch_bwd_v1(const LossP &P, int mode, bool mask, bool inv, bool sig, cudaStream_t st);
+void launch_bwd_stash_v4(const LossP &P, bool mask, bool inv, bool sig, cudaStream_t st);
+void launch_bwd_stash_v1(const LossP &P, bool mask, bool inv, bool sig, cudaStream_t st);
 
 #define MTE_LOSS_DISPATCH_BOOL(flag, NAME, ...) \
     if (flag) { constexpr bool NAME = true; __VA_ARGS__ } else { constexpr bool NAME = false; __VA_ARGS__ }

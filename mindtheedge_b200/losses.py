@@ -29,7 +29,7 @@ def _prep(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.contiguous()
 
 
-def _scales_struct(pred, edge, normal, mask, grad_map, grad_pred, weights):
+def _scales_struct(pred, edge, normal, mask, grad_map, grad_pred, weights, stash=None):
     n = len(pred)
     arr = (_lib.LossScale * n)()
     for i in range(n):
@@ -46,6 +46,7 @@ def _scales_struct(pred, edge, normal, mask, grad_map, grad_pred, weights):
         s.mask = mask[i].data_ptr() if mask else None
         s.grad_map = grad_map[i].data_ptr() if grad_map else None
         s.grad_pred = grad_pred[i].data_ptr() if grad_pred else None
+        s.stash = stash[i].data_ptr() if stash else None
         s.B, s.h, s.w, s.H, s.W = B, h, w, H, W
         s.scale_weight = float(weights[i])
         for other, nm in ((normal, "normal"), (mask, "mask")):
@@ -66,10 +67,10 @@ _LIBDEF = torch.library.Library("mte", "DEF")
 _LIBDEF.define(
     "edge_loss_fwd(Tensor[] pred, Tensor[] edge, Tensor[] normal, Tensor[] mask, float[] scale_weights, "
     "bool is_grad, bool is_sigmoid, bool pred_is_inverse, float sigmoid_thresh, float weight, float pos_to_neg) "
-    "-> (Tensor, Tensor, Tensor[])")
+    "-> (Tensor, Tensor, Tensor[], Tensor[])")
 _LIBDEF.define(
     "edge_loss_bwd(Tensor grad_losses, Tensor ctx, Tensor[] pred, Tensor[] edge, Tensor[] normal, Tensor[] mask, "
-    "float[] scale_weights, bool is_grad, bool is_sigmoid, bool pred_is_inverse, float sigmoid_thresh, "
+    "Tensor[] grad_maps, Tensor[] stash, float[] scale_weights, bool is_grad, bool is_sigmoid, bool pred_is_inverse, float sigmoid_thresh, "
     "float weight, float pos_to_neg) -> Tensor[]")
 
 
@@ -78,7 +79,10 @@ def _edge_loss_fwd_cuda(pred, edge, normal, mask, scale_weights, is_grad, is_sig
     dev = pred[0].device
     n = len(pred)
     grad_maps = [torch.empty_like(e) for e in edge]
-    sc = _scales_struct(pred, edge, normal, mask, grad_maps, None, scale_weights)
+    # 1 byte/px side output (picked direction + sign of the response) that lets the backward skip the stencil
+    use_stash = bool(is_grad) and bool(normal) and all(p.shape == e.shape for p, e in zip(pred, edge))
+    stash = [torch.empty(e.shape, dtype=torch.uint8, device=dev) for e in edge] if use_stash else []
+    sc = _scales_struct(pred, edge, normal, mask, grad_maps, None, scale_weights, stash)
     at = _attrs(is_grad, is_sigmoid, pred_is_inverse, sigmoid_thresh, weight, pos_to_neg)
     losses = torch.empty(1 + n, dtype=torch.float32, device=dev)
     ctx = torch.empty(_lib.lib.mte_edge_loss_ctx_bytes(sc, n) // 4, dtype=torch.float32, device=dev)
@@ -86,15 +90,15 @@ def _edge_loss_fwd_cuda(pred, edge, normal, mask, scale_weights, is_grad, is_sig
     ws = runtime.workspace(dev, nbytes)
     _lib.check(_lib.lib.mte_edge_loss_fwd(sc, n, C.byref(at), losses.data_ptr(), ctx.data_ptr(), ws.data_ptr(),
                                           ws.numel(), runtime.current_stream_ptr(dev)), "mte_edge_loss_fwd")
-    return losses, ctx, grad_maps
+    return losses, ctx, grad_maps, stash
 
 
-def _edge_loss_bwd_cuda(grad_losses, ctx, pred, edge, normal, mask, scale_weights, is_grad, is_sigmoid,
-                        pred_is_inverse, sigmoid_thresh, weight, pos_to_neg):
+def _edge_loss_bwd_cuda(grad_losses, ctx, pred, edge, normal, mask, grad_maps, stash, scale_weights, is_grad,
+                        is_sigmoid, pred_is_inverse, sigmoid_thresh, weight, pos_to_neg):
     dev = pred[0].device
     n = len(pred)
     grads = [torch.empty_like(p) for p in pred]
-    sc = _scales_struct(pred, edge, normal, mask, None, grads, scale_weights)
+    sc = _scales_struct(pred, edge, normal, mask, grad_maps if stash else None, grads, scale_weights, stash)
     at = _attrs(is_grad, is_sigmoid, pred_is_inverse, sigmoid_thresh, weight, pos_to_neg)
     nbytes = _lib.lib.mte_edge_loss_workspace_bytes(sc, n)
     ws = runtime.workspace(dev, nbytes)
@@ -115,18 +119,26 @@ class _EdgeLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, *pred):
         edge, normal, mask, weights, flags = cfg
-        losses, saved, grad_maps = torch.ops.mte.edge_loss_fwd(list(pred), edge, normal, mask, weights, *flags)
+        losses, saved, grad_maps, stash = torch.ops.mte.edge_loss_fwd(list(pred), edge, normal, mask, weights, *flags)
         ctx.cfg = cfg
-        ctx.save_for_backward(saved, *pred)
+        ctx.n = len(pred)
+        ctx.has_stash = len(stash) > 0
+        # the grad maps are outputs the caller may hold on to; the backward only reads them
+        ctx.save_for_backward(saved, *pred, *(grad_maps if stash else []), *stash)
         ctx.mark_non_differentiable(*grad_maps)
         return (losses, *grad_maps)
 
     @staticmethod
     def backward(ctx, grad_losses, *_unused):
         edge, normal, mask, weights, flags = ctx.cfg
-        saved, *pred = ctx.saved_tensors
+        saved, *rest = ctx.saved_tensors
+        n = ctx.n
+        pred = rest[:n]
+        gmaps = rest[n:2 * n] if ctx.has_stash else []
+        stash = rest[2 * n:3 * n] if ctx.has_stash else []
         g = grad_losses.contiguous().float()
-        grads = torch.ops.mte.edge_loss_bwd(g, saved, list(pred), edge, normal, mask, weights, *flags)
+        grads = torch.ops.mte.edge_loss_bwd(g, saved, list(pred), edge, normal, mask, list(gmaps), list(stash),
+                                            weights, *flags)
         return (None, *grads)
 
 

@@ -15,7 +15,8 @@ def make(B, H, W, scales, nsets, dev):
             pred.append(torch.rand(B, 1, h, w, device=dev) * 79 + 1)
             edge.append((torch.rand(B, 1, h, w, device=dev) < 0.015).float() * torch.rand(B, 1, h, w, device=dev).clamp(min=0.3))
             normal.append((torch.randint(0, 256, (B, 1, h, w), device=dev).float() * 360 / 255 - 180) * 3.14159265 / 180)
-        sets.append((pred, edge, normal, [torch.empty_like(p) for p in pred], [torch.empty_like(p) for p in pred]))
+        sets.append((pred, edge, normal, [torch.empty_like(p) for p in pred], [torch.empty_like(p) for p in pred],
+                     [torch.empty(p.shape, dtype=torch.uint8, device=dev) for p in pred]))
     return sets
 
 def run(B, H, W, scales, nsets, iters=50):
@@ -23,9 +24,10 @@ def run(B, H, W, scales, nsets, iters=50):
     sets = make(B, H, W, scales, nsets, dev)
     at = _attrs(True, True, False, 4.0, 10.0, 1.0)
     structs = []
-    for pred, edge, normal, gmap, gpred in sets:
-        structs.append((_scales_struct(pred, edge, normal, None, gmap, None, [1.0 / scales] * scales),
-                        _scales_struct(pred, edge, normal, None, None, gpred, [1.0 / scales] * scales)))
+    use_stash = not os.environ.get("MTE_LOSS_NO_STASH")
+    for pred, edge, normal, gmap, gpred, stash in sets:
+        structs.append((_scales_struct(pred, edge, normal, None, gmap, None, [1.0 / scales] * scales, stash if use_stash else None),
+                        _scales_struct(pred, edge, normal, None, gmap if use_stash else None, gpred, [1.0 / scales] * scales, stash if use_stash else None)))
     n = scales
     losses = torch.zeros(1 + n, device=dev); ctx = torch.zeros(_lib.lib.mte_edge_loss_ctx_bytes(structs[0][0], n) // 4, device=dev)
     ws = runtime.workspace(dev, _lib.lib.mte_edge_loss_workspace_bytes(structs[0][0], n))
