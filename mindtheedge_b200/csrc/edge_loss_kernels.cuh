@@ -82,8 +82,11 @@ __device__ __forceinline__ int dir_index(float t) {
     const bool neg = t < 0.f;
     const int ub = (__float_as_int(t) & 0x7fffffff) - (neg ? 1 : 0);
     const float u = __int_as_float(ub);
-    const int n = (u >= MTE_B1) + (u >= MTE_B3) + (u >= MTE_B5) + (u >= MTE_B7);
-    return (neg ? -n : n) & 3;
+    // count in floating point: FSET + FADD per limit (an integer count costs a predicated move pair each)
+    const float n = ((u >= MTE_B1) ? 1.f : 0.f) + ((u >= MTE_B3) ? 1.f : 0.f) + ((u >= MTE_B5) ? 1.f : 0.f) +
+                    ((u >= MTE_B7) ? 1.f : 0.f);
+    const int ni = __float2int_rz(neg ? 4.f - n : n);
+    return ni & 3;
 }
 
 // cond ? a : b as a real SELP: keeps ptxas from turning value selections into divergent branches
@@ -109,7 +112,12 @@ __device__ __forceinline__ float rcp_rn_normal(float d) {
 __device__ __forceinline__ float inv_to_depth(float v) { return rcp_rn_normal(fmaxf(v, 1e-6f)); }
 
 // Forward: the loss is a mean over millions of terms; MUFU-accuracy sigmoid is far inside 1e-5.
-__device__ __forceinline__ float sigmoid_fast(float z) { return rcp_approx(1.0f + __expf(-z)); }
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sigmoid_fast(float z) { return rcp_approx(1.0f + ex2_approx(z * -1.4426950408889634f)); }
 // Backward: p(1-p)/(1-p+eps) amplifies the last bits of p where the sigmoid saturates, so p is
 // computed the way eager PyTorch does (accurate expf, correctly rounded divide): the gradient then
 // reproduces the reference's own rounding, not only the underlying math.
@@ -206,55 +214,98 @@ __device__ __forceinline__ float pick_response(int k, float P, float R, float Dm
 // to finish (atomic counter) folds the per-image sums into alpha and the loss.
 constexpr double kFix = 4294967296.0;  // 2^32
 
+// double sum over the lanes selected by `in` (fixed butterfly order)
+__device__ __forceinline__ double seg_sum(double v, bool in) { return warp_sum(in ? v : 0.0); }
+
 static __device__ __noinline__ void finalize_loss(const LossP &P, bool hasMask) {
-    // Run by ONE warp (the last to finish).  lane <-> image (strided); fixed shuffle order => reproducible.
+    // Run by ONE warp (the last to finish): it is the tail of the kernel, so every image of every scale is handled
+    // by its own lane at once (one L2 round trip), scales are separated with predicated butterflies.
+    // Fixed shuffle order => reproducible.
     const int lane = threadIdx.x & 31;
-    double total = 0.0;
-    for (int si = 0; si < P.nScales; si++) {
-        const ScaleP &S = P.s[si];
-        const double npix = (double)S.H * (double)S.W;
-        unsigned fl = 0;
-        double wnAll = 0.0, sumM = 0.0;
-        for (int b = lane; b < S.B; b += 32) {
-            const unsigned long long *o = P.accum + (size_t)(S.imgBase + b) * kAcc;
-            unsigned long long v[kAcc];
+    double lossOfScale[MTE_MAX_SCALES];
 #pragma unroll
-            for (int k = 0; k < kAcc; k++) v[k] = __ldcg(o + k);  // one round trip
-            fl |= (unsigned)v[A_FLAGS];
-            const double wp = (double)(long long)v[A_WP] / kFix;
-            wnAll += hasMask ? (double)(long long)v[A_WN] / kFix : (npix - wp);
-            sumM += (double)(long long)v[A_SUMM] / kFix;
+    for (int k = 0; k < MTE_MAX_SCALES; k++) lossOfScale[k] = 0.0;
+    double accOfScale[MTE_MAX_SCALES], validOfScale[MTE_MAX_SCALES];
+    unsigned binaryMask = 0;
+    // pass structure per chunk of 32 images: (1) global sums per scale need ALL images of the scale, so first
+    // accumulate wnAll / sumM / flags per scale over all chunks, then (2) a second sweep computes alpha & the loss.
+    double wnAll[MTE_MAX_SCALES], sumM[MTE_MAX_SCALES];
+    unsigned fl[MTE_MAX_SCALES];
+#pragma unroll
+    for (int k = 0; k < MTE_MAX_SCALES; k++) { wnAll[k] = 0.0; sumM[k] = 0.0; fl[k] = 0; accOfScale[k] = 0.0; }
+    for (int base = 0; base < P.totalImages; base += 32) {
+        const int gi = base + lane;
+        int si = -1;
+#pragma unroll
+        for (int k = 0; k < MTE_MAX_SCALES; k++)
+            if (k < P.nScales && gi >= P.s[k].imgBase && gi < P.s[k].imgBase + P.s[k].B) si = k;
+        unsigned long long v[kAcc];
+#pragma unroll
+        for (int k = 0; k < kAcc; k++) v[k] = (si >= 0) ? __ldcg(P.accum + (size_t)gi * kAcc + k) : 0ull;
+        const double npix = si >= 0 ? (double)P.s[si].H * (double)P.s[si].W : 0.0;
+        const double wp = (double)(long long)v[A_WP] / kFix;
+        const double wn = hasMask ? (double)(long long)v[A_WN] / kFix : (npix - wp);
+        const double sm = (double)(long long)v[A_SUMM] / kFix;
+#pragma unroll
+        for (int k = 0; k < MTE_MAX_SCALES; k++) {
+            if (k < P.nScales) {
+                wnAll[k] += seg_sum(wn, si == k);
+                sumM[k] += seg_sum(sm, si == k);
+                fl[k] |= warp_or(si == k ? (unsigned)v[A_FLAGS] : 0u);
+            }
         }
-        fl = warp_or(fl);
-        wnAll = warp_sum(wnAll);
-        sumM = warp_sum(sumM);
-        // grad_loss.py:183-187: the mask only masks when its value set is exactly {0,1}
-        const bool binary = hasMask && fl == (F_HAS0 | F_HAS1);
-        const double valid = binary ? sumM : npix * (double)S.B;
-        double acc = 0.0;
-        for (int b = lane; b < S.B; b += 32) {
-            unsigned long long *o = P.accum + (size_t)(S.imgBase + b) * kAcc;
-            unsigned long long v[kAcc];
+    }
 #pragma unroll
-            for (int k = 0; k < kAcc; k++) v[k] = __ldcg(o + k);
+    for (int k = 0; k < MTE_MAX_SCALES; k++) {
+        if (k < P.nScales) {
+            // grad_loss.py:183-187: the mask only masks when its value set is exactly {0,1}
+            const bool binary = hasMask && fl[k] == (F_HAS0 | F_HAS1);
+            if (binary) binaryMask |= 1u << k;
+            validOfScale[k] = binary ? sumM[k] : (double)P.s[k].H * (double)P.s[k].W * (double)P.s[k].B;
+        }
+    }
+    for (int base = 0; base < P.totalImages; base += 32) {
+        const int gi = base + lane;
+        int si = -1;
+#pragma unroll
+        for (int k = 0; k < MTE_MAX_SCALES; k++)
+            if (k < P.nScales && gi >= P.s[k].imgBase && gi < P.s[k].imgBase + P.s[k].B) si = k;
+        unsigned long long v[kAcc];
+#pragma unroll
+        for (int k = 0; k < kAcc; k++) v[k] = (si >= 0) ? __ldcg(P.accum + (size_t)gi * kAcc + k) : 0ull;
+        double contrib = 0.0;
+        if (si >= 0) {
+            const bool binary = (binaryMask >> si) & 1u;
+            const double npix = (double)P.s[si].H * (double)P.s[si].W;
             const double wp = (double)(long long)v[A_WP] / kFix;
             const double wn = hasMask ? (double)(long long)v[A_WN] / kFix : (npix - wp);
-            const float alpha = (wnAll == 0.0) ? 1.0f : (float)(wn / (wp + wn));  // grad_loss.py:175-178
+            double wa = 0.0;
+#pragma unroll
+            for (int k = 0; k < MTE_MAX_SCALES; k++) wa = (si == k) ? wnAll[k] : wa;
+            const float alpha = (wa == 0.0) ? 1.0f : (float)(wn / (wp + wn));  // grad_loss.py:175-178
             const double sp = (double)kLn2 * ((double)(long long)(binary ? v[A_SPM] : v[A_SPU]) / kFix);
             const double sn = (double)kLn2 * ((double)(long long)(binary ? v[A_SNM] : v[A_SNU]) / kFix);
-            acc += -(double)P.p2n * (double)alpha * sp - (1.0 - (double)alpha) * sn;
-            P.ctx[S.imgBase + b] = alpha;
+            contrib = -(double)P.p2n * (double)alpha * sp - (1.0 - (double)alpha) * sn;
+            P.ctx[gi] = alpha;
 #pragma unroll
-            for (int k = 0; k < kAcc; k++) o[k] = 0ull;  // leave the accumulators clean
+            for (int k = 0; k < kAcc; k++) P.accum[(size_t)gi * kAcc + k] = 0ull;  // leave the accumulators clean
         }
-        acc = warp_sum(acc);
-        const double lossS = (double)P.weight * (acc / valid);
-        if (lane == 0) {
-            P.lossOut[1 + si] = (float)lossS;
-            P.ctx[P.totalImages + 2 * si] = (float)((double)P.weight / valid);
-            P.ctx[P.totalImages + 2 * si + 1] = binary ? 1.0f : 0.0f;
+#pragma unroll
+        for (int k = 0; k < MTE_MAX_SCALES; k++)
+            if (k < P.nScales) accOfScale[k] += seg_sum(contrib, si == k);
+    }
+    double total = 0.0;
+#pragma unroll
+    for (int k = 0; k < MTE_MAX_SCALES; k++) {
+        if (k < P.nScales) {
+            lossOfScale[k] = (double)P.weight * (accOfScale[k] / validOfScale[k]);
+            total += (double)P.s[k].scaleWeight * lossOfScale[k];
+            if (lane == k) {
+                P.lossOut[1 + k] = (float)lossOfScale[k];
+                P.ctx[P.totalImages + 2 * k] = (float)((double)P.weight / validOfScale[k]);
+                P.ctx[P.totalImages + 2 * k + 1] = ((binaryMask >> k) & 1u) ? 1.0f : 0.0f;
+            }
         }
-        total += (double)S.scaleWeight * lossS;
     }
     if (lane == 0) {
         P.lossOut[0] = (float)total;
@@ -401,13 +452,14 @@ __global__ void __launch_bounds__(kThreads, MTE_FWD_MINB) edge_loss_fwd_kernel(c
     constexpr int LANES = (MODE == MODE_NONE) ? 32 : kHaloLanes;
     constexpr int OFF = (MODE == MODE_NONE) ? 0 : 1;
     const int lane = threadIdx.x & 31;
-    int item = 0;
-    if (lane == 0) item = (int)atomicAdd(P.ticket, 1u);
-    item = __shfl_sync(MTE_FULL_MASK, item, 0);
+    // the first item is static (no round trip before the first loads), later ones come from the atomic queue,
+    // which therefore starts at the number of warps in the grid
+    const int nWarps = gridDim.x * kWarps;
+    int item = blockIdx.x * kWarps + (threadIdx.x >> 5);
     while (item < P.totalItems) {
         // claim the next item now: the atomic's round trip hides behind this item's work
         int next = 0;
-        if (lane == 0) next = (int)atomicAdd(P.ticket, 1u);
+        if (lane == 0) next = nWarps + (int)atomicAdd(P.ticket, 1u);
         int si = 0;
 #pragma unroll
         for (int k = 1; k < MTE_MAX_SCALES; k++)
