@@ -169,7 +169,8 @@ static int make_plan(Plan &pl, const mte_loss_scale_t *sc, int n, const mte_loss
     const int RH = bwd ? kBwdRH : kFwdRH;
     const bool stashBwd = bwd && can_use_stash(sc, n, at);
     const int lanesOut = !pl.isGrad ? 32 : ((bwd && !stashBwd) ? bwd_lanes(VEC) : kHaloLanes);
-    int cta = 0, img = 0, itemBase = 0;
+    int cta = 0, img = 0;
+    long long unitBase = 0;
     for (int i = 0; i < n; i++) {
         ScaleP &S = P.s[i];
         S.B = sc[i].B; S.H = sc[i].H; S.W = sc[i].W;
@@ -181,8 +182,8 @@ static int make_plan(Plan &pl, const mte_loss_scale_t *sc, int n, const mte_loss
         S.items = S.strips * S.rowBlocks;
         S.ctasPerImage = ceil_div(S.items, kWarps);  // capped below: warps loop over several items
         S.ctaBase = cta; S.imgBase = img;
-        S.itemBase = itemBase;
-        itemBase += S.items * S.B;
+        S.unitBase = (int)unitBase;
+        unitBase += (long long)S.strips * S.H * S.B;
         S.scaleWeight = sc[i].scale_weight;
         cta += S.ctasPerImage * S.B;
         img += S.B;
@@ -207,10 +208,14 @@ static int make_plan(Plan &pl, const mte_loss_scale_t *sc, int n, const mte_loss
         }
     }
     P.nScales = n; P.totalCtas = cta; P.totalImages = img;
-    P.totalItems = itemBase;
-    // forward: persistent CTAs (2 per SM) pulling items from the atomic queue; never more warps than items
+    if (unitBase > 0x7fffffffLL) return MTE_ERR_SHAPE;
+    P.totalUnits = (int)unitBase;
+    // forward: persistent CTAs (2 per SM), every warp owns an equal contiguous range of strip rows (at least a few
+    // rows each, so the window prologue is amortised)
     pl.fwdGrid = kNumSMs * 2;
-    if (pl.fwdGrid * kWarps > itemBase) pl.fwdGrid = ceil_div(itemBase, kWarps);
+    const int minRows = 4;
+    if ((long long)pl.fwdGrid * kWarps * minRows > unitBase) pl.fwdGrid = (int)((unitBase + kWarps * minRows - 1) / (kWarps * minRows));
+    if (pl.fwdGrid < 1) pl.fwdGrid = 1;
     if (at) {
         P.T = at->sigmoid_thresh; P.weight = at->weight; P.p2n = at->pos_to_neg;
     }

@@ -51,7 +51,7 @@ struct ScaleP {
     int B, H, W;
     int strips, rowBlocks, items, ctasPerImage;
     int ctaBase, imgBase;
-    int itemBase;  // forward: first work item of this scale in the global (dynamically scheduled) item queue
+    int unitBase;  // forward: first unit (strip row) of this scale in the global unit order
     float scaleWeight;
 };
 
@@ -59,7 +59,7 @@ struct LossP {
     ScaleP s[MTE_MAX_SCALES];
     int nScales, totalCtas, totalImages;
     float T, weight, p2n;
-    int totalItems;                // forward work items over all scales and images
+    int totalUnits;                // forward: strip rows over all scales and images
     unsigned long long *accum;     // forward: [totalImages][kAcc] fixed-point (2^32) per-image sums, zero at launch
     unsigned *ticket;              // forward: dynamic item counter; [1]: finished-warp counter (both self-resetting)
     float *lossOut;         // [1+nScales]
@@ -214,269 +214,356 @@ __device__ __forceinline__ float pick_response(int k, float P, float R, float Dm
 // to finish (atomic counter) folds the per-image sums into alpha and the loss.
 constexpr double kFix = 4294967296.0;  // 2^32
 
-// double sum over the lanes selected by `in` (fixed butterfly order)
-__device__ __forceinline__ double seg_sum(double v, bool in) { return warp_sum(in ? v : 0.0); }
-
-static __device__ __noinline__ void finalize_loss(const LossP &P, bool hasMask) {
-    // Run by ONE warp (the last to finish): it is the tail of the kernel, so every image of every scale is handled
-    // by its own lane at once (one L2 round trip), scales are separated with predicated butterflies.
-    // Fixed shuffle order => reproducible.
-    const int lane = threadIdx.x & 31;
-    double lossOfScale[MTE_MAX_SCALES];
+// Run by the LAST CTA to finish (all of its warps): warp k folds scale k -- one image per lane, plain butterflies in
+// a fixed order (reproducible) -- into alpha, the normalisers and the scale's loss; thread 0 then combines the scales.
+// It is the serial tail of the kernel, so the dependent chain is kept short: one L2 round trip for the sums, three
+// butterflies, two divisions.
+template <bool MASK>
+static __device__ __forceinline__ void finalize_loss(const LossP &P, double *sLoss /* [MTE_MAX_SCALES] shared */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = warp; k < P.nScales; k += kWarps) {
+        const ScaleP &S = P.s[k];
+        const double npix = (double)S.H * (double)S.W;
+        double sumM = 0.0;
+        unsigned fl = 0;
+        if (MASK) {  // the mask's value set and sum decide the normaliser before the per-image pass
+            for (int base = 0; base < S.B; base += 32) {
+                const int i = base + lane;
+                const unsigned long long *a = P.accum + (size_t)(S.imgBase + i) * kAcc;
+                const bool in = i < S.B;
+                const double sm = in ? (double)(long long)__ldcg(a + A_SUMM) / kFix : 0.0;
+                fl |= in ? (unsigned)__ldcg(a + A_FLAGS) : 0u;
+                sumM += sm;
+            }
+            sumM = warp_sum(sumM);
+            fl = warp_or(fl);
+        }
+        // grad_loss.py:183-187: the mask only masks when its value set is exactly {0,1}
+        const bool binary = MASK && fl == (F_HAS0 | F_HAS1);
+        // one image per lane; the three sums are independent butterflies (they overlap), the degenerate
+        // "no negatives anywhere" variant (all alpha = 1, grad_loss.py:175-176) rides along as acc1
+        double acc = 0.0, acc1 = 0.0, wnSum = 0.0;
+        for (int base = 0; base < S.B; base += 32) {
+            const int i = base + lane;
+            if (i < S.B) {
+                unsigned long long *a = P.accum + (size_t)(S.imgBase + i) * kAcc;
+                const double wp = (double)(long long)__ldcg(a + A_WP) / kFix;
+                const double wn = MASK ? (double)(long long)__ldcg(a + A_WN) / kFix : (npix - wp);
+                const double sp = (double)(long long)__ldcg(a + (binary ? A_SPM : A_SPU)) / kFix;
+                const double sn = (double)(long long)__ldcg(a + (binary ? A_SNM : A_SNU)) / kFix;
+                const float alpha = (float)(wn / (wp + wn));  // grad_loss.py:178
+                P.ctx[S.imgBase + i] = alpha;
+                acc += -(double)P.p2n * (double)alpha * sp - (1.0 - (double)alpha) * sn;
+                acc1 += -(double)P.p2n * sp;
+                wnSum += wn;
 #pragma unroll
-    for (int k = 0; k < MTE_MAX_SCALES; k++) lossOfScale[k] = 0.0;
-    double accOfScale[MTE_MAX_SCALES], validOfScale[MTE_MAX_SCALES];
-    unsigned binaryMask = 0;
-    // pass structure per chunk of 32 images: (1) global sums per scale need ALL images of the scale, so first
-    // accumulate wnAll / sumM / flags per scale over all chunks, then (2) a second sweep computes alpha & the loss.
-    double wnAll[MTE_MAX_SCALES], sumM[MTE_MAX_SCALES];
-    unsigned fl[MTE_MAX_SCALES];
-#pragma unroll
-    for (int k = 0; k < MTE_MAX_SCALES; k++) { wnAll[k] = 0.0; sumM[k] = 0.0; fl[k] = 0; accOfScale[k] = 0.0; }
-    for (int base = 0; base < P.totalImages; base += 32) {
-        const int gi = base + lane;
-        int si = -1;
-#pragma unroll
-        for (int k = 0; k < MTE_MAX_SCALES; k++)
-            if (k < P.nScales && gi >= P.s[k].imgBase && gi < P.s[k].imgBase + P.s[k].B) si = k;
-        unsigned long long v[kAcc];
-#pragma unroll
-        for (int k = 0; k < kAcc; k++) v[k] = (si >= 0) ? __ldcg(P.accum + (size_t)gi * kAcc + k) : 0ull;
-        const double npix = si >= 0 ? (double)P.s[si].H * (double)P.s[si].W : 0.0;
-        const double wp = (double)(long long)v[A_WP] / kFix;
-        const double wn = hasMask ? (double)(long long)v[A_WN] / kFix : (npix - wp);
-        const double sm = (double)(long long)v[A_SUMM] / kFix;
-#pragma unroll
-        for (int k = 0; k < MTE_MAX_SCALES; k++) {
-            if (k < P.nScales) {
-                wnAll[k] += seg_sum(wn, si == k);
-                sumM[k] += seg_sum(sm, si == k);
-                fl[k] |= warp_or(si == k ? (unsigned)v[A_FLAGS] : 0u);
+                for (int q = 0; q < kAcc; q++)
+                    if (MASK || q == A_WP || q == A_SPU || q == A_SNU) a[q] = 0ull;  // leave the accumulators clean
             }
         }
-    }
-#pragma unroll
-    for (int k = 0; k < MTE_MAX_SCALES; k++) {
-        if (k < P.nScales) {
-            // grad_loss.py:183-187: the mask only masks when its value set is exactly {0,1}
-            const bool binary = hasMask && fl[k] == (F_HAS0 | F_HAS1);
-            if (binary) binaryMask |= 1u << k;
-            validOfScale[k] = binary ? sumM[k] : (double)P.s[k].H * (double)P.s[k].W * (double)P.s[k].B;
+        acc = warp_sum(acc);
+        acc1 = warp_sum(acc1);
+        wnSum = warp_sum(wnSum);
+        if (wnSum == 0.0) {
+            acc = acc1;
+            for (int base = 0; base < S.B; base += 32)
+                if (base + lane < S.B) P.ctx[S.imgBase + base + lane] = 1.0f;
         }
-    }
-    for (int base = 0; base < P.totalImages; base += 32) {
-        const int gi = base + lane;
-        int si = -1;
-#pragma unroll
-        for (int k = 0; k < MTE_MAX_SCALES; k++)
-            if (k < P.nScales && gi >= P.s[k].imgBase && gi < P.s[k].imgBase + P.s[k].B) si = k;
-        unsigned long long v[kAcc];
-#pragma unroll
-        for (int k = 0; k < kAcc; k++) v[k] = (si >= 0) ? __ldcg(P.accum + (size_t)gi * kAcc + k) : 0ull;
-        double contrib = 0.0;
-        if (si >= 0) {
-            const bool binary = (binaryMask >> si) & 1u;
-            const double npix = (double)P.s[si].H * (double)P.s[si].W;
-            const double wp = (double)(long long)v[A_WP] / kFix;
-            const double wn = hasMask ? (double)(long long)v[A_WN] / kFix : (npix - wp);
-            double wa = 0.0;
-#pragma unroll
-            for (int k = 0; k < MTE_MAX_SCALES; k++) wa = (si == k) ? wnAll[k] : wa;
-            const float alpha = (wa == 0.0) ? 1.0f : (float)(wn / (wp + wn));  // grad_loss.py:175-178
-            const double sp = (double)kLn2 * ((double)(long long)(binary ? v[A_SPM] : v[A_SPU]) / kFix);
-            const double sn = (double)kLn2 * ((double)(long long)(binary ? v[A_SNM] : v[A_SNU]) / kFix);
-            contrib = -(double)P.p2n * (double)alpha * sp - (1.0 - (double)alpha) * sn;
-            P.ctx[gi] = alpha;
-#pragma unroll
-            for (int k = 0; k < kAcc; k++) P.accum[(size_t)gi * kAcc + k] = 0ull;  // leave the accumulators clean
-        }
-#pragma unroll
-        for (int k = 0; k < MTE_MAX_SCALES; k++)
-            if (k < P.nScales) accOfScale[k] += seg_sum(contrib, si == k);
-    }
-    double total = 0.0;
-#pragma unroll
-    for (int k = 0; k < MTE_MAX_SCALES; k++) {
-        if (k < P.nScales) {
-            lossOfScale[k] = (double)P.weight * (accOfScale[k] / validOfScale[k]);
-            total += (double)P.s[k].scaleWeight * lossOfScale[k];
-            if (lane == k) {
-                P.lossOut[1 + k] = (float)lossOfScale[k];
-                P.ctx[P.totalImages + 2 * k] = (float)((double)P.weight / validOfScale[k]);
-                P.ctx[P.totalImages + 2 * k + 1] = ((binaryMask >> k) & 1u) ? 1.0f : 0.0f;
-            }
-        }
-    }
-    if (lane == 0) {
-        P.lossOut[0] = (float)total;
-        P.ticket[0] = 0u;  // leave the workspace header clean for the next launch
-        P.ticket[1] = 0u;
-    }
-}
-
-// per-pixel loss terms of one output row.  okf = 1 inside the image, 0 outside (edge and mask planes are loaded as 0
-// there, so only the "1 - e" term needs it); halo lanes are discarded once per item by the caller.
-template <int VEC, int MODE, bool MASK, bool SIG>
-__device__ __forceinline__ void fwd_row(const LossP &P, const ScaleP &S, size_t plane, int row, int col0, bool ok,
-                                        const Row<VEC> &up, const Row<VEC> &mid, const Row<VEC> &dn,
-                                        const float (&e)[VEC], const float (&th)[VEC], const float (&m)[VEC],
-                                        float (&la)[kAcc - 1], unsigned &lflags) {
-    const float okf = ok ? 1.f : 0.f;
-    float g[VEC];
-    unsigned code[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; v++) {
-        code[v] = 0u;
-        if (MODE == MODE_NONE) {
-            g[v] = mid.c[v];
-        } else {
-            float sP, sR, sDm, sdv;
-            stencil_parts<VEC>(up, mid, dn, v, sP, sR, sDm, sdv);
-            if (MODE == MODE_MAG) {
-                const float cv = sP + sdv, ch = sR + sDm;
-                g[v] = sqrtf(cv * cv + ch * ch + 1e-6f);
-            } else {
-                const int di = dir_index(th[v]);
-                const float c = pick_response(di, sP, sR, sDm, sdv);
-                g[v] = fabsf(c);
-                code[v] = (unsigned)di | (c > 0.f ? 4u : 0u) | (c < 0.f ? 8u : 0u);
-            }
-        }
-        const float p = SIG ? sigmoid_fast(g[v] - P.T) : g[v];
-        const float ee = e[v];
-        const float ne = okf - ee;
-        const float lp = __log2f(p + kEps);
-        const float ln = __log2f((1.0f - p) + kEps);
-        la[A_SPU] = fmaf(ee, lp, la[A_SPU]);
-        la[A_SNU] = fmaf(ne, ln, la[A_SNU]);
-        if (MASK) {
-            const float mm = m[v];
-            la[A_WP] = fmaf(ee, mm, la[A_WP]);
-            la[A_WN] = fmaf(ne, mm, la[A_WN]);
-            la[A_SUMM] += mm;
-            const bool keep = mm != 0.f;
-            la[A_SPM] += keep ? ee * lp : 0.f;
-            la[A_SNM] += keep ? ne * ln : 0.f;
-            const unsigned f = (mm == 0.f) ? F_HAS0 : ((mm == 1.f) ? F_HAS1 : F_OTHER);
-            lflags |= ok ? f : 0u;
-        } else {
-            la[A_WP] += ee;
-        }
-    }
-    if (ok) {
-        const size_t o = plane + (size_t)row * S.W + col0;
-        if (S.g != nullptr) {
-            if (VEC == 4) st_stream4(S.g + o, make_float4(g[0], g[1 % VEC], g[2 % VEC], g[3 % VEC]));
-            else __stcs(S.g + o, g[0]);
-        }
-        if (MODE == MODE_DIR && S.stash != nullptr) {
-            if (VEC == 4)
-                __stcs(reinterpret_cast<unsigned *>(S.stash + o),
-                       code[0] | (code[1 % VEC] << 8) | (code[2 % VEC] << 16) | (code[3 % VEC] << 24));
-            else
-                __stcs(S.stash + o, (unsigned char)code[0]);
+        acc *= (double)kLn2;
+        const double valid = binary ? sumM : npix * (double)S.B;
+        const double lossK = (double)P.weight * (acc / valid);
+        if (lane == 0) {
+            sLoss[k] = lossK;
+            P.lossOut[1 + k] = (float)lossK;
+            P.ctx[P.totalImages + 2 * k] = (float)((double)P.weight / valid);
+            P.ctx[P.totalImages + 2 * k + 1] = binary ? 1.0f : 0.0f;
         }
     }
 }
 
-// One forward work item: RH output rows of a 32-lane strip, streamed through a 3-row register window with a 3-row
-// prefetch ring.  The row loop is unrolled by 3 only (window and ring indices become static); unrolling all RH rows
-// made the kernel ~100 KB of SASS and instruction-cache misses its top stall (profiles/r01_notes.md).
+// One depth row as the stencils consume it: centre values plus the horizontal 3-sum and difference, computed once
+// when the row enters the window and reused by the three output rows it takes part in.
+template <int VEC>
+struct PRow {
+    float c[VEC], s3[VEC], d[VEC];
+};
+template <int VEC, int MODE>
+__device__ __forceinline__ void prep_row(PRow<VEC> &R, const float (&x)[VEC]) {
+#pragma unroll
+    for (int v = 0; v < VEC; v++) R.c[v] = x[v];
+    if (MODE != MODE_NONE) {
+        // horizontal neighbours across the lane boundary (lanes 0 / 31 are halo lanes: their outer values are unused)
+        const float l = __shfl_up_sync(MTE_FULL_MASK, x[VEC - 1], 1);
+        const float r = __shfl_down_sync(MTE_FULL_MASK, x[0], 1);
+#pragma unroll
+        for (int v = 0; v < VEC; v++) {
+            const float xl = v == 0 ? l : x[(v + VEC - 1) % VEC];
+            const float xr = v == VEC - 1 ? r : x[(v + 1) % VEC];
+            R.s3[v] = (xl + x[v]) + xr;
+            R.d[v] = xr - xl;
+        }
+    }
+}
+
+// The two bits of the quantised normal direction (0:h 1:rl 2:v 3:lr) as predicates, straight from the four band
+// compares: with f_k = [u >= B_k] (nested), X = f1 ^ f5, Y = f3 ^ f7:  bit0 = X ^ Y (odd count), bit1 = Y for
+// theta >= 0 and X for theta < 0 (the mirrored table).  See dir_index for the ulp step on the negative side.
+__device__ __forceinline__ void dir_bits(float t, bool &b0, bool &b1) {
+    const bool neg = t < 0.f;
+    const float u = __int_as_float((__float_as_int(t) & 0x7fffffff) - (neg ? 1 : 0));
+    const bool X = (u >= MTE_B1) != (u >= MTE_B5);
+    const bool Y = (u >= MTE_B3) != (u >= MTE_B7);
+    b0 = X != Y;
+    b1 = (X && neg) || (Y && !neg);
+}
+
+// base + 4 * off as ONE 64-bit multiply-add (opaque to the optimiser, which otherwise re-associates the plane
+// offset into every access)
+template <typename T>
+__device__ __forceinline__ T *elem_addr(T *base, unsigned off) {
+    unsigned long long a;
+    asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(a) : "r"(off), "l"((unsigned long long)base));
+    return reinterpret_cast<T *>(a);
+}
+
+// Directional response + stash code of one pixel with the instruction selection pinned (the compiler's version of
+// the same logic spends ~10 more instructions per pixel on predicate spills and integer re-materialisation):
+//   band compares on the ulp-stepped |theta| (see dir_index / dir_bits) -> X = f1^f5, Y = f3^f7
+//   bit0 = X^Y, bit1 = theta<0 ? X : Y ; direction 0:h 1:rl 2:v 3:lr
+//   c = (bit1 ? Pv : Rh) + (bit1 ? (bit0 ? Rh : dv) : (bit0 ? -Pv : Dm))
+//   code = direction | 4 << signbit(c)   (bits 2-3: 1 = "+", 2 = "-"; a zero response is recognised by the
+//   backward from the grad map itself, |c| == 0)
+__device__ __forceinline__ void pick_directional(float th, float Pv, float Rh, float Dm, float dv, float &c,
+                                                 unsigned &code) {
+    asm("{\n\t"
+        ".reg .pred n, x, y, b0, b1, t1, t2;\n\t"
+        ".reg .b32 ub, sg, cd;\n\t"
+        ".reg .f32 a, bh, bl, b, np;\n\t"
+        "and.b32 ub, %2, 0x7fffffff;\n\t"
+        "setp.lt.f32 n, %2, 0f00000000;\n\t"
+        "@n add.s32 ub, ub, -1;\n\t"
+        "setp.ge.f32 x, ub, %9;\n\t"
+        "setp.ge.xor.f32 x, ub, %7, x;\n\t"
+        "setp.ge.f32 y, ub, %10;\n\t"
+        "setp.ge.xor.f32 y, ub, %8, y;\n\t"
+        "xor.pred b0, x, y;\n\t"
+        "and.pred t1, x, n;\n\t"
+        "not.pred t2, n;\n\t"
+        "and.pred t2, y, t2;\n\t"
+        "or.pred b1, t1, t2;\n\t"
+        "selp.f32 a, %3, %4, b1;\n\t"
+        "neg.f32 np, %3;\n\t"
+        "selp.f32 bh, %4, %6, b0;\n\t"
+        "selp.f32 bl, np, %5, b0;\n\t"
+        "selp.f32 b, bh, bl, b1;\n\t"
+        "add.f32 %0, a, b;\n\t"
+        "selp.u32 cd, 6, 4, b1;\n\t"
+        "@b0 add.u32 cd, cd, 1;\n\t"
+        "mov.b32 sg, %0;\n\t"
+        "shr.u32 sg, sg, 31;\n\t"
+        "mad.lo.u32 %1, sg, 4, cd;\n\t"
+        "}"
+        : "=&f"(c), "=r"(code)
+        : "f"(th), "f"(Pv), "f"(Rh), "f"(Dm), "f"(dv), "f"(MTE_B1), "f"(MTE_B3), "f"(MTE_B5), "f"(MTE_B7));
+}
+
+__device__ __forceinline__ float lg2_approx(float x) {  // arguments here are >= 1e-3: no denormal path needed
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Forward work decomposition: the unit is one row of one strip (32 lanes x VEC px, LANES of them writing) of one
+// image of one scale; units are ordered scale, image, strip, row and every warp of the persistent grid owns one
+// contiguous, equally long range of them (the cost of a unit does not depend on its content), cut into segments
+// at strip ends.  A segment streams its rows through a 3-row register window fed by a PD-row prefetch ring; ring
+// slots are refilled right after their last use, so no register copies are needed.
 template <int VEC, int MODE, bool MASK, bool INV, bool SIG>
-__device__ __forceinline__ void fwd_item(const LossP &P, const ScaleP &S, int img, int row0, int colFirst, int lane,
-                                         float (&la)[kAcc - 1], unsigned &lflags) {
-    constexpr int RH = kFwdRH;
+__device__ __forceinline__ void fwd_segment(const LossP &P, const ScaleP &S, int img, int strip, int row0, int nrows,
+                                            int lane, float (&la)[kAcc - 1], unsigned &lflags) {
     constexpr int PD = 3;
-    static_assert(RH % 3 == 0, "row loop is unrolled by the window size");
     constexpr int OFF = (MODE == MODE_NONE) ? 0 : 1;
-    const int H = S.H, W = S.W;
-    const int col0 = colFirst + lane * VEC;
-    const size_t plane = (size_t)img * H * W;
-    const float *x = S.x + plane;
-    const bool writer = (MODE == MODE_NONE) || (lane >= 1 && lane <= kHaloLanes);
-    const bool colOk = writer && col0 >= 0 && col0 < W;
+    constexpr int LANES = (MODE == MODE_NONE) ? 32 : kHaloLanes;
+    // out-of-image depth reads as 0 (zero padding of conv2d); with the fused inv2depth the fill is a huge inverse
+    // depth whose reciprocal flushes to exactly 0
+    constexpr float kFill = INV ? 3.0e38f : 0.f;
+    const int H = S.H;
+    const unsigned W = (unsigned)S.W;
+    const int col0 = (strip * LANES + lane - OFF) * VEC;
+    const bool colOk = col0 >= 0 && col0 < (int)W;
+    const bool writer = colOk && (MODE == MODE_NONE || (lane >= 1 && lane <= kHaloLanes));
+    // per-lane plane pointers at (row 0, clamped col0); rows are reached with one 32-bit element offset shared by
+    // all planes (one IMAD.WIDE per access).  Lanes outside the image read a valid dummy column and are either
+    // replaced by the zero padding (depth) or discarded (targets).
+    const size_t lo = (size_t)img * H * W + (colOk ? col0 : 0);
+    const float *xP = S.x + lo, *eP = S.e + lo, *nP = S.n + lo, *mP = S.m + lo;
+    float *gP = S.g + lo;
+    unsigned char *sP = S.stash + lo;
+    const bool writeG = writer && S.g != nullptr, writeS = writer && (MODE == MODE_DIR) && S.stash != nullptr;
+    const float kT = P.T * 1.4426950408889634f;
 
-    Row<VEC> xr[3];   // depth window: xr[d % 3] holds depth row index d (image row row0 - OFF + d)
-    Row<VEC> pfx[PD];
-    float pfe[PD][VEC], pft[PD][VEC], pfm[PD][VEC];
-    auto fetch = [&](int slot, int j) {  // everything output row j needs that is not in the window yet
-        load_row<VEC, INV>(pfx[slot], x, row0 + j + OFF, H, W, col0);
-        load_vec<VEC>(pfe[slot], S.e + plane, row0 + j, H, W, col0, false);
-        if (MODE == MODE_DIR) load_vec<VEC>(pft[slot], S.n + plane, row0 + j, H, W, col0, false);
-        if (MASK) load_vec<VEC>(pfm[slot], S.m + plane, row0 + j, H, W, col0, false);
+    float pfx[PD][VEC], pfe[PD][VEC], pft[PD][VEC], pfm[PD][VEC];
+    auto load_v = [&](float (&out)[VEC], const float *base, unsigned ro, bool cached) {
+        const float *p = elem_addr(base, ro);
+        if (VEC == 4) {
+            const float4 v = cached ? ld_cached4(p) : ld_stream4(p);
+            out[0] = v.x; out[1 % VEC] = v.y; out[2 % VEC] = v.z; out[3 % VEC] = v.w;
+        } else {
+            out[0] = cached ? __ldg(p) : __ldcs(p);
+        }
     };
+    // depth row `row` (may be -1 or H: zero padding): unconditional load from the clamped row; the padding select is
+    // applied when the row is CONSUMED (a select next to the load would wait for it and defeat the prefetch)
+    auto load_x = [&](float (&out)[VEC], int row) {
+        const int rc = min(max(row, 0), H - 1);
+        load_v(out, xP, (unsigned)rc * W, true);
+    };
+    auto pad_x = [&](float (&x)[VEC], int row) {
+        const bool ok = colOk && row >= 0 && row < H;
+#pragma unroll
+        for (int v = 0; v < VEC; v++) x[v] = ok ? x[v] : kFill;
+    };
+    auto fetch_t = [&](int slot, int j) {
+        const unsigned ro = (unsigned)(row0 + j) * W;
+        load_v(pfe[slot], eP, ro, false);
+        if (MODE == MODE_DIR) load_v(pft[slot], nP, ro, false);
+        if (MASK) load_v(pfm[slot], mP, ro, false);
+    };
+    auto to_depth = [&](float (&x)[VEC]) {
+        if (INV) {
+#pragma unroll
+            for (int v = 0; v < VEC; v++) x[v] = inv_to_depth(x[v]);
+        }
+    };
+
+    PRow<VEC> win[3];  // win[d % 3] holds depth row row0 - OFF + d
+    float xa[VEC], xc[VEC];
     if (MODE != MODE_NONE) {
-        load_row<VEC, INV>(xr[0], x, row0 - 1, H, W, col0);
-        load_row<VEC, INV>(xr[1], x, row0, H, W, col0);
+        load_x(xa, row0 - 1);
+        load_x(xc, row0);
     }
 #pragma unroll
-    for (int k = 0; k < PD; k++) fetch(k, k);
+    for (int k = 0; k < PD; k++)
+        if (k < nrows) {  // output row k needs depth row row0 + k + OFF and the target rows row0 + k
+            load_x(pfx[k], row0 + k + OFF);
+            fetch_t(k, k);
+        }
     if (MODE != MODE_NONE) {
-        exchange_row<VEC>(xr[0]);
-        exchange_row<VEC>(xr[1]);
+        pad_x(xa, row0 - 1);
+        pad_x(xc, row0);
+        to_depth(xa);
+        to_depth(xc);
+        prep_row<VEC, MODE>(win[0], xa);
+        prep_row<VEC, MODE>(win[1], xc);
     }
 #pragma unroll 1
-    for (int jj = 0; jj < RH; jj += 3) {
+    for (int jj = 0; jj < nrows; jj += 3) {
 #pragma unroll
         for (int u = 0; u < 3; u++) {
             const int j = jj + u;
-            float e[VEC], th[VEC], m[VEC];
-            Row<VEC> &newest = xr[(MODE == MODE_NONE) ? 0 : (u + 2) % 3];
-            newest = pfx[u];
+            if (j < nrows) {  // warp-uniform
+                const bool more = j + PD < nrows;
+                PRow<VEC> &dn = win[(MODE == MODE_NONE) ? 0 : (u + 2) % 3];
+                {
+                    float xn[VEC];
 #pragma unroll
-            for (int v = 0; v < VEC; v++) {
-                e[v] = pfe[u][v];
-                th[v] = (MODE == MODE_DIR) ? pft[u][v] : 0.f;
-                m[v] = MASK ? pfm[u][v] : 1.f;
+                    for (int v = 0; v < VEC; v++) xn[v] = pfx[u][v];
+                    pad_x(xn, row0 + j + OFF);
+                    to_depth(xn);
+                    if (more) load_x(pfx[u], row0 + j + PD + OFF);
+                    prep_row<VEC, MODE>(dn, xn);
+                }
+                const PRow<VEC> &up = win[(MODE == MODE_NONE) ? 0 : u % 3];
+                const PRow<VEC> &mid = win[(MODE == MODE_NONE) ? 0 : (u + 1) % 3];
+                float g[VEC];
+                unsigned code = 0u;
+#pragma unroll
+                for (int v = 0; v < VEC; v++) {
+                    if (MODE == MODE_NONE) {
+                        g[v] = dn.c[v];
+                    } else {
+                        // separable parts of the four zero-padded 3x3 cross-correlations of grad_loss.py:20-31:
+                        // c_v = Pv + dv, c_h = Rh + Dm, c_lr = Pv + Rh, c_rl = Rh - Pv
+                        const float Pv = dn.s3[v] - up.s3[v];
+                        const float Dm = mid.d[v];
+                        const float Rh = (up.d[v] + Dm) + dn.d[v];
+                        const float dv = dn.c[v] - up.c[v];
+                        if (MODE == MODE_MAG) {
+                            const float cv = Pv + dv, ch = Rh + Dm;
+                            g[v] = sqrtf(cv * cv + ch * ch + 1e-6f);
+                        } else {
+                            float c;
+                            unsigned cd;
+                            pick_directional(pft[u][v], Pv, Rh, Dm, dv, c, cd);
+                            g[v] = fabsf(c);
+                            code |= cd << (8 * v);
+                        }
+                    }
+                    const float p = SIG ? rcp_approx(1.0f + ex2_approx(fmaf(g[v], -1.4426950408889634f, kT))) : g[v];
+                    const float ee = pfe[u][v];
+                    const float ne = 1.0f - ee;
+                    const float lp = lg2_approx(p + kEps);
+                    const float ln = lg2_approx((1.0f - p) + kEps);
+                    la[A_SPU] = fmaf(ee, lp, la[A_SPU]);
+                    la[A_SNU] = fmaf(ne, ln, la[A_SNU]);
+                    if (MASK) {
+                        const float mm = pfm[u][v];
+                        la[A_WP] = fmaf(ee, mm, la[A_WP]);
+                        la[A_WN] = fmaf(ne, mm, la[A_WN]);
+                        la[A_SUMM] += mm;
+                        const bool keep = mm != 0.f;
+                        la[A_SPM] += keep ? ee * lp : 0.f;
+                        la[A_SNM] += keep ? ne * ln : 0.f;
+                        lflags |= (mm == 0.f) ? F_HAS0 : ((mm == 1.f) ? F_HAS1 : F_OTHER);
+                    } else {
+                        la[A_WP] += ee;
+                    }
+                }
+                if (more) fetch_t(u, j + PD);
+                const unsigned ro = (unsigned)(row0 + j) * W;
+                if (writeG) {
+                    float *gp = elem_addr(gP, ro);
+                    if (VEC == 4) st_stream4(gp, make_float4(g[0], g[1 % VEC], g[2 % VEC], g[3 % VEC]));
+                    else __stcs(gp, g[0]);
+                }
+                if (writeS) {
+                    if (VEC == 4) __stcs(reinterpret_cast<unsigned *>(sP + ro), code);
+                    else __stcs(sP + ro, (unsigned char)code);
+                }
             }
-            if (j + PD < RH) fetch(u, j + PD);
-            if (MODE != MODE_NONE) exchange_row<VEC>(newest);
-            const int row = row0 + j;
-            const bool ok = colOk && row < H;
-            if (MODE == MODE_NONE)
-                fwd_row<VEC, MODE, MASK, SIG>(P, S, plane, row, col0, ok, xr[0], xr[0], xr[0], e, th, m, la, lflags);
-            else
-                fwd_row<VEC, MODE, MASK, SIG>(P, S, plane, row, col0, ok, xr[u % 3], xr[(u + 1) % 3], xr[(u + 2) % 3], e,
-                                              th, m, la, lflags);
         }
     }
-    if (!writer) {  // halo lanes: discard (select, no NaN propagation)
+    if (!writer) {  // halo / out-of-image lanes: discard (select, no NaN propagation)
 #pragma unroll
         for (int k = 0; k < kAcc - 1; k++) la[k] = 0.f;
+        lflags = 0;
     }
 }
 
 template <int VEC, int MODE, bool MASK, bool INV, bool SIG>
 __global__ void __launch_bounds__(kThreads, MTE_FWD_MINB) edge_loss_fwd_kernel(const __grid_constant__ LossP P) {
-    constexpr int RH = kFwdRH;
-    constexpr int LANES = (MODE == MODE_NONE) ? 32 : kHaloLanes;
-    constexpr int OFF = (MODE == MODE_NONE) ? 0 : 1;
     const int lane = threadIdx.x & 31;
-    // the first item is static (no round trip before the first loads), later ones come from the atomic queue,
-    // which therefore starts at the number of warps in the grid
     const int nWarps = gridDim.x * kWarps;
-    int item = blockIdx.x * kWarps + (threadIdx.x >> 5);
-    while (item < P.totalItems) {
-        // claim the next item now: the atomic's round trip hides behind this item's work
-        int next = 0;
-        if (lane == 0) next = nWarps + (int)atomicAdd(P.ticket, 1u);
+    const int gw = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    int u0 = (int)((long long)P.totalUnits * gw / nWarps);
+    const int u1 = (int)((long long)P.totalUnits * (gw + 1) / nWarps);
+    while (u0 < u1) {
         int si = 0;
 #pragma unroll
         for (int k = 1; k < MTE_MAX_SCALES; k++)
-            if (k < P.nScales && item >= P.s[k].itemBase) si = k;
+            if (k < P.nScales && u0 >= P.s[k].unitBase) si = k;
         const ScaleP &S = P.s[si];
-        const int local = item - S.itemBase;
-        const int img = local / S.items;
-        const int it = local - img * S.items;
-        const int strip = it / S.rowBlocks;
-        const int rb = it - strip * S.rowBlocks;
-        const int row0 = rb * RH;
-        const int colFirst = (strip * LANES - OFF) * VEC;  // column of lane 0
+        const int local = u0 - S.unitBase;
+        const int t = local / S.H;  // (image, strip)
+        const int row0 = local - t * S.H;
+        const int nrows = min(S.H - row0, u1 - u0);
+        const int img = t / S.strips;
+        const int strip = t - img * S.strips;
         float la[kAcc - 1];
 #pragma unroll
         for (int k = 0; k < kAcc - 1; k++) la[k] = 0.f;
         unsigned lflags = 0;
-        fwd_item<VEC, MODE, MASK, INV, SIG>(P, S, img, row0, colFirst, lane, la, lflags);
+        fwd_segment<VEC, MODE, MASK, INV, SIG>(P, S, img, strip, row0, nrows, lane, la, lflags);
         // order-independent accumulation: warp tree (fixed) -> 2^32 fixed point -> integer atomics
         unsigned long long *acc = P.accum + (size_t)(S.imgBase + img) * kAcc;
 #pragma unroll
@@ -490,19 +577,26 @@ __global__ void __launch_bounds__(kThreads, MTE_FWD_MINB) edge_loss_fwd_kernel(c
             lflags = warp_or(lflags);
             if (lane == 0 && lflags) atomicOr(acc + A_FLAGS, (unsigned long long)lflags);
         }
-        item = __shfl_sync(MTE_FULL_MASK, next, 0);
+        u0 += nrows;
     }
-    // the last warp to leave finalises
-    int last = 0;
-    if (lane == 0) {
+    // the last CTA to leave finalises (its warps share the scales)
+    __shared__ double sLoss[MTE_MAX_SCALES];
+    __shared__ int sLast;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) sLast = atomicAdd(P.ticket + 1, 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (sLast) {
         __threadfence();
-        const unsigned t = atomicAdd(P.ticket + 1, 1u);
-        last = (t == gridDim.x * kWarps - 1u);
-    }
-    last = __shfl_sync(MTE_FULL_MASK, last, 0);
-    if (last) {
-        __threadfence();
-        finalize_loss(P, MASK);
+        finalize_loss<MASK>(P, sLoss);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double total = 0.0;
+            for (int k = 0; k < P.nScales; k++) total += (double)P.s[k].scaleWeight * sLoss[k];
+            P.lossOut[0] = (float)total;
+            P.ticket[0] = 0u;  // leave the workspace header clean for the next launch
+            P.ticket[1] = 0u;
+        }
     }
 }
 
@@ -785,7 +879,7 @@ __global__ void __launch_bounds__(kThreads, 2) edge_loss_bwd_stash_kernel(const 
 #pragma unroll
             for (int v = 0; v < VEC; v++) {
                 float d = dloss_dg<MASK, SIG>(g[v], e[v], m[v], I, P.T);
-                d = live ? d : 0.f;
+                d = (live && g[v] != 0.f) ? d : 0.f;  // sign(0) = 0: a zero response passes no gradient
                 const float4 k = sLut[(codes >> (8 * v)) & 15u];
                 A[v] = d * k.x; C[v] = d * k.y; A2[v] = d * k.z; C2[v] = d * k.w;
             }

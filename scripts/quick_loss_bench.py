@@ -22,7 +22,7 @@ def make(B, H, W, scales, nsets, dev):
 def run(B, H, W, scales, nsets, iters=50):
     dev = torch.device("cuda:0")
     sets = make(B, H, W, scales, nsets, dev)
-    at = _attrs(True, True, False, 4.0, 10.0, 1.0)
+    at = _attrs(True, True, not os.environ.get("MTE_QB_NOINV"), 4.0, 10.0, 1.0)
     structs = []
     use_stash = not os.environ.get("MTE_LOSS_NO_STASH")
     for pred, edge, normal, gmap, gpred, stash in sets:
@@ -33,18 +33,29 @@ def run(B, H, W, scales, nsets, iters=50):
     ws = runtime.workspace(dev, _lib.lib.mte_edge_loss_workspace_bytes(structs[0][0], n))
     gl = torch.zeros(1 + n, device=dev); gl[0] = 1.0
     st = runtime.current_stream_ptr(dev)
+    out = {}
     def fwd(i): _lib.check(_lib.lib.mte_edge_loss_fwd(structs[i][0], n, C.byref(at), losses.data_ptr(), ctx.data_ptr(), ws.data_ptr(), ws.numel(), st))
     def bwd(i): _lib.check(_lib.lib.mte_edge_loss_bwd(structs[i][1], n, C.byref(at), gl.data_ptr(), ctx.data_ptr(), ws.data_ptr(), ws.numel(), st))
     px = sum(B * (H >> s) * (W >> s) for s in range(scales))
     out = {}
+    # device time per kernel: CUDA-graph replays of `nsets` back-to-back launches (no CPU launch gaps)
+    stream = torch.cuda.Stream(dev)
+    st = stream.cuda_stream
     for name, fn in (("fwd", fwd), ("bwd", bwd)):
-        for i in range(5): fn(i % nsets)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(iters): fn(i % nsets)
-        e1.record(); torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) * 1000 / iters
+        with torch.cuda.stream(stream):
+            for i in range(nsets): fn(i)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                for i in range(nsets): fn(i)
+            for _ in range(3): g.replay()
+            torch.cuda.synchronize()
+            reps = max(1, iters // nsets)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps): g.replay()
+            e1.record(stream); torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1000 / (reps * nsets)
         out[name] = dict(us=round(us, 2), gpx_s=round(px / us / 1e3, 1), gbs=round(16 * px / us / 1e3, 1))
     return dict(B=B, H=H, W=W, scales=scales, nsets=nsets, mpx=px / 1e6, **out)
 
