@@ -183,7 +183,7 @@ static int make_plan(Plan &pl, const mte_loss_scale_t *sc, int n, const mte_loss
         S.ctasPerImage = ceil_div(S.items, kWarps);  // capped below: warps loop over several items
         S.ctaBase = cta; S.imgBase = img;
         S.unitBase = (int)unitBase;
-        unitBase += (long long)S.strips * S.H * S.B;
+        unitBase += (long long)S.strips * (S.H + (bwd ? kSegCostB : kSegCost)) * S.B;
         S.scaleWeight = sc[i].scale_weight;
         cta += S.ctasPerImage * S.B;
         img += S.B;
@@ -328,7 +328,10 @@ extern "C" int mte_edge_loss_bwd(const mte_loss_scale_t *sc, int n, const mte_lo
     } else {
         const int mode = pl.hasNormal ? MODE_DIR : MODE_MAG;
         if (can_use_stash(sc, n, at)) {
-            if (pl.vec) launch_bwd_stash_v4(P, pl.hasMask, at->pred_is_inverse != 0, at->is_sigmoid != 0, st);
+            if (pl.vec && !getenv("MTE_LOSS_BWD_OLD")) {
+                P.totalCtas = pl.fwdGrid;  // persistent grid over the cost-balanced unit ranges
+                launch_bwd_ring_v4(P, pl.hasMask, at->pred_is_inverse != 0, at->is_sigmoid != 0, st);
+            } else if (pl.vec) launch_bwd_stash_v4(P, pl.hasMask, at->pred_is_inverse != 0, at->is_sigmoid != 0, st);
             else launch_bwd_stash_v1(P, pl.hasMask, at->pred_is_inverse != 0, at->is_sigmoid != 0, st);
         } else if (pl.vec) launch_bwd_v4(P, mode, pl.hasMask, at->pred_is_inverse != 0, at->is_sigmoid != 0, st);
         else launch_bwd_v1(P, mode, pl.hasMask, at->pred_is_inverse != 0, at->is_sigmoid != 0, st);

@@ -3,7 +3,7 @@
 namespace mte { namespace loss {
 template <int MODE> static void go_fwd_v1(const LossP &P, bool mask, bool inv, bool sig, cudaStream_t st) {
     MTE_LOSS_DISPATCH_BOOL(mask, MASK, MTE_LOSS_DISPATCH_BOOL(inv, INV, MTE_LOSS_DISPATCH_BOOL(sig, SIG,
-        edge_loss_fwd_kernel<1, MODE, MASK, INV, SIG><<<P.totalCtas, kThreads, 0, st>>>(P);)))
+        launch_fwd_one<1, MODE, MASK, INV, SIG>(P, st);)))
 }
 void launch_fwd_v1(const LossP &P, int mode, bool mask, bool inv, bool sig, cudaStream_t st) {
     if (mode == MODE_NONE) go_fwd_v1<MODE_NONE>(P, mask, inv, sig, st); else

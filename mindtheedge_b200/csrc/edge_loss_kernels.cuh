@@ -35,6 +35,7 @@ enum { MODE_NONE = 0, MODE_MAG = 1, MODE_DIR = 2 };
 #endif
 constexpr int kFwdRH = MTE_FWD_RH;   // output rows per forward work item
 constexpr int kBwdRH = 8;   // output rows per backward work item
+constexpr int kSegCost = 4;     // forward partition: cost of opening a segment, in rows
 constexpr int kHaloLanes = 30;  // writing lanes of an overlapped strip (one halo lane per side)
 // The backward needs the coefficient of the neighbouring pixel, i.e. depth two columns out: with
 // VEC=1 that is two halo lanes per side.
@@ -373,19 +374,50 @@ __device__ __forceinline__ float lg2_approx(float x) {  // arguments here are >=
     return r;
 }
 
+// ---- asynchronous global -> shared row ring (cp.async / LDGSTS) ----------------------------------------------
+// Every lane copies its own VEC*4 bytes of a row into its own slot of the warp's ring and later reads only that slot
+// back, so no cross-lane synchronisation is needed: cp.async.wait_group orders a thread's own copies.  The ring
+// keeps kRingDepth rows per warp in flight without holding registers (a register ring of that depth would not fit).
+template <int VEC>
+__device__ __forceinline__ void cp_async_vec(unsigned dst, const void *src, bool ok) {  // !ok: zero-fill
+    const unsigned n = ok ? VEC * 4u : 0u;
+    if (VEC == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+template <int VEC>
+__device__ __forceinline__ void lds_vec(float (&out)[VEC], const unsigned char *p) {
+    if (VEC == 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(p);
+        out[0] = v.x; out[1 % VEC] = v.y; out[2 % VEC] = v.z; out[3 % VEC] = v.w;
+    } else {
+        out[0] = *reinterpret_cast<const float *>(p);
+    }
+}
+
+__host__ __device__ constexpr int fwd_planes(int mode, bool mask) { return 2 + (mode == MODE_DIR ? 1 : 0) + (mask ? 1 : 0); }
+__host__ __device__ constexpr int fwd_ring_depth(int mode, bool mask) { return fwd_planes(mode, mask) >= 4 ? 6 : 8; }
+__host__ __device__ constexpr int fwd_smem_bytes(int vec, int mode, bool mask) {
+    return kWarps * fwd_ring_depth(mode, mask) * fwd_planes(mode, mask) * 32 * vec * 4;
+}
+
 // Forward work decomposition: the unit is one row of one strip (32 lanes x VEC px, LANES of them writing) of one
 // image of one scale; units are ordered scale, image, strip, row and every warp of the persistent grid owns one
 // contiguous, equally long range of them (the cost of a unit does not depend on its content), cut into segments
-// at strip ends.  A segment streams its rows through a 3-row register window fed by a PD-row prefetch ring; ring
-// slots are refilled right after their last use, so no register copies are needed.
+// at strip ends.  A segment streams its rows through a 3-row register window fed by the shared-memory row ring.
 template <int VEC, int MODE, bool MASK, bool INV, bool SIG>
 __device__ __forceinline__ void fwd_segment(const LossP &P, const ScaleP &S, int img, int strip, int row0, int nrows,
-                                            int lane, float (&la)[kAcc - 1], unsigned &lflags) {
-    constexpr int PD = 3;
+                                            int lane, unsigned char *ring, float (&la)[kAcc - 1], unsigned &lflags) {
+    constexpr int D = fwd_ring_depth(MODE, MASK);
+    constexpr int NPL = fwd_planes(MODE, MASK);
+    constexpr unsigned PLB = 32 * VEC * 4;     // bytes of one plane row in a slot
+    constexpr unsigned SLB = NPL * PLB;        // bytes of a slot
     constexpr int OFF = (MODE == MODE_NONE) ? 0 : 1;
     constexpr int LANES = (MODE == MODE_NONE) ? 32 : kHaloLanes;
-    // out-of-image depth reads as 0 (zero padding of conv2d); with the fused inv2depth the fill is a huge inverse
-    // depth whose reciprocal flushes to exactly 0
+    // out-of-image depth reads as 0 (zero padding of conv2d): the copies zero-fill; with the fused inv2depth the
+    // fill must be a huge inverse depth whose reciprocal flushes to exactly 0, selected when the row is consumed
     constexpr float kFill = INV ? 3.0e38f : 0.f;
     const int H = S.H;
     const unsigned W = (unsigned)S.W;
@@ -393,41 +425,35 @@ __device__ __forceinline__ void fwd_segment(const LossP &P, const ScaleP &S, int
     const bool colOk = col0 >= 0 && col0 < (int)W;
     const bool writer = colOk && (MODE == MODE_NONE || (lane >= 1 && lane <= kHaloLanes));
     // per-lane plane pointers at (row 0, clamped col0); rows are reached with one 32-bit element offset shared by
-    // all planes (one IMAD.WIDE per access).  Lanes outside the image read a valid dummy column and are either
-    // replaced by the zero padding (depth) or discarded (targets).
+    // all planes (one IMAD.WIDE per access)
     const size_t lo = (size_t)img * H * W + (colOk ? col0 : 0);
     const float *xP = S.x + lo, *eP = S.e + lo, *nP = S.n + lo, *mP = S.m + lo;
     float *gP = S.g + lo;
     unsigned char *sP = S.stash + lo;
     const bool writeG = writer && S.g != nullptr, writeS = writer && (MODE == MODE_DIR) && S.stash != nullptr;
     const float kT = P.T * 1.4426950408889634f;
+    unsigned char *slot0 = ring + lane * (VEC * 4);
+    const unsigned ringS = (unsigned)__cvta_generic_to_shared(slot0);
+    constexpr int PL_E = 1, PL_N = 2, PL_M = (MODE == MODE_DIR) ? 3 : 2;
 
-    float pfx[PD][VEC], pfe[PD][VEC], pft[PD][VEC], pfm[PD][VEC];
-    auto load_v = [&](float (&out)[VEC], const float *base, unsigned ro, bool cached) {
-        const float *p = elem_addr(base, ro);
-        if (VEC == 4) {
-            const float4 v = cached ? ld_cached4(p) : ld_stream4(p);
-            out[0] = v.x; out[1 % VEC] = v.y; out[2 % VEC] = v.z; out[3 % VEC] = v.w;
-        } else {
-            out[0] = cached ? __ldg(p) : __ldcs(p);
+    // copies of everything output row j needs that is not in the window yet: depth row row0 + j + OFF, target rows
+    // row0 + j (writer lanes only; the others never look at their slots)
+    auto issue = [&](unsigned so, int j) {
+        const int rx = row0 + j + OFF;
+        cp_async_vec<VEC>(ringS + so, elem_addr(xP, (unsigned)min(rx, H - 1) * W), colOk && rx < H);
+        if (writer) {
+            const unsigned ro = (unsigned)(row0 + j) * W;
+            cp_async_vec<VEC>(ringS + so + PL_E * PLB, elem_addr(eP, ro), true);
+            if (MODE == MODE_DIR) cp_async_vec<VEC>(ringS + so + PL_N * PLB, elem_addr(nP, ro), true);
+            if (MASK) cp_async_vec<VEC>(ringS + so + PL_M * PLB, elem_addr(mP, ro), true);
         }
     };
-    // depth row `row` (may be -1 or H: zero padding): unconditional load from the clamped row; the padding select is
-    // applied when the row is CONSUMED (a select next to the load would wait for it and defeat the prefetch)
-    auto load_x = [&](float (&out)[VEC], int row) {
-        const int rc = min(max(row, 0), H - 1);
-        load_v(out, xP, (unsigned)rc * W, true);
-    };
     auto pad_x = [&](float (&x)[VEC], int row) {
-        const bool ok = colOk && row >= 0 && row < H;
+        if (INV) {
+            const bool ok = colOk && row >= 0 && row < H;
 #pragma unroll
-        for (int v = 0; v < VEC; v++) x[v] = ok ? x[v] : kFill;
-    };
-    auto fetch_t = [&](int slot, int j) {
-        const unsigned ro = (unsigned)(row0 + j) * W;
-        load_v(pfe[slot], eP, ro, false);
-        if (MODE == MODE_DIR) load_v(pft[slot], nP, ro, false);
-        if (MASK) load_v(pfm[slot], mP, ro, false);
+            for (int v = 0; v < VEC; v++) x[v] = ok ? x[v] : kFill;
+        }
     };
     auto to_depth = [&](float (&x)[VEC]) {
         if (INV) {
@@ -438,16 +464,25 @@ __device__ __forceinline__ void fwd_segment(const LossP &P, const ScaleP &S, int
 
     PRow<VEC> win[3];  // win[d % 3] holds depth row row0 - OFF + d
     float xa[VEC], xc[VEC];
-    if (MODE != MODE_NONE) {
-        load_x(xa, row0 - 1);
-        load_x(xc, row0);
+#pragma unroll
+    for (int v = 0; v < VEC; v++) { xa[v] = 0.f; xc[v] = 0.f; }
+    if (MODE != MODE_NONE) {  // the two rows that open the window: plain loads
+        if (colOk && row0 >= 1) {
+            const float *p = elem_addr(xP, (unsigned)(row0 - 1) * W);
+            if (VEC == 4) { const float4 v = ld_cached4(p); xa[0] = v.x; xa[1 % VEC] = v.y; xa[2 % VEC] = v.z; xa[3 % VEC] = v.w; }
+            else xa[0] = __ldg(p);
+        }
+        if (colOk) {
+            const float *p = elem_addr(xP, (unsigned)row0 * W);
+            if (VEC == 4) { const float4 v = ld_cached4(p); xc[0] = v.x; xc[1 % VEC] = v.y; xc[2 % VEC] = v.z; xc[3 % VEC] = v.w; }
+            else xc[0] = __ldg(p);
+        }
     }
 #pragma unroll
-    for (int k = 0; k < PD; k++)
-        if (k < nrows) {  // output row k needs depth row row0 + k + OFF and the target rows row0 + k
-            load_x(pfx[k], row0 + k + OFF);
-            fetch_t(k, k);
-        }
+    for (int k = 0; k < D; k++) {
+        if (k < nrows) issue(k * SLB, k);
+        cp_async_commit();
+    }
     if (MODE != MODE_NONE) {
         pad_x(xa, row0 - 1);
         pad_x(xc, row0);
@@ -456,23 +491,26 @@ __device__ __forceinline__ void fwd_segment(const LossP &P, const ScaleP &S, int
         prep_row<VEC, MODE>(win[0], xa);
         prep_row<VEC, MODE>(win[1], xc);
     }
+    unsigned so = 0;  // ring slot (byte offset) of the row being consumed
 #pragma unroll 1
     for (int jj = 0; jj < nrows; jj += 3) {
 #pragma unroll
         for (int u = 0; u < 3; u++) {
             const int j = jj + u;
             if (j < nrows) {  // warp-uniform
-                const bool more = j + PD < nrows;
+                cp_async_wait<D - 1>();
+                float xn[VEC], e[VEC], th[VEC], m[VEC];
+                lds_vec<VEC>(xn, slot0 + so);
+                lds_vec<VEC>(e, slot0 + so + PL_E * PLB);
+                if (MODE == MODE_DIR) lds_vec<VEC>(th, slot0 + so + PL_N * PLB);
+                if (MASK) lds_vec<VEC>(m, slot0 + so + PL_M * PLB);
+                if (j + D < nrows) issue(so, j + D);  // refill the slot just read
+                cp_async_commit();
+                so = (so + SLB == D * SLB) ? 0u : so + SLB;
                 PRow<VEC> &dn = win[(MODE == MODE_NONE) ? 0 : (u + 2) % 3];
-                {
-                    float xn[VEC];
-#pragma unroll
-                    for (int v = 0; v < VEC; v++) xn[v] = pfx[u][v];
-                    pad_x(xn, row0 + j + OFF);
-                    to_depth(xn);
-                    if (more) load_x(pfx[u], row0 + j + PD + OFF);
-                    prep_row<VEC, MODE>(dn, xn);
-                }
+                pad_x(xn, row0 + j + OFF);
+                to_depth(xn);
+                prep_row<VEC, MODE>(dn, xn);
                 const PRow<VEC> &up = win[(MODE == MODE_NONE) ? 0 : u % 3];
                 const PRow<VEC> &mid = win[(MODE == MODE_NONE) ? 0 : (u + 1) % 3];
                 float g[VEC];
@@ -494,20 +532,20 @@ __device__ __forceinline__ void fwd_segment(const LossP &P, const ScaleP &S, int
                         } else {
                             float c;
                             unsigned cd;
-                            pick_directional(pft[u][v], Pv, Rh, Dm, dv, c, cd);
+                            pick_directional(th[v], Pv, Rh, Dm, dv, c, cd);
                             g[v] = fabsf(c);
                             code |= cd << (8 * v);
                         }
                     }
                     const float p = SIG ? rcp_approx(1.0f + ex2_approx(fmaf(g[v], -1.4426950408889634f, kT))) : g[v];
-                    const float ee = pfe[u][v];
+                    const float ee = e[v];
                     const float ne = 1.0f - ee;
                     const float lp = lg2_approx(p + kEps);
                     const float ln = lg2_approx((1.0f - p) + kEps);
                     la[A_SPU] = fmaf(ee, lp, la[A_SPU]);
                     la[A_SNU] = fmaf(ne, ln, la[A_SNU]);
                     if (MASK) {
-                        const float mm = pfm[u][v];
+                        const float mm = m[v];
                         la[A_WP] = fmaf(ee, mm, la[A_WP]);
                         la[A_WN] = fmaf(ne, mm, la[A_WN]);
                         la[A_SUMM] += mm;
@@ -519,7 +557,6 @@ __device__ __forceinline__ void fwd_segment(const LossP &P, const ScaleP &S, int
                         la[A_WP] += ee;
                     }
                 }
-                if (more) fetch_t(u, j + PD);
                 const unsigned ro = (unsigned)(row0 + j) * W;
                 if (writeG) {
                     float *gp = elem_addr(gP, ro);
@@ -533,6 +570,7 @@ __device__ __forceinline__ void fwd_segment(const LossP &P, const ScaleP &S, int
             }
         }
     }
+    cp_async_wait<0>();
     if (!writer) {  // halo / out-of-image lanes: discard (select, no NaN propagation)
 #pragma unroll
         for (int k = 0; k < kAcc - 1; k++) la[k] = 0.f;
@@ -542,9 +580,11 @@ __device__ __forceinline__ void fwd_segment(const LossP &P, const ScaleP &S, int
 
 template <int VEC, int MODE, bool MASK, bool INV, bool SIG>
 __global__ void __launch_bounds__(kThreads, MTE_FWD_MINB) edge_loss_fwd_kernel(const __grid_constant__ LossP P) {
+    extern __shared__ __align__(16) unsigned char fwdRing[];
     const int lane = threadIdx.x & 31;
     const int nWarps = gridDim.x * kWarps;
     const int gw = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    unsigned char *ring = fwdRing + (threadIdx.x >> 5) * (fwd_smem_bytes(VEC, MODE, MASK) / kWarps);
     int u0 = (int)((long long)P.totalUnits * gw / nWarps);
     const int u1 = (int)((long long)P.totalUnits * (gw + 1) / nWarps);
     while (u0 < u1) {
@@ -553,17 +593,24 @@ __global__ void __launch_bounds__(kThreads, MTE_FWD_MINB) edge_loss_fwd_kernel(c
         for (int k = 1; k < MTE_MAX_SCALES; k++)
             if (k < P.nScales && u0 >= P.s[k].unitBase) si = k;
         const ScaleP &S = P.s[si];
+        // a strip is H rows plus kSegCost virtual units that stand for the cost of opening a segment (window
+        // prologue + pipeline fill), so ranges that span several strips are charged for it
         const int local = u0 - S.unitBase;
-        const int t = local / S.H;  // (image, strip)
-        const int row0 = local - t * S.H;
-        const int nrows = min(S.H - row0, u1 - u0);
+        const int HV = S.H + kSegCost;
+        const int t = local / HV;  // (image, strip)
+        const int r = local - t * HV;
+        const int take = min(HV - r, u1 - u0);
+        const int row0 = max(r - kSegCost, 0);
+        const int nrows = max(r + take - kSegCost, 0) - row0;
+        u0 += take;
+        if (nrows <= 0) continue;
         const int img = t / S.strips;
         const int strip = t - img * S.strips;
         float la[kAcc - 1];
 #pragma unroll
         for (int k = 0; k < kAcc - 1; k++) la[k] = 0.f;
         unsigned lflags = 0;
-        fwd_segment<VEC, MODE, MASK, INV, SIG>(P, S, img, strip, row0, nrows, lane, la, lflags);
+        fwd_segment<VEC, MODE, MASK, INV, SIG>(P, S, img, strip, row0, nrows, lane, ring, la, lflags);
         // order-independent accumulation: warp tree (fixed) -> 2^32 fixed point -> integer atomics
         unsigned long long *acc = P.accum + (size_t)(S.imgBase + img) * kAcc;
 #pragma unroll
@@ -577,17 +624,20 @@ __global__ void __launch_bounds__(kThreads, MTE_FWD_MINB) edge_loss_fwd_kernel(c
             lflags = warp_or(lflags);
             if (lane == 0 && lflags) atomicOr(acc + A_FLAGS, (unsigned long long)lflags);
         }
-        u0 += nrows;
     }
     // the last CTA to leave finalises (its warps share the scales)
     __shared__ double sLoss[MTE_MAX_SCALES];
     __shared__ int sLast;
-    __threadfence();
+    // grid-wide "last CTA" detection in the cooperative-groups grid-sync style: the CTA barrier orders every warp's
+    // accumulator atomics before thread 0's cumulative fence + ticket
     __syncthreads();
-    if (threadIdx.x == 0) sLast = atomicAdd(P.ticket + 1, 1u) == gridDim.x - 1u;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        sLast = atomicAdd(P.ticket + 1, 1u) == gridDim.x - 1u;
+        __threadfence();
+    }
     __syncthreads();
     if (sLast) {
-        __threadfence();
         finalize_loss<MASK>(P, sLoss);
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -921,12 +971,197 @@ __global__ void __launch_bounds__(kThreads, 2) edge_loss_bwd_stash_kernel(const 
     }
 }
 
+// ---------------------------------------------------------------------------
+// Backward from the stash, streaming version (VEC = 4): same decomposition as the forward -- persistent warps, each
+// owning an equal, cost-balanced range of strip rows, fed by a cp.async shared-memory row ring -- around the
+// per-pixel work of edge_loss_bwd_stash_kernel.  Rows / columns outside the image are zero-filled by the copies:
+// a zero stash byte selects the all-zero table entry, so padding needs no predicates in the row loop.
+// ---------------------------------------------------------------------------
+constexpr int kSegCostB = 5;
+__host__ __device__ constexpr int bwd_ring_depth(bool mask, bool inv) { return (mask && inv) ? 5 : 6; }
+__host__ __device__ constexpr int bwd_slot_bytes(bool mask, bool inv) { return (2 + (mask ? 1 : 0) + (inv ? 1 : 0)) * 512 + 128; }
+__host__ __device__ constexpr int bwd_smem_bytes(bool mask, bool inv) { return kWarps * bwd_ring_depth(mask, inv) * bwd_slot_bytes(mask, inv); }
+
+template <bool MASK, bool INV, bool SIG>
+__global__ void __launch_bounds__(kThreads, 2) edge_loss_bwd_ring_kernel(const __grid_constant__ LossP P) {
+    constexpr int VEC = 4;
+    constexpr int D = bwd_ring_depth(MASK, INV);
+    constexpr unsigned PLB = 512, SLB = bwd_slot_bytes(MASK, INV);
+    constexpr unsigned O_G = 0, O_E = PLB, O_M = 2 * PLB, O_X = (MASK ? 3 : 2) * PLB, O_S = SLB - 128;
+    extern __shared__ __align__(16) unsigned char bwdRing[];
+    __shared__ float4 sLut[16];  // per code: (A, C, A2, C2) for s = 1
+    if (threadIdx.x < 16) {
+        const int di = threadIdx.x & 3, sg = threadIdx.x >> 2;
+        const float sgn = sg == 1 ? 1.f : (sg == 2 ? -1.f : 0.f);
+        const float a = (di == 2 || di == 3) ? 1.f : (di == 1 ? -1.f : 0.f);  // h:0 rl:-1 v:1 lr:1
+        const float c = (di == 2) ? 0.f : 1.f;                                // h:1 rl:1 v:0 lr:1
+        const float bb = (di & 1) ? 1.f : 2.f;                                // axis stencils weigh the centre twice
+        sLut[threadIdx.x] = make_float4(sgn * a, sgn * c, sgn * a * bb, sgn * c * bb);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *ring = bwdRing + warp * (D * SLB);
+    unsigned char *slot0 = ring + lane * 16, *slotS = ring + O_S + lane * 4;
+    const unsigned ringS = (unsigned)__cvta_generic_to_shared(slot0);
+    const unsigned ringSS = (unsigned)__cvta_generic_to_shared(slotS);
+    const int nWarps = gridDim.x * kWarps;
+    const int gw = blockIdx.x * kWarps + warp;
+    int u0 = (int)((long long)P.totalUnits * gw / nWarps);
+    const int u1 = (int)((long long)P.totalUnits * (gw + 1) / nWarps);
+    while (u0 < u1) {
+        int si = 0;
+#pragma unroll
+        for (int k = 1; k < MTE_MAX_SCALES; k++)
+            if (k < P.nScales && u0 >= P.s[k].unitBase) si = k;
+        const ScaleP &S = P.s[si];
+        const int local = u0 - S.unitBase;
+        const int HV = S.H + kSegCostB;
+        const int t = local / HV;  // (image, strip)
+        const int r = local - t * HV;
+        const int take = min(HV - r, u1 - u0);
+        const int row0 = max(r - kSegCostB, 0);
+        const int nrows = max(r + take - kSegCostB, 0) - row0;
+        u0 += take;
+        if (nrows <= 0) continue;
+        const int img = t / S.strips;
+        const int strip = t - img * S.strips;
+        const int H = S.H;
+        const unsigned W = (unsigned)S.W;
+
+        BwdImg I;
+        {
+            const float G = __ldg(P.gradLoss) * S.scaleWeight + __ldg(P.gradLoss + 1 + si);
+            const float coef = __ldg(P.ctx + P.totalImages + 2 * si) * G;
+            const float alpha = __ldg(P.ctx + S.imgBase + img);
+            I.cp = -coef * P.p2n * alpha;
+            I.cn = coef * (1.0f - alpha);
+            I.maskBinary = MASK && (__ldg(P.ctx + P.totalImages + 2 * si + 1) != 0.f);
+        }
+        // one halo lane per side (the coefficients are pointwise): lanes 1..30 write
+        const int col0 = (strip * kHaloLanes + lane - 1) * VEC;
+        const bool colOk = col0 >= 0 && col0 < (int)W;
+        const bool writer = lane >= 1 && lane <= kHaloLanes && colOk;
+        const size_t lo = (size_t)img * H * W + (colOk ? col0 : 0);
+        const float *gP = S.g + lo, *eP = S.e + lo, *mP = S.m + lo, *xP = S.x + lo;
+        const unsigned char *sP = S.stash + lo;
+        float *dP = S.dx + lo;
+
+        // coefficient row j of the segment is image row row0 - 1 + j, j = 0 .. nrows + 1
+        const int ncoef = nrows + 2;
+        auto issue = [&](unsigned so, int j) {
+            const int row = row0 - 1 + j;
+            const bool ok = colOk && row >= 0 && row < H;
+            const unsigned ro = (unsigned)min(max(row, 0), H - 1) * W;
+            cp_async_vec<4>(ringS + so + O_G, elem_addr(gP, ro), ok);
+            cp_async_vec<4>(ringS + so + O_E, elem_addr(eP, ro), ok);
+            if (MASK) cp_async_vec<4>(ringS + so + O_M, elem_addr(mP, ro), ok);
+            if (INV) cp_async_vec<4>(ringS + so + O_X, elem_addr(xP, ro), ok);
+            cp_async_vec<1>(ringSS + so, sP + ro, ok);
+        };
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            if (k < ncoef) issue(k * SLB, k);
+            cp_async_commit();
+        }
+        float oacc[3][VEC], xrow[3][VEC];
+#pragma unroll
+        for (int o = 0; o < 3; o++)
+#pragma unroll
+            for (int v = 0; v < VEC; v++) { oacc[o][v] = 0.f; xrow[o][v] = 0.f; }
+        unsigned so = 0;
+#pragma unroll 1
+        for (int jj = 0; jj < ncoef; jj += 3) {
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+                const int j = jj + u;
+                if (j < ncoef) {  // warp-uniform
+                    cp_async_wait<D - 1>();
+                    float g[VEC], e[VEC], m[VEC];
+                    lds_vec<VEC>(g, slot0 + so + O_G);
+                    lds_vec<VEC>(e, slot0 + so + O_E);
+                    if (MASK) lds_vec<VEC>(m, slot0 + so + O_M);
+                    if (INV) lds_vec<VEC>(xrow[u], slot0 + so + O_X);
+                    const unsigned codes = *reinterpret_cast<const unsigned *>(slotS + so);
+                    if (j + D < ncoef) issue(so, j + D);
+                    cp_async_commit();
+                    so = (so + SLB == D * SLB) ? 0u : so + SLB;
+                    float A[VEC], C[VEC], A2[VEC], C2[VEC];
+#pragma unroll
+                    for (int v = 0; v < VEC; v++) {
+                        float d = dloss_dg<MASK, SIG>(g[v], e[v], MASK ? m[v] : 1.f, I, P.T);
+                        d = (g[v] != 0.f) ? d : 0.f;  // sign(0) = 0: a zero response passes no gradient
+                        const float4 k = sLut[(codes >> (8 * v)) & 15u];
+                        A[v] = d * k.x; C[v] = d * k.y; A2[v] = d * k.z; C2[v] = d * k.w;
+                    }
+                    const float Al = __shfl_up_sync(MTE_FULL_MASK, A[VEC - 1], 1), Ar = __shfl_down_sync(MTE_FULL_MASK, A[0], 1);
+                    const float Cl = __shfl_up_sync(MTE_FULL_MASK, C[VEC - 1], 1), Cr = __shfl_down_sync(MTE_FULL_MASK, C[0], 1);
+                    const float C2l = __shfl_up_sync(MTE_FULL_MASK, C2[VEC - 1], 1), C2r = __shfl_down_sync(MTE_FULL_MASK, C2[0], 1);
+                    // this coefficient row acts as "up" for output row j (image row row0 - 1 + j ... stored as
+                    // segment output o = j), as "mid" for o = j - 1 and as "down" for o = j - 2, which it completes
+#pragma unroll
+                    for (int v = 0; v < VEC; v++) {
+                        const float a_l = v == 0 ? Al : A[(v + VEC - 1) % VEC], a_r = v == VEC - 1 ? Ar : A[(v + 1) % VEC];
+                        const float c_l = v == 0 ? Cl : C[(v + VEC - 1) % VEC], c_r = v == VEC - 1 ? Cr : C[(v + 1) % VEC];
+                        const float c2_l = v == 0 ? C2l : C2[(v + VEC - 1) % VEC], c2_r = v == VEC - 1 ? C2r : C2[(v + 1) % VEC];
+                        const float SA = (a_l + a_r) + A2[v], DC = c_l - c_r;
+                        oacc[u][v] = SA + DC;
+                        oacc[(u + 2) % 3][v] += c2_l - c2_r;
+                        oacc[(u + 1) % 3][v] -= SA - DC;
+                    }
+                    if (j >= 2) {
+                        float out[VEC];
+#pragma unroll
+                        for (int v = 0; v < VEC; v++) {
+                            float d = oacc[(u + 1) % 3][v];
+                            if (INV) {
+                                // pred was an inverse depth: chain through depth = 1/clamp(inv, 1e-6); the inverse depth
+                                // of this output row came with coefficient row j - 1
+                                const float inv = xrow[(u + 2) % 3][v];
+                                const float dep = rcp_approx(fmaxf(inv, 1e-6f));
+                                d = (inv > 1e-6f) ? -d * dep * dep : 0.f;
+                            }
+                            out[v] = d;
+                        }
+                        if (writer)
+                            st_stream4(elem_addr(dP, (unsigned)(row0 + j - 2) * W), make_float4(out[0], out[1], out[2], out[3]));
+                    }
+                }
+            }
+        }
+        cp_async_wait<0>();
+    }
+}
+
+template <bool MASK, bool INV, bool SIG>
+static void launch_bwd_ring_one(const LossP &P, cudaStream_t st) {
+    constexpr int smem = bwd_smem_bytes(MASK, INV);
+    static bool optedIn = false;
+    if (!optedIn) {
+        cudaFuncSetAttribute(edge_loss_bwd_ring_kernel<MASK, INV, SIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        optedIn = true;
+    }
+    edge_loss_bwd_ring_kernel<MASK, INV, SIG><<<P.totalCtas, kThreads, smem, st>>>(P);
+}
+
+// the forward's row ring lives in dynamic shared memory (> 48 KB: opt in once per instantiation)
+template <int VEC, int MODE, bool MASK, bool INV, bool SIG>
+static void launch_fwd_one(const LossP &P, cudaStream_t st) {
+    constexpr int smem = fwd_smem_bytes(VEC, MODE, MASK);
+    static bool optedIn = false;
+    if (!optedIn) {
+        cudaFuncSetAttribute(edge_loss_fwd_kernel<VEC, MODE, MASK, INV, SIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        optedIn = true;
+    }
+    edge_loss_fwd_kernel<VEC, MODE, MASK, INV, SIG><<<P.totalCtas, kThreads, smem, st>>>(P);
+}
+
 // launchers implemented one translation unit per (direction, VEC) so they compile in parallel
 void launch_fwd_v4(const LossP &P, int mode, bool mask, bool inv, bool sig, cudaStream_t st);
 void launch_fwd_v1(const LossP &P, int mode, bool mask, bool inv, bool sig, cudaStream_t st);
 void launch_bwd_v4(const LossP &P, int mode, bool mask, bool inv, bool sig, cudaStream_t st);
 void launch_bwd_v1(const LossP &P, int mode, bool mask, bool inv, bool sig, cudaStream_t st);
 void launch_bwd_stash_v4(const LossP &P, bool mask, bool inv, bool sig, cudaStream_t st);
+void launch_bwd_ring_v4(const LossP &P, bool mask, bool inv, bool sig, cudaStream_t st);
 void launch_bwd_stash_v1(const LossP &P, bool mask, bool inv, bool sig, cudaStream_t st);
 
 #define MTE_LOSS_DISPATCH_BOOL(flag, NAME, ...) \
