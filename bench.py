@@ -194,16 +194,29 @@ def bench_loss(args, rank, world, device):
             with torch.cuda.graph(g, stream=stream):
                 step()
             graphs.append(g)
+        # one more graph holding a whole round of n_sets consecutive steps: replaying it keeps the GPU fed across
+        # steps (kernel launches inside a graph are programmatic-dependent launches, see edge_loss_kernels.cuh)
+        round_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(round_graph, stream=stream):
+            for (f, b, _gm, _gp, losses, ctx, ws, gl, _st) in keep:
+                _lib.check(_lib.lib.mte_edge_loss_fwd(f, SCALES, C.byref(at), losses.data_ptr(), ctx.data_ptr(),
+                                                      ws.data_ptr(), ws.numel(), st))
+                _lib.check(_lib.lib.mte_edge_loss_bwd(b, SCALES, C.byref(at), gl.data_ptr(), ctx.data_ptr(),
+                                                      ws.data_ptr(), ws.numel(), st))
         for i in range(args.warmup):
             graphs[i % n_sets].replay()
+        round_graph.replay()
         barrier(world)
         sampler = ClockSampler(torch.cuda.current_device())
         if rank == 0:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for i in range(args.steps):
-            graphs[(args.warmup + i) % n_sets].replay()
+        rounds, rest = divmod(args.steps, n_sets)
+        for _ in range(rounds):
+            round_graph.replay()
+        for i in range(rest):
+            graphs[i].replay()
         e1.record(stream)
         barrier(world)
         ms = e0.elapsed_time(e1)
@@ -212,24 +225,31 @@ def bench_loss(args, rank, world, device):
     ms_per_step = ms / args.steps
     value = world * px_per_step / (ms_per_step * 1e-3) / 1e6
 
-    # per-kernel split (same stream, CUDA events around each launch of one replayed step, ungraphed)
+    # per-kernel split: graphs of n_sets back-to-back launches of ONE kernel (rotating input sets), CUDA events around
+    # the replays on the launching stream
+    def time_kernel(which):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            for (f, b, _gm, _gp, losses, ctx, ws, gl, _st) in keep:
+                if which == "fwd":
+                    _lib.check(_lib.lib.mte_edge_loss_fwd(f, SCALES, C.byref(at), losses.data_ptr(), ctx.data_ptr(),
+                                                          ws.data_ptr(), ws.numel(), st))
+                else:
+                    _lib.check(_lib.lib.mte_edge_loss_bwd(b, SCALES, C.byref(at), gl.data_ptr(), ctx.data_ptr(),
+                                                          ws.data_ptr(), ws.numel(), st))
+        for _ in range(3):
+            g.replay()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 50
+        a0.record(stream)
+        for _ in range(reps):
+            g.replay()
+        a1.record(stream)
+        torch.cuda.synchronize()
+        return a0.elapsed_time(a1) / (reps * n_sets)
+
     with torch.cuda.stream(stream):
-        f, b, gmap, gpred, losses, ctx, ws, gl, _stash = keep[0]
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        tf = tb = 0.0
-        reps = 10
-        for r in range(reps):
-            f, b, gmap, gpred, losses, ctx, ws, gl, _stash = keep[r % n_sets]
-            ev[0].record(stream)
-            _lib.check(_lib.lib.mte_edge_loss_fwd(f, SCALES, C.byref(at), losses.data_ptr(), ctx.data_ptr(),
-                                                  ws.data_ptr(), ws.numel(), stream.cuda_stream))
-            ev[1].record(stream)
-            _lib.check(_lib.lib.mte_edge_loss_bwd(b, SCALES, C.byref(at), gl.data_ptr(), ctx.data_ptr(),
-                                                  ws.data_ptr(), ws.numel(), stream.cuda_stream))
-            ev[2].record(stream)
-            torch.cuda.synchronize()
-            tf += ev[0].elapsed_time(ev[1]); tb += ev[1].elapsed_time(ev[2])
-        tf, tb = tf / reps, tb / reps
+        tf, tb = time_kernel("fwd"), time_kernel("bwd")
 
     # end to end through the public API with host buffers
     host = [loss_inputs(B_PER_GPU, 5000 + 1000 * rank + i, None, pinned=True) for i in range(2)]
@@ -274,7 +294,7 @@ def bench_loss(args, rank, world, device):
         "config": {"workload": "edge loss fwd+bwd, batch 8/GPU x 4-scale pyramid 384x1280..48x160 fp32, DEE normals, "
                                "no mask, inv2depth fused (BASELINE.json config 3 loss shape)",
                    "pixels_per_step_per_gpu": px_per_step, "l2_policy": f"rotating {n_sets} input sets "
-                   f"({n_sets * set_bytes / 1e6:.0f} MB > L2)", "launch": "CUDA graph replay of 2 kernels/step",
+                   f"({n_sets * set_bytes / 1e6:.0f} MB > L2)", "launch": f"CUDA graph replay, {n_sets} steps x 2 kernels per graph, programmatic dependent launch",
                    "parallelism": f"dp{world} (batch-sharded, no data-path collective in the loss)"},
         "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e, 4), "api": "mindtheedge_b200.losses.multiscale_edge_loss + backward"},
@@ -283,6 +303,8 @@ def bench_loss(args, rank, world, device):
                      "frac": round(achieved / peak, 4), "traffic": recorded_traffic("edge_loss_fwd_bwd"),
                      "kernel": "edge_loss_fwd_kernel + edge_loss_bwd_kernel",
                      "fwd_us": round(tf * 1e3, 2), "bwd_us": round(tb * 1e3, 2),
+                     "fwd_frac": round(0.5 * LOSS_BYTES_PER_PX * px_per_step / (tf * 1e-3) / 1e9 / peak, 4),
+                     "bwd_frac": round(0.5 * LOSS_BYTES_PER_PX * px_per_step / (tb * 1e-3) / 1e9 / peak, 4),
                      "algorithmic_bytes_per_px": LOSS_BYTES_PER_PX, "peak_source": peak_src},
         "clocks": clocks,
     }

@@ -212,9 +212,9 @@ static int make_plan(Plan &pl, const mte_loss_scale_t *sc, int n, const mte_loss
     P.totalUnits = (int)unitBase;
     // forward: persistent CTAs (2 per SM), every warp owns an equal contiguous range of strip rows (at least a few
     // rows each, so the window prologue is amortised)
-    pl.fwdGrid = kNumSMs * 2;
+    pl.fwdGrid = kNumSMs * kRMinB;
     const int minRows = 4;
-    if ((long long)pl.fwdGrid * kWarps * minRows > unitBase) pl.fwdGrid = (int)((unitBase + kWarps * minRows - 1) / (kWarps * minRows));
+    if ((long long)pl.fwdGrid * kRWarps * minRows > unitBase) pl.fwdGrid = (int)((unitBase + kRWarps * minRows - 1) / (kRWarps * minRows));
     if (pl.fwdGrid < 1) pl.fwdGrid = 1;
     if (at) {
         P.T = at->sigmoid_thresh; P.weight = at->weight; P.p2n = at->pos_to_neg;

@@ -14,6 +14,7 @@
 //    the forward stashes only alpha) and gathers the 3x3 adjoint from registers + shuffles.
 #pragma once
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -35,7 +36,30 @@ enum { MODE_NONE = 0, MODE_MAG = 1, MODE_DIR = 2 };
 #endif
 constexpr int kFwdRH = MTE_FWD_RH;   // output rows per forward work item
 constexpr int kBwdRH = 8;   // output rows per backward work item
-constexpr int kSegCost = 4;     // forward partition: cost of opening a segment, in rows
+// the streaming (ring) kernels: warps per CTA, CTAs per SM, ring depths -- tuning knobs.  Measured on B200 at the
+// config-3 loss shape (bench.py, us per fwd+bwd step): 2 CTAs x 8 warps, depths 8/6: 43.4; 1 CTA x 16 warps: depths
+// 8/6 43.4, 7/5 41.7, 5/4 40.8, 4/4 39.9, 3/3 39.2, 3/2 38.5, 3/1 41.3; 24 warps 42.0.  Shallow rings win: deeper
+// queues only add memory latency and let warps drift apart (the kernel ends with its slowest warp).
+#ifndef MTE_LOSS_WARPS
+#define MTE_LOSS_WARPS 16
+#endif
+#ifndef MTE_LOSS_MINB
+#define MTE_LOSS_MINB 1
+#endif
+#ifndef MTE_FWD_D
+#define MTE_FWD_D 3
+#endif
+#ifndef MTE_BWD_D
+#define MTE_BWD_D 2
+#endif
+constexpr int kRWarps = MTE_LOSS_WARPS, kRThreads = kRWarps * 32, kRMinB = MTE_LOSS_MINB;
+#ifndef MTE_SEGCOST_F
+#define MTE_SEGCOST_F 4
+#endif
+#ifndef MTE_SEGCOST_B
+#define MTE_SEGCOST_B 5
+#endif
+constexpr int kSegCost = MTE_SEGCOST_F;     // forward partition: cost of opening a segment, in rows
 constexpr int kHaloLanes = 30;  // writing lanes of an overlapped strip (one halo lane per side)
 // The backward needs the coefficient of the neighbouring pixel, i.e. depth two columns out: with
 // VEC=1 that is two halo lanes per side.
@@ -222,7 +246,7 @@ constexpr double kFix = 4294967296.0;  // 2^32
 template <bool MASK>
 static __device__ __forceinline__ void finalize_loss(const LossP &P, double *sLoss /* [MTE_MAX_SCALES] shared */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int k = warp; k < P.nScales; k += kWarps) {
+    for (int k = warp; k < P.nScales; k += kRWarps) {
         const ScaleP &S = P.s[k];
         const double npix = (double)S.H * (double)S.W;
         double sumM = 0.0;
@@ -374,6 +398,28 @@ __device__ __forceinline__ float lg2_approx(float x) {  // arguments here are >=
     return r;
 }
 
+// ---- programmatic dependent launch (PDL): the kernels are launched with programmatic stream serialisation, so their
+// launch latency, CTA scheduling and index prologue overlap the tail of the previous kernel in the stream / graph;
+// pdl_wait() blocks until that kernel has completed and its writes are visible and precedes every global access.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename K>
+static void launch_pdl(K kernel, int grid, int block, int smem, cudaStream_t st, const LossP &P) {
+    static const bool noPdl = getenv("MTE_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = noPdl ? 0 : 1;
+    cudaLaunchKernelEx(&cfg, kernel, P);
+}
+
 // ---- asynchronous global -> shared row ring (cp.async / LDGSTS) ----------------------------------------------
 // Every lane copies its own VEC*4 bytes of a row into its own slot of the warp's ring and later reads only that slot
 // back, so no cross-lane synchronisation is needed: cp.async.wait_group orders a thread's own copies.  The ring
@@ -398,9 +444,9 @@ __device__ __forceinline__ void lds_vec(float (&out)[VEC], const unsigned char *
 }
 
 __host__ __device__ constexpr int fwd_planes(int mode, bool mask) { return 2 + (mode == MODE_DIR ? 1 : 0) + (mask ? 1 : 0); }
-__host__ __device__ constexpr int fwd_ring_depth(int mode, bool mask) { return fwd_planes(mode, mask) >= 4 ? 6 : 8; }
+__host__ __device__ constexpr int fwd_ring_depth(int mode, bool mask) { return MTE_FWD_D; }
 __host__ __device__ constexpr int fwd_smem_bytes(int vec, int mode, bool mask) {
-    return kWarps * fwd_ring_depth(mode, mask) * fwd_planes(mode, mask) * 32 * vec * 4;
+    return kRWarps * fwd_ring_depth(mode, mask) * fwd_planes(mode, mask) * 32 * vec * 4;
 }
 
 // Forward work decomposition: the unit is one row of one strip (32 lanes x VEC px, LANES of them writing) of one
@@ -579,14 +625,16 @@ __device__ __forceinline__ void fwd_segment(const LossP &P, const ScaleP &S, int
 }
 
 template <int VEC, int MODE, bool MASK, bool INV, bool SIG>
-__global__ void __launch_bounds__(kThreads, MTE_FWD_MINB) edge_loss_fwd_kernel(const __grid_constant__ LossP P) {
+__global__ void __launch_bounds__(kRThreads, kRMinB) edge_loss_fwd_kernel(const __grid_constant__ LossP P) {
     extern __shared__ __align__(16) unsigned char fwdRing[];
     const int lane = threadIdx.x & 31;
-    const int nWarps = gridDim.x * kWarps;
-    const int gw = blockIdx.x * kWarps + (threadIdx.x >> 5);
-    unsigned char *ring = fwdRing + (threadIdx.x >> 5) * (fwd_smem_bytes(VEC, MODE, MASK) / kWarps);
+    const int nWarps = gridDim.x * kRWarps;
+    const int gw = blockIdx.x * kRWarps + (threadIdx.x >> 5);
+    unsigned char *ring = fwdRing + (threadIdx.x >> 5) * (fwd_smem_bytes(VEC, MODE, MASK) / kRWarps);
     int u0 = (int)((long long)P.totalUnits * gw / nWarps);
     const int u1 = (int)((long long)P.totalUnits * (gw + 1) / nWarps);
+    pdl_launch_dependents();
+    pdl_wait();
     while (u0 < u1) {
         int si = 0;
 #pragma unroll
@@ -977,13 +1025,13 @@ __global__ void __launch_bounds__(kThreads, 2) edge_loss_bwd_stash_kernel(const 
 // per-pixel work of edge_loss_bwd_stash_kernel.  Rows / columns outside the image are zero-filled by the copies:
 // a zero stash byte selects the all-zero table entry, so padding needs no predicates in the row loop.
 // ---------------------------------------------------------------------------
-constexpr int kSegCostB = 5;
-__host__ __device__ constexpr int bwd_ring_depth(bool mask, bool inv) { return (mask && inv) ? 5 : 6; }
+constexpr int kSegCostB = MTE_SEGCOST_B;
+__host__ __device__ constexpr int bwd_ring_depth(bool mask, bool inv) { return MTE_BWD_D; }
 __host__ __device__ constexpr int bwd_slot_bytes(bool mask, bool inv) { return (2 + (mask ? 1 : 0) + (inv ? 1 : 0)) * 512 + 128; }
-__host__ __device__ constexpr int bwd_smem_bytes(bool mask, bool inv) { return kWarps * bwd_ring_depth(mask, inv) * bwd_slot_bytes(mask, inv); }
+__host__ __device__ constexpr int bwd_smem_bytes(bool mask, bool inv) { return kRWarps * bwd_ring_depth(mask, inv) * bwd_slot_bytes(mask, inv); }
 
 template <bool MASK, bool INV, bool SIG>
-__global__ void __launch_bounds__(kThreads, 2) edge_loss_bwd_ring_kernel(const __grid_constant__ LossP P) {
+__global__ void __launch_bounds__(kRThreads, kRMinB) edge_loss_bwd_ring_kernel(const __grid_constant__ LossP P) {
     constexpr int VEC = 4;
     constexpr int D = bwd_ring_depth(MASK, INV);
     constexpr unsigned PLB = 512, SLB = bwd_slot_bytes(MASK, INV);
@@ -1004,10 +1052,12 @@ __global__ void __launch_bounds__(kThreads, 2) edge_loss_bwd_ring_kernel(const _
     unsigned char *slot0 = ring + lane * 16, *slotS = ring + O_S + lane * 4;
     const unsigned ringS = (unsigned)__cvta_generic_to_shared(slot0);
     const unsigned ringSS = (unsigned)__cvta_generic_to_shared(slotS);
-    const int nWarps = gridDim.x * kWarps;
-    const int gw = blockIdx.x * kWarps + warp;
+    const int nWarps = gridDim.x * kRWarps;
+    const int gw = blockIdx.x * kRWarps + warp;
     int u0 = (int)((long long)P.totalUnits * gw / nWarps);
     const int u1 = (int)((long long)P.totalUnits * (gw + 1) / nWarps);
+    pdl_launch_dependents();
+    pdl_wait();
     while (u0 < u1) {
         int si = 0;
 #pragma unroll
@@ -1140,7 +1190,7 @@ static void launch_bwd_ring_one(const LossP &P, cudaStream_t st) {
         cudaFuncSetAttribute(edge_loss_bwd_ring_kernel<MASK, INV, SIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         optedIn = true;
     }
-    edge_loss_bwd_ring_kernel<MASK, INV, SIG><<<P.totalCtas, kThreads, smem, st>>>(P);
+    launch_pdl(edge_loss_bwd_ring_kernel<MASK, INV, SIG>, P.totalCtas, kRThreads, smem, st, P);
 }
 
 // the forward's row ring lives in dynamic shared memory (> 48 KB: opt in once per instantiation)
@@ -1152,7 +1202,7 @@ static void launch_fwd_one(const LossP &P, cudaStream_t st) {
         cudaFuncSetAttribute(edge_loss_fwd_kernel<VEC, MODE, MASK, INV, SIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         optedIn = true;
     }
-    edge_loss_fwd_kernel<VEC, MODE, MASK, INV, SIG><<<P.totalCtas, kThreads, smem, st>>>(P);
+    launch_pdl(edge_loss_fwd_kernel<VEC, MODE, MASK, INV, SIG>, P.totalCtas, kRThreads, smem, st, P);
 }
 
 // launchers implemented one translation unit per (direction, VEC) so they compile in parallel

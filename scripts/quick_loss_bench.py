@@ -41,7 +41,8 @@ def run(B, H, W, scales, nsets, iters=50):
     # device time per kernel: CUDA-graph replays of `nsets` back-to-back launches (no CPU launch gaps)
     stream = torch.cuda.Stream(dev)
     st = stream.cuda_stream
-    for name, fn in (("fwd", fwd), ("bwd", bwd)):
+    def both(i): fwd(i); bwd(i)
+    for name, fn in (("fwd", fwd), ("bwd", bwd), ("step", both)):
         with torch.cuda.stream(stream):
             for i in range(nsets): fn(i)
             torch.cuda.synchronize()
