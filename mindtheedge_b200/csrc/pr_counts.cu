@@ -659,6 +659,372 @@ __global__ void __launch_bounds__(kSmThreads, 1) match_smem_kernel(const __grid_
 }
 
 // ---------------------------------------------------------------------------
+// Threshold-sweep matcher: ONE CTA per image solves all T nested problems incrementally.
+//
+// The predicted sets are nested in the threshold (level planes: P_t grows with t; strength maps with ascending
+// thresholds: P_t shrinks with t), and only the predicted side changes.  Adding predicted pixels to a maximum matching
+// and augmenting from the new pixels only gives a maximum matching of the larger problem (a vertex whose search
+// failed can never be matched later -- Kuhn's lemma), so the stages s = 0..T-1 (sets growing with s) are solved in
+// turn on one persistent state:
+//   stage s: greedy nearest-first proposals of the new pixels, then phases of { asynchronous alternating forest
+//   from the new pixels that are still free; one CAS-claimed augmenting path per tree } until a phase finds no
+//   free GT pixel.  That last forest is closed under alternating reachability and contains no free GT pixel, so no
+//   later augmenting path can enter it: its GT vertices are marked DEAD and never explored again.
+// Every GT vertex dies at most once, so the whole sweep costs about as much as its largest problem instead of T
+// independent solves.  |M_t| after stage s is the count of threshold t_s.  Images whose vertex sets do not fit the
+// shared-memory budget hand their T problems to the per-problem kernels through the overflow list.
+// ---------------------------------------------------------------------------
+constexpr unsigned short kDeadStamp = 0xFFFF;
+
+__global__ void __launch_bounds__(kSmThreads, 1) match_sweep_kernel(const __grid_constant__ MatchP Pin,
+                                                                    const __grid_constant__ ParamTables tabs,
+                                                                    int tablesInParam, const SmemLayout SL) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ int sImage, sNP, sNQ, sCntA, sEnds, sMatched, sHead, sTail, sPending;
+    __shared__ int sScan[kSmThreads];
+    __shared__ int sStage[MTE_MAX_THRESHOLDS + 2];   // histogram, then start offset of every stage
+    __shared__ int sCursor[MTE_MAX_THRESHOLDS + 2];
+    __shared__ short2 sOff[kSmemTableOff];
+    __shared__ double sThr[MTE_MAX_THRESHOLDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    MatchP P = Pin;
+    const int w = P.w, h = P.h, hw = w * h, T = P.T;
+    unsigned *qbits = reinterpret_cast<unsigned *>(dyn + SL.oBits);
+    unsigned short *qrank = reinterpret_cast<unsigned short *>(dyn + SL.oRank);
+    unsigned *ppix = reinterpret_cast<unsigned *>(dyn + SL.oPpix);
+    unsigned short *mateP = reinterpret_cast<unsigned short *>(dyn + SL.oMateP);
+    unsigned short *claimP = reinterpret_cast<unsigned short *>(dyn + SL.oClaimP);
+    unsigned short *fa = reinterpret_cast<unsigned short *>(dyn + SL.oFa);
+    unsigned short *mateQ = reinterpret_cast<unsigned short *>(dyn + SL.oMateQ);
+    unsigned short *parentQ = reinterpret_cast<unsigned short *>(dyn + SL.oParentQ);
+    unsigned short *stampQ = reinterpret_cast<unsigned short *>(dyn + SL.oStampQ);
+    unsigned short *ends = reinterpret_cast<unsigned short *>(dyn + SL.oEnds);
+    for (int i = threadIdx.x; i < P.noff; i += kSmThreads) sOff[i] = tablesInParam ? tabs.off[i] : P.off[i];
+    const bool levels = P.inMode == IN_LEVELS;
+    if (!levels)
+        for (int i = threadIdx.x; i < T; i += kSmThreads) sThr[i] = tablesInParam ? tabs.thr[i] : P.thr[i];
+    __syncthreads();
+    const int noff = P.noff;
+    long long tk = 0;
+    auto tick = [&](int slot) {  // profiling: cycles (>> 8) per section, accumulated by thread 0
+        if (P.stats && threadIdx.x == 0) {
+            const long long now = clock64();
+            if (slot >= 0) atomicAdd(P.stats + slot, (unsigned)((now - tk) >> 8));
+            tk = now;
+        }
+    };
+
+    auto qid = [&](int q) -> int {
+        const unsigned bits = qbits[q >> 5];
+        return (int)qrank[q >> 5] + __popc(bits & ((1u << (q & 31)) - 1u));
+    };
+    // stage at which window pixel (gy, gx) of image img joins the predicted set; T = never
+    auto stage_of = [&](int img, int gy, int gx) -> int {
+        const size_t o = (size_t)img * P.H * P.W + (size_t)gy * P.W + gx;
+        if (levels) {
+            const int L = ((const unsigned char *)P.pred)[o];
+            return L < T ? L : T;
+        }
+        const double v = P.inMode == IN_F32 ? (double)((const float *)P.pred)[o] : ((const double *)P.pred)[o];
+        // thresholds ascend: count = #{t : v >= thr[t]} by bisection; the pixel belongs to P_t for t < count and the
+        // stages run from the largest threshold down
+        int lo = 0, hi = T;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (v >= sThr[mid]) lo = mid + 1; else hi = mid;
+        }
+        return T - lo;  // lo == 0 (below every threshold, or NaN) -> T = never
+    };
+
+    for (;;) {
+        if (threadIdx.x == 0) sImage = (int)atomicAdd(P.nextProblem, 1u);
+        __syncthreads();
+        const int img = sImage;
+        if (img >= P.N) break;
+        const unsigned char *gt = P.gt + (size_t)img * P.H * P.W;
+        if (threadIdx.x == 0) { sNQ = 0; sMatched = 0; }
+        for (int i = threadIdx.x; i < T + 2; i += kSmThreads) sStage[i] = 0;
+        __syncthreads();
+        tick(-1);
+
+        // ---- pass 1: GT bitmap (one ballot per 32 window pixels) and the stage histogram of the predicted pixels
+        for (int base = 0; base < SL.nW * 32; base += 8 * kSmThreads) {
+            int stg[8];
+            bool isQ[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = base + u * kSmThreads + threadIdx.x;
+                stg[u] = T; isQ[u] = false;
+                if (i < hw) {
+                    const int y = i / w, x = i - y * w;
+                    stg[u] = stage_of(img, P.y0 + y, P.x0 + x);
+                    isQ[u] = gt[(size_t)(P.y0 + y) * P.W + P.x0 + x] != 0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = base + u * kSmThreads + threadIdx.x;
+                if (base + u * kSmThreads >= SL.nW * 32) break;  // warp-uniform
+                const unsigned mq = __ballot_sync(MTE_FULL_MASK, isQ[u]);
+                if (lane == 0) {
+                    qbits[i >> 5] = mq;
+                    if (mq) atomicAdd(&sNQ, __popc(mq));
+                }
+                if (stg[u] < T) atomicAdd(&sStage[stg[u]], 1);
+            }
+        }
+        __syncthreads();
+        const int nQ = sNQ;
+        // stage offsets (T <= 254: one warp scans them)
+        if (warp == 0) {
+            int run = 0;
+            for (int b0 = 0; b0 < T; b0 += 32) {
+                const int k = b0 + lane;
+                const int c = k < T ? sStage[k] : 0;
+                int incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(MTE_FULL_MASK, incl, o); if (lane >= o) incl += v; }
+                if (k < T) { sStage[k] = run + incl - c; sCursor[k] = run + incl - c; }
+                run += __shfl_sync(MTE_FULL_MASK, incl, 31);
+            }
+            if (lane == 0) { sStage[T] = run; sNP = run; }
+        }
+        __syncthreads();
+        const int nPall = sNP;
+        if (nPall > SL.capP || nQ > SL.capQ || nQ >= 0xFFF0 || nPall >= 0xFFF0) {  // does not fit: per-problem kernels
+            if (threadIdx.x == 0) {
+                const int at = (int)atomicAdd(P.overflowCount, (unsigned)T);
+                for (int t = 0; t < T; t++) P.overflowList[at + t] = img * T + t;
+            }
+            __syncthreads();
+            continue;
+        }
+        // ---- pass 2: predicted pixels grouped by stage (order inside a stage is arbitrary: counts do not depend on it)
+        for (int base = 0; base < hw; base += 8 * kSmThreads) {
+            int stg[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = base + u * kSmThreads + threadIdx.x;
+                stg[u] = T;
+                if (i < hw) {
+                    const int y = i / w, x = i - y * w;
+                    stg[u] = stage_of(img, P.y0 + y, P.x0 + x);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = base + u * kSmThreads + threadIdx.x;
+                if (stg[u] < T) {
+                    const int slot = atomicAdd(&sCursor[stg[u]], 1);
+                    ppix[slot] = (unsigned)i; mateP[slot] = kFree; claimP[slot] = 0;
+                }
+            }
+        }
+        // ---- rank: exclusive prefix popcount over the bitmap words
+        {
+            const int per = (SL.nW + kSmThreads - 1) / kSmThreads;
+            const int w0 = threadIdx.x * per, w1 = min(w0 + per, SL.nW);
+            int sum = 0;
+            for (int k = w0; k < w1; k++) sum += __popc(qbits[k]);
+            sScan[threadIdx.x] = sum;
+            __syncthreads();
+            if (warp == 0) {
+                int loc[kSmThreads / 32], run = 0;
+#pragma unroll
+                for (int k = 0; k < kSmThreads / 32; k++) { loc[k] = run; run += sScan[lane * (kSmThreads / 32) + k]; }
+                int incl = run;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(MTE_FULL_MASK, incl, o); if (lane >= o) incl += v; }
+                const int excl = incl - run;
+#pragma unroll
+                for (int k = 0; k < kSmThreads / 32; k++) sScan[lane * (kSmThreads / 32) + k] = excl + loc[k];
+            }
+            __syncthreads();
+            int run = sScan[threadIdx.x];
+            for (int k = w0; k < w1; k++) { qrank[k] = (unsigned short)run; run += __popc(qbits[k]); }
+        }
+        for (int k = threadIdx.x; k < nQ; k += kSmThreads) { mateQ[k] = kFree; stampQ[k] = 0; }
+        __syncthreads();
+        tick(4);
+
+        unsigned short phase = 0;
+        for (int s = 0; s < T; s++) {
+            const int p0 = sStage[s], p1 = sStage[s + 1];  // the pixels that join at this stage
+            if (p1 > p0) {
+                // ---- greedy start: nearest free GT pixel (warp per new predicted pixel, lanes over offsets)
+                for (int pi = p0 + warp; pi < p1; pi += kSmWarps) {
+                    const int p = (int)ppix[pi];
+                    const int py = p / w, px = p - py * w;
+                    bool done = false, anyQ = false;
+                    for (int k0 = 0; k0 < noff && !done; k0 += 32) {
+                        const int k = k0 + lane;
+                        bool cand = false;
+                        int q = 0;
+                        if (k < noff) {
+                            const short2 o = sOff[k];
+                            const int qy = py + o.y, qx = px + o.x;
+                            if (qy >= 0 && qy < h && qx >= 0 && qx < w) {
+                                q = qy * w + qx;
+                                cand = (qbits[q >> 5] >> (q & 31)) & 1u;
+                            }
+                        }
+                        unsigned m = __ballot_sync(MTE_FULL_MASK, cand);
+                        anyQ |= m != 0;
+                        while (m && !done) {
+                            const int l = __ffs(m) - 1;
+                            m &= m - 1;
+                            int ok = 0;
+                            if (lane == l) {
+                                const int qi = qid(q);
+                                ok = cas16(&mateQ[qi], kFree, (unsigned short)pi) == kFree;
+                                if (ok) mateP[pi] = (unsigned short)qi;
+                            }
+                            done = __shfl_sync(MTE_FULL_MASK, ok, l) != 0;
+                        }
+                    }
+                    if (done && lane == 0) atomicAdd(&sMatched, 1);
+                    if (!done && !anyQ && lane == 0) mateP[pi] = kDead;
+                }
+                __syncthreads();
+                tick(5);
+                // ---- augmenting phases rooted at the new pixels that are still free
+                for (;;) {
+                    phase++;
+                    if (threadIdx.x == 0) { sCntA = 0; sEnds = 0; }
+                    __syncthreads();
+                    for (int base = p0; base < p1; base += kSmThreads) {
+                        const int pi = base + threadIdx.x;
+                        const bool fr = pi < p1 && mateP[pi] == kFree;
+                        const unsigned m = __ballot_sync(MTE_FULL_MASK, fr);
+                        int wbase = 0;
+                        if (lane == 0 && m) wbase = atomicAdd(&sCntA, __popc(m));
+                        wbase = __shfl_sync(MTE_FULL_MASK, wbase, 0);
+                        if (fr) fa[wbase + __popc(m & ((1u << lane) - 1))] = (unsigned short)pi;
+                    }
+                    __syncthreads();
+                    const int nRoots = sCntA;
+                    if (nRoots == 0) break;
+                    if (P.stats && threadIdx.x == 0) { atomicAdd(P.stats + 0, 1u); atomicAdd(P.stats + 3, (unsigned)nRoots); }
+                    // asynchronous alternating forest (see match_smem_kernel); dead GT vertices are walls
+                    for (int i = nRoots + threadIdx.x; i < p1; i += kSmThreads) fa[i] = kFree;  // unpublished slots
+                    if (threadIdx.x == 0) { sHead = 0; sTail = nRoots; sPending = nRoots; }
+                    __syncthreads();
+                    tick(6);
+                    for (;;) {
+                        int my = -1;
+                        if (lane == 0) {
+                            for (;;) {
+                                const int hd = *(volatile int *)&sHead, tl = *(volatile int *)&sTail;
+                                if (hd < tl) {
+                                    if (atomicCAS(&sHead, hd, hd + 1) == hd) { my = hd; break; }
+                                } else if (*(volatile int *)&sPending == 0) {
+                                    my = -2;
+                                    break;
+                                }
+                            }
+                            if (my >= 0) {
+                                int v;
+                                while ((v = ((volatile unsigned short *)fa)[my]) == kFree) {}
+                                my = v;
+                            }
+                        }
+                        my = __shfl_sync(MTE_FULL_MASK, my, 0);
+                        if (my == -2) break;
+                        const int pi = my;
+                        const int p = (int)ppix[pi];
+                        const int py = p / w, px = p - py * w;
+                        for (int k = lane; k < noff; k += 32) {
+                            const short2 o = sOff[k];
+                            const int qy = py + o.y, qx = px + o.x;
+                            if (qy < 0 || qy >= h || qx < 0 || qx >= w) continue;
+                            const int q = qy * w + qx;
+                            if (!((qbits[q >> 5] >> (q & 31)) & 1u)) continue;
+                            const int qi = qid(q);
+                            const unsigned short st = stampQ[qi];
+                            if (st == phase || st == kDeadStamp) continue;
+                            if (cas16(&stampQ[qi], st, phase) != st) continue;
+                            parentQ[qi] = (unsigned short)pi;
+                            const unsigned short mq = mateQ[qi];
+                            if (mq == kFree) {
+                                ends[atomicAdd(&sEnds, 1)] = (unsigned short)qi;
+                            } else {
+                                atomicAdd(&sPending, 1);
+                                const int slot = atomicAdd(&sTail, 1);
+                                ((volatile unsigned short *)fa)[slot] = mq;
+                            }
+                        }
+                        __syncwarp();
+                        if (lane == 0) {
+                            __threadfence_block();
+                            atomicSub(&sPending, 1);
+                            if (P.stats) atomicAdd(P.stats + 2, 1u);
+                        }
+                    }
+                    __syncthreads();
+                    tick(7);
+                    const int nEnds = sEnds;
+                    if (nEnds == 0) {
+                        // the forest of this phase is closed and holds no free GT pixel: wall it off for good
+                        for (int k = threadIdx.x; k < nQ; k += kSmThreads)
+                            if (stampQ[k] == phase) stampQ[k] = kDeadStamp;
+                        __syncthreads();
+                        tick(8);
+                        break;
+                    }
+                    for (int ei = threadIdx.x; ei < nEnds; ei += kSmThreads) {
+                        const int qEnd = ends[ei];
+                        int q = qEnd;
+                        bool ok = true;
+                        for (;;) {  // claim walk
+                            const int pi = parentQ[q];
+                            const unsigned short c = claimP[pi];
+                            if (c == phase || cas16(&claimP[pi], c, phase) != c) { ok = false; break; }
+                            const unsigned short mp = mateP[pi];
+                            if (mp == kFree) break;
+                            q = mp;
+                        }
+                        if (!ok) continue;
+                        q = qEnd;
+                        for (;;) {  // flip walk
+                            const int pi = parentQ[q];
+                            const unsigned short prev = mateP[pi];
+                            mateP[pi] = (unsigned short)q;
+                            mateQ[q] = (unsigned short)pi;
+                            if (prev == kFree) break;
+                            q = prev;
+                        }
+                        atomicAdd(&sMatched, 1);
+                    }
+                    __syncthreads();
+                    tick(8);
+                    if (phase >= 0xFFF0) break;  // unreachable in practice (every phase adds a match or ends the stage)
+                }
+            }
+            __syncthreads();
+            // ---- the count of this stage's threshold
+            if (threadIdx.x == 0) {
+                const int t = levels ? s : T - 1 - s;
+                const int matched = sMatched;
+                unsigned long long *c = P.counts + (size_t)t * 4;
+                atomicAdd(c + 0, (unsigned long long)matched);
+                atomicAdd(c + 1, (unsigned long long)nQ);
+                atomicAdd(c + 2, (unsigned long long)matched);
+                atomicAdd(c + 3, (unsigned long long)p1);
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned d = atomicAdd(P.doneCtas, 1u);
+        if (d == gridDim.x - 1) {
+            *P.nextProblem = 0u;
+            *P.doneCtas = 0u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 struct OffsetTable {
@@ -803,6 +1169,41 @@ static int launch(MatchP &P, const Layout &L, char *ws, double max_dist, const d
     }
     const SmemLayout SL = smem_layout(P.h, P.w, smemBudget);
     const bool useSmem = SL.capP > 0 && tb.n <= kSmemTableOff && !getenv("MTE_MATCH_DENSE");
+    // threshold sweeps (level planes; strength maps with ascending thresholds): one CTA per image solves all T nested
+    // problems incrementally; what does not fit falls through to the per-problem kernels via the overflow list
+    bool sweep = useSmem && P.counts && !P.matchA && !P.matchB && P.inMode != IN_BINARY && P.T > 1 &&
+                 !getenv("MTE_MATCH_NO_SWEEP");
+    if (sweep && P.inMode != IN_LEVELS)
+        for (int t = 1; t < P.T; t++)
+            if (!(thr_host[t] > thr_host[t - 1])) sweep = false;
+    if (sweep) {
+        static int sweepBudget = -1;
+        if (sweepBudget < 0) {
+            int dev = 0, optin = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+            cudaFuncAttributes fa;
+            cudaFuncGetAttributes(&fa, match_sweep_kernel);
+            sweepBudget = optin - (int)fa.sharedSizeBytes - 1024;
+            if (sweepBudget > 0 &&
+                cudaFuncSetAttribute(match_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sweepBudget) != cudaSuccess)
+                sweepBudget = 0;
+            cudaGetLastError();
+        }
+        const SmemLayout SW = smem_layout(P.h, P.w, sweepBudget);
+        if (SW.capP > 0) {
+            int grid = kNumSMs;
+            if (grid > P.N) grid = P.N;
+            match_sweep_kernel<<<grid, kSmThreads, SW.total, st>>>(P, pt, inParam ? 1 : 0, SW);
+            MTE_RETURN_IF_CUDA_ERROR();
+            // the overflowed problems (usually none) go to the dense kernel
+            P.problemList = P.overflowList;
+            P.listCount = P.overflowCount;
+            match_kernel<<<L.nArenas, kThreads, 0, st>>>(P, pt, inParam ? 1 : 0);
+            MTE_RETURN_IF_CUDA_ERROR();
+            return MTE_OK;
+        }
+    }
     if (useSmem) {
         int grid = kNumSMs;
         if (grid > P.nProblems) grid = P.nProblems;
