@@ -674,11 +674,20 @@ __global__ void __launch_bounds__(kSmThreads, 1) match_smem_kernel(const __grid_
 // independent solves.  |M_t| after stage s is the count of threshold t_s.  Images whose vertex sets do not fit the
 // shared-memory budget hand their T problems to the per-problem kernels through the overflow list.
 // ---------------------------------------------------------------------------
-constexpr unsigned short kDeadStamp = 0xFFFF;
+constexpr unsigned kDeadStamp = 0xFFFFFFFFu;   // GT stamp word: phase << 16 | root (predicted vertex id of the tree)
+constexpr unsigned short kFailed = 0xFFFD;     // predicted pixel whose search failed conclusively (Kuhn: for good)
+enum { RF_FOUND = 1u, RF_BLOCKED = 2u };
+constexpr int kEndsCap = 2048;  // free GT pixels recorded per phase (further ones wait for the next phase)
+
+struct SweepLayout {
+    int nW, capP, capQ;
+    unsigned oBits, oRank, oPpix, oMateP, oClaimP, oFa, oRootP, oRflag, oMateQ, oParentQ, oStamp, oEnds, total;
+};
+
 
 __global__ void __launch_bounds__(kSmThreads, 1) match_sweep_kernel(const __grid_constant__ MatchP Pin,
                                                                     const __grid_constant__ ParamTables tabs,
-                                                                    int tablesInParam, const SmemLayout SL) {
+                                                                    int tablesInParam, const SweepLayout SL) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ int sImage, sNP, sNQ, sCntA, sEnds, sMatched, sHead, sTail, sPending;
     __shared__ int sScan[kSmThreads];
@@ -697,7 +706,9 @@ __global__ void __launch_bounds__(kSmThreads, 1) match_sweep_kernel(const __grid
     unsigned short *fa = reinterpret_cast<unsigned short *>(dyn + SL.oFa);
     unsigned short *mateQ = reinterpret_cast<unsigned short *>(dyn + SL.oMateQ);
     unsigned short *parentQ = reinterpret_cast<unsigned short *>(dyn + SL.oParentQ);
-    unsigned short *stampQ = reinterpret_cast<unsigned short *>(dyn + SL.oStampQ);
+    unsigned *stamp = reinterpret_cast<unsigned *>(dyn + SL.oStamp);
+    unsigned short *rootP = reinterpret_cast<unsigned short *>(dyn + SL.oRootP);
+    unsigned *rflagW = reinterpret_cast<unsigned *>(dyn + SL.oRflag);  // one flag byte per predicted vertex
     unsigned short *ends = reinterpret_cast<unsigned short *>(dyn + SL.oEnds);
     for (int i = threadIdx.x; i < P.noff; i += kSmThreads) sOff[i] = tablesInParam ? tabs.off[i] : P.off[i];
     const bool levels = P.inMode == IN_LEVELS;
@@ -714,9 +725,13 @@ __global__ void __launch_bounds__(kSmThreads, 1) match_sweep_kernel(const __grid
         }
     };
 
-    auto qid = [&](int q) -> int {
+    auto rflag_get = [&](int pi) -> unsigned { return (((volatile unsigned *)rflagW)[pi >> 2] >> (8 * (pi & 3))) & 0xFFu; };
+    auto rflag_or = [&](int pi, unsigned f) { atomicOr(&rflagW[pi >> 2], f << (8 * (pi & 3))); };
+    auto qid = [&](int q) -> int {  // rank is kept per 64 window pixels (two bitmap words)
         const unsigned bits = qbits[q >> 5];
-        return (int)qrank[q >> 5] + __popc(bits & ((1u << (q & 31)) - 1u));
+        int r = (int)qrank[q >> 6] + __popc(bits & ((1u << (q & 31)) - 1u));
+        if (q & 32) r += __popc(qbits[(q >> 5) - 1]);
+        return r;
     };
     // stage at which window pixel (gy, gx) of image img joins the predicted set; T = never
     auto stage_of = [&](int img, int gy, int gx) -> int {
@@ -820,30 +835,32 @@ __global__ void __launch_bounds__(kSmThreads, 1) match_sweep_kernel(const __grid
                 }
             }
         }
-        // ---- rank: exclusive prefix popcount over the bitmap words
+        // ---- rank: exclusive prefix popcount over pairs of bitmap words
         {
-            const int per = (SL.nW + kSmThreads - 1) / kSmThreads;
-            const int w0 = threadIdx.x * per, w1 = min(w0 + per, SL.nW);
+            const int nW2 = (SL.nW + 1) >> 1;
+            const int per = (nW2 + kSmThreads - 1) / kSmThreads;
+            const int w0 = threadIdx.x * per, w1 = min(w0 + per, nW2);
+            auto pc2 = [&](int k2) { return __popc(qbits[2 * k2]) + (2 * k2 + 1 < SL.nW ? __popc(qbits[2 * k2 + 1]) : 0); };
             int sum = 0;
-            for (int k = w0; k < w1; k++) sum += __popc(qbits[k]);
+            for (int k2 = w0; k2 < w1; k2++) sum += pc2(k2);
             sScan[threadIdx.x] = sum;
             __syncthreads();
             if (warp == 0) {
                 int loc[kSmThreads / 32], run = 0;
 #pragma unroll
-                for (int k = 0; k < kSmThreads / 32; k++) { loc[k] = run; run += sScan[lane * (kSmThreads / 32) + k]; }
+                for (int q = 0; q < kSmThreads / 32; q++) { loc[q] = run; run += sScan[lane * (kSmThreads / 32) + q]; }
                 int incl = run;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(MTE_FULL_MASK, incl, o); if (lane >= o) incl += v; }
                 const int excl = incl - run;
 #pragma unroll
-                for (int k = 0; k < kSmThreads / 32; k++) sScan[lane * (kSmThreads / 32) + k] = excl + loc[k];
+                for (int q = 0; q < kSmThreads / 32; q++) sScan[lane * (kSmThreads / 32) + q] = excl + loc[q];
             }
             __syncthreads();
             int run = sScan[threadIdx.x];
-            for (int k = w0; k < w1; k++) { qrank[k] = (unsigned short)run; run += __popc(qbits[k]); }
+            for (int k2 = w0; k2 < w1; k2++) { qrank[k2] = (unsigned short)run; run += pc2(k2); }
         }
-        for (int k = threadIdx.x; k < nQ; k += kSmThreads) { mateQ[k] = kFree; stampQ[k] = 0; }
+        for (int k = threadIdx.x; k < nQ; k += kSmThreads) { mateQ[k] = kFree; stamp[k] = 0u; }
         __syncthreads();
         tick(4);
 
@@ -899,13 +916,18 @@ __global__ void __launch_bounds__(kSmThreads, 1) match_sweep_kernel(const __grid
                         int wbase = 0;
                         if (lane == 0 && m) wbase = atomicAdd(&sCntA, __popc(m));
                         wbase = __shfl_sync(MTE_FULL_MASK, wbase, 0);
-                        if (fr) fa[wbase + __popc(m & ((1u << lane) - 1))] = (unsigned short)pi;
+                        if (fr) { fa[wbase + __popc(m & ((1u << lane) - 1))] = (unsigned short)pi; rootP[pi] = (unsigned short)pi; }
                     }
+                    // flag bytes of this stage's pixels (only roots use theirs)
+                    for (int i = (p0 >> 2) + threadIdx.x; i <= ((p1 - 1) >> 2); i += kSmThreads) rflagW[i] = 0u;
                     __syncthreads();
                     const int nRoots = sCntA;
                     if (nRoots == 0) break;
                     if (P.stats && threadIdx.x == 0) { atomicAdd(P.stats + 0, 1u); atomicAdd(P.stats + 3, (unsigned)nRoots); }
-                    // asynchronous alternating forest (see match_smem_kernel); dead GT vertices are walls
+                    // asynchronous alternating forest (see match_smem_kernel); dead GT vertices are walls.  Every GT
+                    // stamp carries the tree (root) that claimed it: a tree that has found a free GT pixel stops
+                    // growing, and a tree that found none WITHOUT ever running into another tree's vertices is closed
+                    // under alternating reachability, hence dead, whatever the other trees of the phase do.
                     for (int i = nRoots + threadIdx.x; i < p1; i += kSmThreads) fa[i] = kFree;  // unpublished slots
                     if (threadIdx.x == 0) { sHead = 0; sTail = nRoots; sPending = nRoots; }
                     __syncthreads();
@@ -931,26 +953,41 @@ __global__ void __launch_bounds__(kSmThreads, 1) match_sweep_kernel(const __grid
                         my = __shfl_sync(MTE_FULL_MASK, my, 0);
                         if (my == -2) break;
                         const int pi = my;
-                        const int p = (int)ppix[pi];
-                        const int py = p / w, px = p - py * w;
-                        for (int k = lane; k < noff; k += 32) {
-                            const short2 o = sOff[k];
-                            const int qy = py + o.y, qx = px + o.x;
-                            if (qy < 0 || qy >= h || qx < 0 || qx >= w) continue;
-                            const int q = qy * w + qx;
-                            if (!((qbits[q >> 5] >> (q & 31)) & 1u)) continue;
-                            const int qi = qid(q);
-                            const unsigned short st = stampQ[qi];
-                            if (st == phase || st == kDeadStamp) continue;
-                            if (cas16(&stampQ[qi], st, phase) != st) continue;
-                            parentQ[qi] = (unsigned short)pi;
-                            const unsigned short mq = mateQ[qi];
-                            if (mq == kFree) {
-                                ends[atomicAdd(&sEnds, 1)] = (unsigned short)qi;
-                            } else {
-                                atomicAdd(&sPending, 1);
-                                const int slot = atomicAdd(&sTail, 1);
-                                ((volatile unsigned short *)fa)[slot] = mq;
+                        const int root = rootP[pi];
+                        if (!(rflag_get(root) & RF_FOUND)) {
+                            const int p = (int)ppix[pi];
+                            const int py = p / w, px = p - py * w;
+                            const unsigned mine = ((unsigned)phase << 16) | (unsigned)root;
+                            for (int k = lane; k < noff; k += 32) {
+                                const short2 o = sOff[k];
+                                const int qy = py + o.y, qx = px + o.x;
+                                if (qy < 0 || qy >= h || qx < 0 || qx >= w) continue;
+                                const int q = qy * w + qx;
+                                if (!((qbits[q >> 5] >> (q & 31)) & 1u)) continue;
+                                const int qi = qid(q);
+                                unsigned st = stamp[qi];
+                                if (st == kDeadStamp) continue;
+                                if ((st >> 16) != phase) {
+                                    const unsigned old = atomicCAS(&stamp[qi], st, mine);
+                                    if (old == st) {  // claimed for this tree
+                                        parentQ[qi] = (unsigned short)pi;
+                                        const unsigned short mq = mateQ[qi];
+                                        if (mq == kFree) {
+                                            const int es = atomicAdd(&sEnds, 1);
+                                            if (es < kEndsCap) ends[es] = (unsigned short)qi;
+                                            rflag_or(root, RF_FOUND);
+                                        } else {
+                                            rootP[mq] = (unsigned short)root;
+                                            atomicAdd(&sPending, 1);
+                                            const int slot = atomicAdd(&sTail, 1);
+                                            __threadfence_block();
+                                            ((volatile unsigned short *)fa)[slot] = mq;
+                                        }
+                                        continue;
+                                    }
+                                    st = old;  // somebody else got it first
+                                }
+                                if (st != kDeadStamp && (st & 0xFFFFu) != (unsigned)root) rflag_or(root, RF_BLOCKED);
                             }
                         }
                         __syncwarp();
@@ -962,15 +999,21 @@ __global__ void __launch_bounds__(kSmThreads, 1) match_sweep_kernel(const __grid
                     }
                     __syncthreads();
                     tick(7);
-                    const int nEnds = sEnds;
-                    if (nEnds == 0) {
-                        // the forest of this phase is closed and holds no free GT pixel: wall it off for good
-                        for (int k = threadIdx.x; k < nQ; k += kSmThreads)
-                            if (stampQ[k] == phase) stampQ[k] = kDeadStamp;
-                        __syncthreads();
-                        tick(8);
-                        break;
+                    const int nEnds = min(sEnds, kEndsCap);
+                    // wall off the trees that failed conclusively (all of them when the phase found nothing) ...
+                    for (int k = threadIdx.x; k < nQ; k += kSmThreads) {
+                        const unsigned st = stamp[k];
+                        if (st != kDeadStamp && (st >> 16) == phase &&
+                            (nEnds == 0 || !(rflag_get((int)(st & 0xFFFFu)) & (RF_FOUND | RF_BLOCKED))))
+                            stamp[k] = kDeadStamp;
                     }
+                    // ... and retire their roots (fa[0..nRoots) still holds them: the queue is append-only)
+                    for (int i = threadIdx.x; i < nRoots; i += kSmThreads) {
+                        const int rp = fa[i];
+                        if (nEnds == 0 || !(rflag_get(rp) & (RF_FOUND | RF_BLOCKED))) mateP[rp] = kFailed;
+                    }
+                    __syncthreads();
+                    if (nEnds == 0) { tick(8); break; }
                     for (int ei = threadIdx.x; ei < nEnds; ei += kSmThreads) {
                         const int qEnd = ends[ei];
                         int q = qEnd;
@@ -1084,6 +1127,34 @@ static SmemLayout smem_layout(int h, int w, int budget) {
     return S;
 }
 
+static SweepLayout sweep_layout(int h, int w, int budget) {
+    SweepLayout S;
+    memset(&S, 0, sizeof(S));
+    const long long hw = (long long)h * w;
+    S.nW = (int)((hw + 31) / 32);
+    const long long fixed = (long long)S.nW * 4 + (long long)S.nW + 2 * kEndsCap + 512;
+    // 13 B per predicted vertex, 8 B per GT vertex, equal capacities
+    const long long cap = (budget - fixed) / 21;
+    if (cap < 512) return S;
+    S.capP = S.capQ = (int)(cap > 0xFFF0 ? 0xFFF0 : cap) & ~7;
+    unsigned o = 0;
+    auto take = [&](unsigned bytes) { const unsigned r = o; o += (bytes + 15u) & ~15u; return r; };
+    S.oBits = take(S.nW * 4);
+    S.oRank = take(((S.nW + 1) / 2) * 2);
+    S.oPpix = take(S.capP * 4);
+    S.oMateP = take(S.capP * 2);
+    S.oClaimP = take(S.capP * 2);
+    S.oFa = take(S.capP * 2);
+    S.oRootP = take(S.capP * 2);
+    S.oRflag = take(S.capP + 4);
+    S.oMateQ = take(S.capQ * 2);
+    S.oParentQ = take(S.capQ * 2);
+    S.oStamp = take(S.capQ * 4);
+    S.oEnds = take(kEndsCap * 2);
+    S.total = o;
+    return S;
+}
+
 static Layout layout(int nProblems, int h, int w, int T) {
     Layout L;
     size_t off = MTE_WS_HEADER_BYTES;
@@ -1190,7 +1261,7 @@ static int launch(MatchP &P, const Layout &L, char *ws, double max_dist, const d
                 sweepBudget = 0;
             cudaGetLastError();
         }
-        const SmemLayout SW = smem_layout(P.h, P.w, sweepBudget);
+        const SweepLayout SW = sweep_layout(P.h, P.w, sweepBudget);
         if (SW.capP > 0) {
             int grid = kNumSMs;
             if (grid > P.N) grid = P.N;

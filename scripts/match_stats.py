@@ -17,5 +17,6 @@ for trial in range(2):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); c = pr_counts(lv, g, n_levels=12, max_dist=0.002, crop=[44, 1197, 153, 371]); e1.record(); torch.cuda.synchronize()
     hdr = runtime.workspace(d.device, 0)[:256].view(torch.int32).cpu().numpy()
+    print("sections(cyc>>8): scan,greedy,phase-setup,explore,augment/mark:", hdr[36:41], end=" ")
     print("problems", n * 12, "ms %.2f" % e0.elapsed_time(e1), "phases, levels, expanded, roots:", hdr[32:36], "per problem:", (hdr[32:36] / (n * 12)).round(1))
 print(c.cpu().numpy()[[0, 5, 11]].tolist())
