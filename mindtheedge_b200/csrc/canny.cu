@@ -11,6 +11,8 @@
 //                        E with  E(p) <= t  <=>  p is an edge of cv2.Canny at pair t  (instead of T planes).
 //  3. canny_expand_kernel  optional: the T {0,255} planes the reference API returns.
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mte {
@@ -134,6 +136,10 @@ struct UfP {
     int *list;            // [N,H,W] candidate pixels, sorted by cl
     int *merged;          // [N,H,W] roots linked away during the current level
     unsigned char *flag;  // [N,H,W] "component holds an edge pixel", valid at roots
+    int *todo;            // [N] written by the shared-memory kernel: 1 = image left to the L2 kernel (nullptr = all)
+    int cap;              // shared-memory kernel: candidate capacity
+    unsigned long long *prof;  // optional per-section cycle counters (MTE_HYST_PROF)
+    unsigned oRank, oParent, oFlag, oEc;  // shared-memory kernel: byte offsets of its arrays behind the bitmap
 };
 
 // find with path halving (every visited node is re-pointed to its grandparent; lock-free safe: a node only
@@ -165,6 +171,7 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_kernel(const UfP P) 
     __shared__ int sEnd[256];    // sEnd[t] = number of candidates with cl <= t (list is sorted by cl)
     __shared__ int sMerged;
     const int img = blockIdx.x;
+    if (P.todo && !P.todo[img]) return;  // solved by the shared-memory kernel
     const int HW = P.H * P.W;
     const size_t base = (size_t)img * HW;
     const unsigned char *cl = P.cl + base;
@@ -270,6 +277,218 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_kernel(const UfP P) 
     }
 }
 
+// ---------------------------------------------------------------------------
+// The same incremental union-find with the whole per-image state in SHARED memory: candidates get compact 16-bit
+// ids (raster rank: window bitmap + per-64-pixel rank, as in the matcher), parents are 16-bit shared-memory words,
+// component flags one bit each.  A find is then a few 30-cycle shared-memory hops instead of dependent L2 round
+// trips (the L2 kernel above spends its time there: ~2 x candidates finds per level).  Per-candidate edge levels
+// live in a compact global array in list order (coalesced) and are scattered to the plane at the end.  Images with
+// more candidates than fit (or planes whose bitmap does not fit) are left to the L2 kernel through P.todo.
+// ---------------------------------------------------------------------------
+constexpr unsigned short kNoCand = 0xFFFF;
+
+__device__ __forceinline__ int ufs_find(volatile unsigned short *parent, int x) {
+    int p = parent[x];
+    while (p != x) {
+        const int gp = parent[p];
+        if (gp == p) return p;
+        parent[x] = (unsigned short)gp;
+        x = gp;
+        p = parent[x];
+    }
+    return x;
+}
+
+__global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const UfP P) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ int sHist[256], sEnd[256], sScan[kUfThreads];
+    __shared__ int sMerged;
+    const int img = blockIdx.x;
+    const int H = P.H, W = P.W, HW = H * W, T = P.T;
+    const int nW = (HW + 31) >> 5, nW2 = (nW + 1) >> 1;
+    const size_t base = (size_t)img * HW;
+    const unsigned char *cl = P.cl + base;
+    unsigned char *E = P.E + base;
+    int *list = P.list + base;
+    int *merged = P.merged + base;
+    // candidate ids are positions in the level-sorted list: "is a candidate at level t" is id < sEnd[t], the
+    // per-candidate state (parent, edge level, flag) is indexed by id in shared memory and the per-level passes touch
+    // nothing else; only the neighbour lookup of step (i) goes raster rank -> id through a global table
+    unsigned short *perm = reinterpret_cast<unsigned short *>(P.parent + base);
+    unsigned *qbits = reinterpret_cast<unsigned *>(dyn);
+    unsigned short *qrank = reinterpret_cast<unsigned short *>(dyn + P.oRank);
+    unsigned short *parent = reinterpret_cast<unsigned short *>(dyn + P.oParent);
+    unsigned *flagW = reinterpret_cast<unsigned *>(dyn + P.oFlag);
+    unsigned char *Ec = dyn + P.oEc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long tk = clock64();
+    auto tick = [&](int slot) {
+        if (P.prof && threadIdx.x == 0) {
+            const long long now = clock64();
+            atomicAdd(P.prof + slot, (unsigned long long)(now - tk));
+            tk = now;
+        }
+    };
+    for (int i = threadIdx.x; i < 256; i += kUfThreads) sHist[i] = 0;
+    __syncthreads();
+    const bool vec = (HW % 16) == 0 && (reinterpret_cast<uintptr_t>(cl) & 15) == 0;
+    // ---- pass 1: candidate bitmap + histogram of first-candidate levels
+    for (int i0 = threadIdx.x * 16; i0 < nW * 32; i0 += kUfThreads * 16) {
+        unsigned char v[16];
+        if (i0 < HW) load16(v, cl, i0, HW, vec);
+        else {
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = (unsigned char)kNever;
+        }
+        unsigned half = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            half |= (v[k] != kNever ? 1u : 0u) << k;
+            const unsigned grp = __match_any_sync(__activemask(), (int)v[k]);
+            if (v[k] != kNever && (int)(__ffs(grp) - 1) == lane) atomicAdd(&sHist[v[k]], __popc(grp));
+        }
+        const unsigned hi = __shfl_down_sync(__activemask(), half, 1);
+        if (!(lane & 1)) qbits[i0 >> 5] = half | (hi << 16);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int t = 0; t < 255; t++) {
+            const int c = sHist[t];
+            sHist[t] = run;
+            run += c;
+            sEnd[t] = run;
+        }
+    }
+    __syncthreads();
+    const int nCand = sEnd[254];
+    tick(0);
+    if (P.prof && threadIdx.x == 0) atomicAdd(P.prof + 8, (unsigned long long)nCand);
+    if (nCand > P.cap) {  // leave the image to the L2 kernel
+        if (threadIdx.x == 0) P.todo[img] = 1;
+        return;
+    }
+    if (threadIdx.x == 0) P.todo[img] = 0;
+    // ---- rank: exclusive prefix popcount over pairs of bitmap words
+    {
+        const int per = (nW2 + kUfThreads - 1) / kUfThreads;
+        const int w0 = threadIdx.x * per, w1 = min(w0 + per, nW2);
+        auto pc2 = [&](int k2) { return __popc(qbits[2 * k2]) + (2 * k2 + 1 < nW ? __popc(qbits[2 * k2 + 1]) : 0); };
+        int sum = 0;
+        for (int k2 = w0; k2 < w1; k2++) sum += pc2(k2);
+        sScan[threadIdx.x] = sum;
+        __syncthreads();
+        if (warp == 0) {
+            int loc[kUfThreads / 32], run = 0;
+#pragma unroll
+            for (int q = 0; q < kUfThreads / 32; q++) { loc[q] = run; run += sScan[lane * (kUfThreads / 32) + q]; }
+            int incl = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(MTE_FULL_MASK, incl, o); if (lane >= o) incl += v; }
+            const int excl = incl - run;
+#pragma unroll
+            for (int q = 0; q < kUfThreads / 32; q++) sScan[lane * (kUfThreads / 32) + q] = excl + loc[q];
+        }
+        __syncthreads();
+        int run = sScan[threadIdx.x];
+        for (int k2 = w0; k2 < w1; k2++) { qrank[k2] = (unsigned short)run; run += pc2(k2); }
+    }
+    for (int i = threadIdx.x; i < nCand; i += kUfThreads) parent[i] = (unsigned short)i;
+    for (int i = threadIdx.x; i < (nCand + 31) / 32; i += kUfThreads) flagW[i] = 0u;
+    __syncthreads();
+    auto qid = [&](int q) -> int {
+        const unsigned bits = qbits[q >> 5];
+        int r = (int)qrank[q >> 6] + __popc(bits & ((1u << (q & 31)) - 1u));
+        if (q & 32) r += __popc(qbits[(q >> 5) - 1]);
+        return r;
+    };
+    // ---- pass 2: candidates sorted by level, with their compact ids and strong levels
+    for (int i0 = threadIdx.x * 16; i0 < HW; i0 += kUfThreads * 16) {
+        unsigned char v[16];
+        load16(v, cl, i0, HW, vec);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const unsigned act = __activemask();
+            const unsigned grp = __match_any_sync(act, (int)v[k]);
+            const int leader = __ffs(grp) - 1;
+            int slot = 0;
+            if (v[k] != kNever && lane == leader) slot = atomicAdd(&sHist[v[k]], __popc(grp));
+            slot = __shfl_sync(act, slot, leader);
+            if (v[k] != kNever) {
+                const int at = slot + __popc(grp & ((1u << lane) - 1));
+                list[at] = i0 + k;
+                perm[qid(i0 + k)] = (unsigned short)at;
+                Ec[at] = E[i0 + k];
+            }
+        }
+    }
+    __syncthreads();
+    tick(1);
+    volatile unsigned short *vparent = parent;
+    for (int t = 0; t < T; t++) {
+        const int begin = t ? sEnd[t - 1] : 0, end = sEnd[t];
+        // (i) the pixels that become candidates at this level join their 8-neighbours that already are
+        for (int k = begin + threadIdx.x; k < end; k += kUfThreads) {
+            const int p = list[k];
+            const int y = p / W, x = p - y * W;
+            int nid[8];
+#pragma unroll
+            for (int d = 0; d < 8; d++) {  // all neighbour lookups first: the table reads overlap
+                const int dy = (d < 3) ? -1 : ((d < 5) ? 0 : 1);
+                const int dx = (d == 0 || d == 3 || d == 5) ? -1 : ((d == 1 || d == 6) ? 0 : 1);
+                const int yy = y + dy, xx = x + dx;
+                nid[d] = 0xFFFF;
+                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                const int q = yy * W + xx;
+                if ((qbits[q >> 5] >> (q & 31)) & 1u) nid[d] = __ldcg(perm + qid(q));
+            }
+#pragma unroll
+            for (int d = 0; d < 8; d++) {
+                if (nid[d] >= end) continue;  // not a candidate, or a candidate of a later level
+                if (nid[d] >= begin && nid[d] > k) continue;  // same level: the pair is united from its larger end
+#ifdef MTE_HYST_EXP
+                if (MTE_HYST_EXP == 1) continue;
+#endif
+                int a = k, b = nid[d];
+                for (;;) {
+                    a = ufs_find(vparent, a);
+                    b = ufs_find(vparent, b);
+                    if (a == b) break;
+                    // link by a hashed priority, not by index: neighbouring pixels have consecutive ids, and when a
+                    // whole level is united at once "larger under smaller" builds chains as long as the contours
+                    if ((unsigned)a * 0x9E3779B1u < (unsigned)b * 0x9E3779B1u) { const int tmp = a; a = b; b = tmp; }
+                    if (atomicCAS(parent + a, (unsigned short)a, (unsigned short)b) == (unsigned short)a) break;
+                }
+            }
+        }
+        __syncthreads();
+        tick(2);
+        // (ii) flags follow the roots that were linked away (a node that ever carried a flag hands it to its current
+        //      root: no list of merged roots, whose single shared counter serialised the unions); pixels that turn
+        //      strong at this level seed theirs
+        for (int k = threadIdx.x; k < end; k += kUfThreads) {
+            if (Ec[k] == t || ((((volatile unsigned *)flagW)[k >> 5] >> (k & 31)) & 1u)) {
+                const int r = ufs_find(vparent, k);
+                if (r != k || Ec[k] == t) atomicOr(&flagW[r >> 5], 1u << (r & 31));
+            }
+        }
+        __syncthreads();
+        tick(3);
+        // (iii) every unassigned candidate of a flagged component becomes an edge at this level
+        for (int k = threadIdx.x; k < end; k += kUfThreads) {
+            if (Ec[k] > t) {
+                const int r = ufs_find(vparent, k);
+                if ((((volatile unsigned *)flagW)[r >> 5] >> (r & 31)) & 1u) Ec[k] = (unsigned char)t;
+            }
+        }
+        __syncthreads();
+        tick(4);
+    }
+    for (int k = threadIdx.x; k < nCand; k += kUfThreads) E[list[k]] = Ec[k];
+    __syncthreads();
+    tick(5);
+}
+
 __global__ void canny_expand_kernel(const unsigned char *__restrict__ E, unsigned char *__restrict__ edges, size_t n,
                                     int T) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -308,13 +527,47 @@ int run_level_hysteresis(const unsigned char *cl, unsigned char *E, int N, int H
     P.list = reinterpret_cast<int *>(w + align_up(px * 4, 256));
     P.merged = reinterpret_cast<int *>(w + 2 * align_up(px * 4, 256));
     P.flag = reinterpret_cast<unsigned char *>(w + 3 * align_up(px * 4, 256));
+    P.todo = nullptr;
+    P.cap = 0;
+    P.prof = getenv("MTE_HYST_PROF") ? reinterpret_cast<unsigned long long *>(w + hysteresis_scratch_bytes(N, H, W) - 256) : nullptr;
+    // shared-memory kernel first when the plane's bitmap leaves room for a useful number of candidates
+    static int budget = -1;
+    if (budget < 0) {
+        int dev = 0, optin = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, canny_uf_hyst_smem_kernel);
+        budget = optin - (int)fa.sharedSizeBytes - 1024;
+        if (budget > 0 && cudaFuncSetAttribute(canny_uf_hyst_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               budget) != cudaSuccess)
+            budget = 0;
+        cudaGetLastError();
+    }
+    const long long HW = (long long)H * W;
+    const long long nW = (HW + 31) / 32, nW2 = (nW + 1) / 2;
+    const long long fixed = align_up((size_t)nW * 4, 16) + align_up((size_t)nW2 * 2, 16) + 64;
+    long long cap = ((long long)budget - fixed) * 8 / 25;  // 2 B parent + 1 B edge level + 1 bit flag per candidate
+    if (cap > 65535) cap = 65535;
+    if (cap >= 4096 && !getenv("MTE_HYST_L2")) {
+        cap &= ~31LL;
+        P.cap = (int)cap;
+        P.oRank = (unsigned)align_up((size_t)nW * 4, 16);
+        P.oParent = P.oRank + (unsigned)align_up((size_t)nW2 * 2, 16);
+        P.oFlag = P.oParent + (unsigned)align_up((size_t)cap * 2, 16);
+        P.oEc = P.oFlag + (unsigned)align_up((size_t)cap / 8 + 4, 16);
+        const size_t smem = P.oEc + align_up((size_t)cap, 16);
+        P.todo = reinterpret_cast<int *>(w + 3 * align_up(px * 4, 256) + align_up(px, 256));
+        canny_uf_hyst_smem_kernel<<<N, kUfThreads, smem, st>>>(P);
+        MTE_RETURN_IF_CUDA_ERROR();
+    }
     canny_uf_hyst_kernel<<<N, kUfThreads, 0, st>>>(P);
     MTE_RETURN_IF_CUDA_ERROR();
     return MTE_OK;
 }
 size_t hysteresis_scratch_bytes(int N, int H, int W) {
     const size_t px = (size_t)N * H * W;
-    return 3 * align_up(px * 4, 256) + align_up(px, 256);
+    return 3 * align_up(px * 4, 256) + align_up(px, 256) + align_up((size_t)N * sizeof(int), 256) + 256;
 }
 
 static int run_pairs(const void *depth, int dtype, int N, int H, int W, double min_depth, double max_depth,

@@ -88,6 +88,35 @@ def test_golden_pr_evaluation_files():
     assert mean_recall_at_precision_range(pr, 0.12, 0.65) == z["pr_auc_part"]
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_soft_map_99_threshold_sweep_vs_oracle(dtype):
+    """evaluate_boundaries' default threshold grid (99 ascending thresholds on a strength map): the incremental
+    sweep matcher must give the count of every threshold exactly as 99 independent matchings do."""
+    from mindtheedge_b200.eval_depth_edges import pr_counts
+    from oracle import pr_counts as opr
+    h, w = 120, 300
+    r = np.random.default_rng(7)
+    thr = np.linspace(0.01, 0.99, 99)
+    preds, gts = [], []
+    for k in range(3):
+        pb, gb = random_boundary_maps(h, w, 900 + k)
+        soft = (cv2.GaussianBlur((pb != 0).astype(np.float32), (5, 5), 1.2) * 2.5).clip(0, 1)
+        soft = (soft * (0.4 + 0.6 * r.random((h, w)))).astype(dtype)
+        soft[5, 7] = thr[40]          # values sitting exactly on thresholds
+        soft[9, 11] = np.nan
+        preds.append(soft)
+        gts.append((gb != 0).astype(np.uint8))
+    c = pr_counts(torch.from_numpy(np.stack(preds)).cuda(), torch.from_numpy(np.stack(gts)).cuda(), thr,
+                  max_dist=0.0075).cpu().numpy()
+    ref = np.zeros((99, 4), np.int64)
+    for k in range(3):
+        for t in range(99):
+            b = (preds[k].astype(np.float64) >= thr[t])
+            m = opr.match_count(b.astype(np.uint8), gts[k], 0.0075)
+            ref[t] += (m, int(gts[k].sum()), m, int(b.sum()))
+    assert np.array_equal(c, ref)
+
+
 def test_kitti_size_sweep_vs_oracle():
     """Config 2 shape: 384x1280 planes, 12 Canny settings, KITTI crop, max_dist 0.002 -- bit-exact counts."""
     from mindtheedge_b200.eval_depth_edges import pr_evaluation_arrays
