@@ -164,13 +164,18 @@ int mte_binary_thin(const uint8_t *in, uint8_t *out, int n_images, int H, int W,
 
 /* ------------------------------------------------------------------------
  * In-training "light" metric: chamfer_distance
- * (packnet_code/packnet_sfm/utils/edge.py:20-62) for a batch of u8 edge maps.
- * out: device double[N,4] = {sum of EDT(gt) over pred px, #pred px,
- *      #pred px with distance < thresh, unused}.
+ * (packnet_code/packnet_sfm/utils/edge.py:20-62; called per Canny setting in
+ * both directions by compute_edge_metrics, models/model_wrapper.py:434-440)
+ * for a batch of u8 edge maps (set = value/255 > 0.5).
+ * out: device double[N,4] = {sum over pred px of the Euclidean distance to the
+ *      nearest gt px (exact EDT, as scipy.ndimage.distance_transform_edt),
+ *      #pred px, #pred px with distance < thresh, 0}.
+ * cond_out: optional int8 [N,H,W]: -1 = not a pred px, 1 = closer than thresh,
+ *      0 = not (the third return value of the reference), or NULL.
  * ------------------------------------------------------------------------ */
 size_t mte_chamfer_workspace_bytes(int n_images, int H, int W);
 int mte_chamfer_counts(const uint8_t *pred, const uint8_t *gt, int n_images, int H, int W, double thresh,
-                       double *out, void *workspace, size_t workspace_bytes, mte_stream_t stream);
+                       double *out, int8_t *cond_out, void *workspace, size_t workspace_bytes, mte_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -58,7 +58,7 @@ _SIGNATURES = {
     "mte_thin_workspace_bytes": (_sz, [_i, _i, _i]),
     "mte_binary_thin": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "mte_chamfer_workspace_bytes": (_sz, [_i, _i, _i]),
-    "mte_chamfer_counts": (_i, [_vp, _vp, _i, _i, _i, _d, _vp, _vp, _sz, _vp]),
+    "mte_chamfer_counts": (_i, [_vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _sz, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

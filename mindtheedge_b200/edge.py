@@ -6,6 +6,9 @@
   ``edge_from_depth_cfg`` is the cfg-taking twin of ``utils/edge.py:64-89``.
 * ``Canny``            ``cv2.Canny(u8, t1, t2)`` replacement for the bare calls in
   ``models/model_wrapper.py:399-401``.
+* ``chamfer_distance`` / ``compute_edge_metrics``  the in-training "light" edge metric of
+  ``utils/edge.py:20-62`` and ``models/model_wrapper.py:376-442`` (3 Canny settings, chamfer
+  precision / recall / F1) without the host round trip and the scipy EDT.
 * ``canny_from_depth`` the tensor-level op the evaluation pipeline uses: a batch
   of depth planes and T threshold pairs in, either the T edge planes or the
   single "birth level" plane out (no host round trip).
@@ -24,7 +27,8 @@ import torch
 
 from . import _lib, runtime
 
-__all__ = ["canny_from_depth", "edge_from_depth", "edge_from_depth_cfg", "Canny", "read_depth_file"]
+__all__ = ["canny_from_depth", "edge_from_depth", "edge_from_depth_cfg", "Canny", "read_depth_file",
+           "chamfer_counts", "chamfer_distance", "compute_edge_metrics"]
 
 _DT = {torch.float32: _lib.MTE_F32, torch.float64: _lib.MTE_F64, torch.uint8: _lib.MTE_U8}
 
@@ -117,3 +121,88 @@ def Canny(image: np.ndarray, threshold1, threshold2) -> np.ndarray:
         raise _lib.MteError("Canny expects a 2-D uint8 image")
     d = torch.from_numpy(img).cuda(non_blocking=True)
     return canny_from_depth(d, [(threshold1, threshold2)])[0].cpu().numpy()
+
+
+# ---------------------------------------------------------------------------
+# in-training "light" edge metric
+# ---------------------------------------------------------------------------
+def chamfer_counts(pred: torch.Tensor, gt: torch.Tensor, edge_to_edge_thresh: float = 5, want_map: bool = False):
+    """pred, gt: CUDA uint8 [N,H,W] edge maps (set = value/255 > 0.5).
+    -> float64 [N,4] on the device: sum of the exact Euclidean distances from every pred pixel to the nearest
+    gt pixel, number of pred pixels, number of pred pixels closer than the threshold, 0; and, with ``want_map``,
+    the int8 [N,H,W] map (-1 not a pred pixel, 1 close, 0 not)."""
+    runtime.require_cuda(pred, "pred")
+    runtime.require_cuda(gt, "gt")
+    if pred.dtype != torch.uint8 or gt.dtype != torch.uint8 or pred.shape != gt.shape or pred.dim() != 3:
+        raise _lib.MteError("chamfer_counts expects two uint8 [N,H,W] maps of the same shape")
+    pred, gt = pred.contiguous(), gt.contiguous()
+    N, H, W = pred.shape
+    dev = pred.device
+    out = torch.empty((N, 4), dtype=torch.float64, device=dev)
+    cond = torch.empty((N, H, W), dtype=torch.int8, device=dev) if want_map else None
+    ws = runtime.workspace(dev, _lib.lib.mte_chamfer_workspace_bytes(N, H, W))
+    _lib.check(_lib.lib.mte_chamfer_counts(pred.data_ptr(), gt.data_ptr(), N, H, W, float(edge_to_edge_thresh),
+                                           out.data_ptr(), runtime.ptr(cond), ws.data_ptr(), ws.numel(),
+                                           runtime.current_stream_ptr(dev)), "mte_chamfer_counts")
+    return (out, cond) if want_map else out
+
+
+def chamfer_distance(im_pred, im_gt, mask=None, edge_to_edge_thresh=5):
+    """Drop-in for ``packnet_sfm.utils.edge.chamfer_distance`` (utils/edge.py:20-62) for 2-D maps:
+    -> (c_dist, percentage, edges_cond_reshaped).  ``mask`` must be None: the reference's mask branch only
+    broadcasts for 3-channel images (utils/edge.py:27-28) and no call site passes one."""
+    if mask is not None:
+        raise NotImplementedError("chamfer_distance: the mask branch of the reference is 3-channel only and unused")
+    p = np.ascontiguousarray(im_pred)
+    g = np.ascontiguousarray(im_gt)
+    if p.ndim != 2 or p.shape != g.shape:
+        raise _lib.MteError("chamfer_distance expects two 2-D maps of the same shape")
+    # value / 255 > 0.5 for any numeric dtype -> the u8 convention of the kernel
+    pb = torch.from_numpy(((p / 255) > 0.5).astype(np.uint8) * 255).cuda()
+    gb = torch.from_numpy(((g / 255) > 0.5).astype(np.uint8) * 255).cuda()
+    out, cond = chamfer_counts(pb[None], gb[None], edge_to_edge_thresh, want_map=True)
+    s, n, k, _ = out[0].cpu().numpy()
+    with np.errstate(invalid="ignore", divide="ignore"):
+        c_dist = np.float64(s) / np.float64(n)
+        percentage = np.float64(k) / np.float64(n)
+    return c_dist, percentage, cond[0].cpu().numpy().astype(np.float64)
+
+
+def compute_edge_metrics(depth: torch.Tensor, edge: torch.Tensor, gt_crop=None, edge_model: bool = False):
+    """Device version of ``ModelWrapper.compute_edge_metrics`` (models/model_wrapper.py:376-442).
+
+    depth  CUDA [H,W] (or [1,1,H,W]): predicted DEPTH at the GT size (``inv2depth`` + resize already applied),
+           or, with ``edge_model``, the predicted edge probability map (thresholds 0.5 / 0.75 / 0.9).
+    edge   CUDA [H,W] GT edge map in [0,1] (the reference multiplies by 255 and binarises at 0.5).
+    ->     the 9 numbers the reference appends: for each of the three settings, chamfer precision
+           (pred px within < 5 px of a GT px), recall (the converse) and their harmonic mean."""
+    d = depth.reshape(depth.shape[-2], depth.shape[-1])
+    g = edge.reshape(edge.shape[-2], edge.shape[-1])
+    runtime.require_cuda(d, "depth")
+    runtime.require_cuda(g, "edge")
+    if edge_model:
+        preds = torch.stack([(d > t).to(torch.uint8) * 255 for t in (0.5, 0.75, 0.9)])
+    else:
+        d = d.float()
+        # depth * (255 / max) -> uint8 (model_wrapper.py:396-397), then the three Canny settings of :399-401 in one
+        # nested sweep (strictest first)
+        mx = float(d.max().item())
+        lv = canny_from_depth(d, [(30, 60), (20, 40), (10, 20)], float("-inf"), mx, want_edges=False,
+                              want_levels=True)
+        preds = torch.stack([(lv <= t).to(torch.uint8) * 255 for t in (2, 1, 0)])
+    gt = ((g.float() * 255) / 255 > 0.5).to(torch.uint8) * 255
+    if gt_crop is not None and len(gt_crop) > 0:
+        c = gt_crop
+        gt = gt[c[2]:c[3], c[0]:c[1]]
+        preds = preds[:, c[2]:c[3], c[0]:c[1]]
+    gts = gt[None].expand_as(preds).contiguous()
+    preds = preds.contiguous()
+    a = chamfer_counts(preds, gts).cpu().numpy()   # pred -> gt
+    b = chamfer_counts(gts, preds).cpu().numpy()   # gt -> pred
+    out = []
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for i in range(3):
+            p1 = np.float64(a[i, 2]) / np.float64(a[i, 1])
+            p2 = np.float64(b[i, 2]) / np.float64(b[i, 1])
+            out += [p1, p2, 2 * ((p1 * p2) / (p1 + p2))]
+    return out

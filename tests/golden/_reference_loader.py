@@ -59,3 +59,22 @@ def load_eval_depth_edges(thin_mod, correspond_mod):
     sys.modules[spec.name] = mod  # picklable for the reference's multiprocessing.Pool
     spec.loader.exec_module(mod)
     return mod
+
+
+def load_utils_edge():
+    """packnet_sfm/utils/edge.py (chamfer_distance).  Its import chain wants `yacs`, which is not installed here and
+    is only used for an isinstance check in utils/types.py: a stub module stands in."""
+    y = types.ModuleType("yacs")
+    yc = types.ModuleType("yacs.config")
+
+    class CfgNode(dict):
+        pass
+    yc.CfgNode = CfgNode
+    y.config = yc
+    y.CfgNode = CfgNode
+    sys.modules.setdefault("yacs", y)
+    sys.modules.setdefault("yacs.config", yc)
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from packnet_code.packnet_sfm.utils import edge as ref_utils_edge
+    return ref_utils_edge

@@ -236,9 +236,62 @@ def gen_pr():
     print("pr:", {k: v for k, v in out.items() if k.startswith("pr_") and np.size(v) < 8})
 
 
+def gen_chamfer():
+    """chamfer_distance of the UNMODIFIED packnet_sfm/utils/edge.py on synthetic edge maps (both directions), and
+    the 9 light metrics of compute_edge_metrics restated around it (cv2.Canny + the reference chamfer_distance)."""
+    import cv2
+    from _reference_loader import load_utils_edge
+    E = load_utils_edge()
+    out = {}
+    r = np.random.default_rng(5)
+    cases = []
+    for k, (H, W) in enumerate([(60, 90), (218, 1153), (40, 300), (7, 5)]):
+        gt, depth = synth_gt_and_depth(max(H, 32), max(W, 32), 300 + k)
+        gt = gt[:H, :W].astype(np.uint8) * 255
+        pred = cv2.Canny((np.clip(depth[:H, :W], 0, 80) * (255.0 / 80)).astype(np.uint8), 10, 20)
+        cases.append((pred, gt))
+    cases.append((np.zeros((20, 30), np.uint8), cases[0][1][:20, :30]))           # no predicted pixel
+    cases.append((cases[0][0][:20, :30], np.zeros((20, 30), np.uint8)))           # no GT pixel (scipy's convention)
+    cases.append(((r.random((33, 47)) < 0.5).astype(np.uint8) * 255, (r.random((33, 47)) < 0.01).astype(np.uint8) * 255))
+    out["n"] = np.int64(len(cases))
+    for i, (p, g) in enumerate(cases):
+        out[f"pred{i}"] = np.packbits(p > 127)
+        out[f"gt{i}"] = np.packbits(g > 127)
+        out[f"shape{i}"] = np.array(p.shape)
+        for tag, (a, b) in (("pg", (p, g)), ("gp", (g, p))):
+            with np.errstate(invalid="ignore", divide="ignore"):
+                c_dist, perc, cond = E.chamfer_distance(a.astype(np.float64), b.astype(np.float64))
+            out[f"{tag}{i}_cdist"] = np.float64(c_dist)
+            out[f"{tag}{i}_perc"] = np.float64(perc)
+            out[f"{tag}{i}_cond"] = cond.astype(np.int8)
+    # compute_edge_metrics: model_wrapper.py cannot be imported here (yacs, MinkowskiEngine, ...): its body for a
+    # depth model is restated in oracle/chamfer.py; pin the restatement's arithmetic to the reference chamfer_distance
+    gt, depth = synth_gt_and_depth(160, 512, 311)
+    vis = (depth * (255.0 / np.max(depth))).astype(np.uint8)
+    crop = [18, 480, 60, 150]
+    vals = []
+    for lo, hi in ((10, 20), (20, 40), (30, 60)):
+        im = cv2.Canny(vis, lo, hi)[crop[2]:crop[3], crop[0]:crop[1]]
+        g = (gt.astype(np.float64) * 255)[crop[2]:crop[3], crop[0]:crop[1]]
+        _, p1, _ = E.chamfer_distance(im, g)
+        _, p2, _ = E.chamfer_distance(g, im)
+        vals += [p1, p2, 2 * ((p1 * p2) / (p1 + p2))]
+    out["metrics_depth_u16"] = np.round(depth * 256).astype(np.uint16)   # depth is on the 1/256 m grid
+    out["metrics_crop"] = np.array(crop)
+    out["metrics_shape"] = np.array(depth.shape)
+    out["metrics_gt"] = np.packbits(gt)
+    out["metrics_vals"] = np.array(vals, np.float64)
+    np.savez_compressed(os.path.join(HERE, "chamfer.npz"), **out)
+    print("chamfer:", out["metrics_vals"])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "chamfer":
+        gen_chamfer()
+        sys.exit(0)
     torch.manual_seed(0)
     gen_edge_loss()
     gen_canny()
     gen_dee()
     gen_pr()
+    gen_chamfer()

@@ -66,6 +66,9 @@ def test_host_side_argument_checks_without_a_gpu():
     assert L.mte_pr_counts(256, 2, 256, 1, 8, 8, None, None, 300, 0.002, 0, 256, 256, 1 << 30, None) == -4
     assert L.mte_dee_workspace_bytes(2, 384, 1280) > 0 and L.mte_thin_workspace_bytes(2, 10, 10) > 0
     assert L.mte_dee_postprocess(None, 0, 1, 8, 8, 1, 1, 0.3, 0.7, None, None, 1, None, 0, None) == -1
+    assert L.mte_chamfer_workspace_bytes(3, 384, 1280) > 3 * 384 * 1280 * 2 and L.mte_chamfer_workspace_bytes(0, 4, 4) == 0
+    assert L.mte_chamfer_counts(None, None, 1, 8, 8, 5.0, None, None, None, 0, None) == -1
+    assert L.mte_chamfer_counts(256, 256, 1, 8, 8, 5.0, 256, None, 256, 16, None) == -3
 
 
 def test_no_cpu_fallback():

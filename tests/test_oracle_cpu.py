@@ -133,3 +133,30 @@ def test_thin_oracle_properties():
     assert np.array_equal(thin.binary_thin(line), line)  # a 1-px line is already thin
     lut1, lut2 = thin.build_luts()
     assert lut1.sum() == lut2.sum() and not lut1[0] and not lut1[255]
+
+
+def _chamfer_cases():
+    z = np.load(os.path.join(GOLDEN, "chamfer.npz"))
+    for i in range(int(z["n"])):
+        H, W = z[f"shape{i}"]
+        p = np.unpackbits(z[f"pred{i}"])[: H * W].reshape(H, W).astype(np.uint8) * 255
+        g = np.unpackbits(z[f"gt{i}"])[: H * W].reshape(H, W).astype(np.uint8) * 255
+        yield i, z, p, g
+
+
+def test_chamfer_oracle_vs_reference_golden():
+    """oracle/chamfer.py against chamfer_distance of the unmodified packnet_sfm/utils/edge.py (both directions,
+    incl. the empty-pred (nan) and empty-GT (scipy's virtual background sample) cases) and the 9 light metrics."""
+    from oracle import chamfer as och
+    for i, z, p, g in _chamfer_cases():
+        for tag, (a, b) in (("pg", (p, g)), ("gp", (g, p))):
+            c, pc, close, n = och.chamfer_distance(a, b)
+            assert np.array_equal(c, z[f"{tag}{i}_cdist"], equal_nan=True), (i, tag)
+            assert np.array_equal(pc, z[f"{tag}{i}_perc"], equal_nan=True), (i, tag)
+            cond = z[f"{tag}{i}_cond"]
+            assert n == int((cond >= 0).sum()) and close == int((cond == 1).sum())
+    z = np.load(os.path.join(GOLDEN, "chamfer.npz"))
+    H, W = z["metrics_shape"]
+    d = (z["metrics_depth_u16"] / 256).astype(np.float32)
+    g = np.unpackbits(z["metrics_gt"])[: H * W].reshape(H, W).astype(np.float64)
+    assert np.array_equal(np.array(och.compute_edge_metrics(d, g, list(z["metrics_crop"]))), z["metrics_vals"])
