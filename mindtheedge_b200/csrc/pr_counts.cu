@@ -677,6 +677,10 @@ __global__ void __launch_bounds__(kSmThreads, 1) match_smem_kernel(const __grid_
 constexpr unsigned kDeadStamp = 0xFFFFFFFFu;   // GT stamp word: phase << 16 | root (predicted vertex id of the tree)
 constexpr unsigned short kFailed = 0xFFFD;     // predicted pixel whose search failed conclusively (Kuhn: for good)
 enum { RF_FOUND = 1u, RF_BLOCKED = 2u };
+#ifndef MTE_SWEEP_THREADS
+#define MTE_SWEEP_THREADS 512
+#endif
+constexpr int kSwThreads = MTE_SWEEP_THREADS, kSwWarps = kSwThreads / 32;
 constexpr int kEndsCap = 2048;  // free GT pixels recorded per phase (further ones wait for the next phase)
 
 struct SweepLayout {
@@ -685,12 +689,12 @@ struct SweepLayout {
 };
 
 
-__global__ void __launch_bounds__(kSmThreads, 1) match_sweep_kernel(const __grid_constant__ MatchP Pin,
+__global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid_constant__ MatchP Pin,
                                                                     const __grid_constant__ ParamTables tabs,
                                                                     int tablesInParam, const SweepLayout SL) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ int sImage, sNP, sNQ, sCntA, sEnds, sMatched, sHead, sTail, sPending;
-    __shared__ int sScan[kSmThreads];
+    __shared__ int sScan[kSwThreads];
     __shared__ int sStage[MTE_MAX_THRESHOLDS + 2];   // histogram, then start offset of every stage
     __shared__ int sCursor[MTE_MAX_THRESHOLDS + 2];
     __shared__ short2 sOff[kSmemTableOff];
@@ -710,10 +714,10 @@ __global__ void __launch_bounds__(kSmThreads, 1) match_sweep_kernel(const __grid
     unsigned short *rootP = reinterpret_cast<unsigned short *>(dyn + SL.oRootP);
     unsigned *rflagW = reinterpret_cast<unsigned *>(dyn + SL.oRflag);  // one flag byte per predicted vertex
     unsigned short *ends = reinterpret_cast<unsigned short *>(dyn + SL.oEnds);
-    for (int i = threadIdx.x; i < P.noff; i += kSmThreads) sOff[i] = tablesInParam ? tabs.off[i] : P.off[i];
+    for (int i = threadIdx.x; i < P.noff; i += kSwThreads) sOff[i] = tablesInParam ? tabs.off[i] : P.off[i];
     const bool levels = P.inMode == IN_LEVELS;
     if (!levels)
-        for (int i = threadIdx.x; i < T; i += kSmThreads) sThr[i] = tablesInParam ? tabs.thr[i] : P.thr[i];
+        for (int i = threadIdx.x; i < T; i += kSwThreads) sThr[i] = tablesInParam ? tabs.thr[i] : P.thr[i];
     __syncthreads();
     const int noff = P.noff;
     long long tk = 0;
@@ -758,17 +762,17 @@ __global__ void __launch_bounds__(kSmThreads, 1) match_sweep_kernel(const __grid
         if (img >= P.N) break;
         const unsigned char *gt = P.gt + (size_t)img * P.H * P.W;
         if (threadIdx.x == 0) { sNQ = 0; sMatched = 0; }
-        for (int i = threadIdx.x; i < T + 2; i += kSmThreads) sStage[i] = 0;
+        for (int i = threadIdx.x; i < T + 2; i += kSwThreads) sStage[i] = 0;
         __syncthreads();
         tick(-1);
 
         // ---- pass 1: GT bitmap (one ballot per 32 window pixels) and the stage histogram of the predicted pixels
-        for (int base = 0; base < SL.nW * 32; base += 8 * kSmThreads) {
+        for (int base = 0; base < SL.nW * 32; base += 8 * kSwThreads) {
             int stg[8];
             bool isQ[8];
 #pragma unroll
             for (int u = 0; u < 8; u++) {
-                const int i = base + u * kSmThreads + threadIdx.x;
+                const int i = base + u * kSwThreads + threadIdx.x;
                 stg[u] = T; isQ[u] = false;
                 if (i < hw) {
                     const int y = i / w, x = i - y * w;
@@ -778,8 +782,8 @@ __global__ void __launch_bounds__(kSmThreads, 1) match_sweep_kernel(const __grid
             }
 #pragma unroll
             for (int u = 0; u < 8; u++) {
-                const int i = base + u * kSmThreads + threadIdx.x;
-                if (base + u * kSmThreads >= SL.nW * 32) break;  // warp-uniform
+                const int i = base + u * kSwThreads + threadIdx.x;
+                if (base + u * kSwThreads >= SL.nW * 32) break;  // warp-uniform
                 const unsigned mq = __ballot_sync(MTE_FULL_MASK, isQ[u]);
                 if (lane == 0) {
                     qbits[i >> 5] = mq;
@@ -815,11 +819,11 @@ __global__ void __launch_bounds__(kSmThreads, 1) match_sweep_kernel(const __grid
             continue;
         }
         // ---- pass 2: predicted pixels grouped by stage (order inside a stage is arbitrary: counts do not depend on it)
-        for (int base = 0; base < hw; base += 8 * kSmThreads) {
+        for (int base = 0; base < hw; base += 8 * kSwThreads) {
             int stg[8];
 #pragma unroll
             for (int u = 0; u < 8; u++) {
-                const int i = base + u * kSmThreads + threadIdx.x;
+                const int i = base + u * kSwThreads + threadIdx.x;
                 stg[u] = T;
                 if (i < hw) {
                     const int y = i / w, x = i - y * w;
@@ -828,7 +832,7 @@ __global__ void __launch_bounds__(kSmThreads, 1) match_sweep_kernel(const __grid
             }
 #pragma unroll
             for (int u = 0; u < 8; u++) {
-                const int i = base + u * kSmThreads + threadIdx.x;
+                const int i = base + u * kSwThreads + threadIdx.x;
                 if (stg[u] < T) {
                     const int slot = atomicAdd(&sCursor[stg[u]], 1);
                     ppix[slot] = (unsigned)i; mateP[slot] = kFree; claimP[slot] = 0;
@@ -838,7 +842,7 @@ __global__ void __launch_bounds__(kSmThreads, 1) match_sweep_kernel(const __grid
         // ---- rank: exclusive prefix popcount over pairs of bitmap words
         {
             const int nW2 = (SL.nW + 1) >> 1;
-            const int per = (nW2 + kSmThreads - 1) / kSmThreads;
+            const int per = (nW2 + kSwThreads - 1) / kSwThreads;
             const int w0 = threadIdx.x * per, w1 = min(w0 + per, nW2);
             auto pc2 = [&](int k2) { return __popc(qbits[2 * k2]) + (2 * k2 + 1 < SL.nW ? __popc(qbits[2 * k2 + 1]) : 0); };
             int sum = 0;
@@ -846,21 +850,21 @@ __global__ void __launch_bounds__(kSmThreads, 1) match_sweep_kernel(const __grid
             sScan[threadIdx.x] = sum;
             __syncthreads();
             if (warp == 0) {
-                int loc[kSmThreads / 32], run = 0;
+                int loc[kSwThreads / 32], run = 0;
 #pragma unroll
-                for (int q = 0; q < kSmThreads / 32; q++) { loc[q] = run; run += sScan[lane * (kSmThreads / 32) + q]; }
+                for (int q = 0; q < kSwThreads / 32; q++) { loc[q] = run; run += sScan[lane * (kSwThreads / 32) + q]; }
                 int incl = run;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(MTE_FULL_MASK, incl, o); if (lane >= o) incl += v; }
                 const int excl = incl - run;
 #pragma unroll
-                for (int q = 0; q < kSmThreads / 32; q++) sScan[lane * (kSmThreads / 32) + q] = excl + loc[q];
+                for (int q = 0; q < kSwThreads / 32; q++) sScan[lane * (kSwThreads / 32) + q] = excl + loc[q];
             }
             __syncthreads();
             int run = sScan[threadIdx.x];
             for (int k2 = w0; k2 < w1; k2++) { qrank[k2] = (unsigned short)run; run += pc2(k2); }
         }
-        for (int k = threadIdx.x; k < nQ; k += kSmThreads) { mateQ[k] = kFree; stamp[k] = 0u; }
+        for (int k = threadIdx.x; k < nQ; k += kSwThreads) { mateQ[k] = kFree; stamp[k] = 0u; }
         __syncthreads();
         tick(4);
 
@@ -869,7 +873,7 @@ __global__ void __launch_bounds__(kSmThreads, 1) match_sweep_kernel(const __grid
             const int p0 = sStage[s], p1 = sStage[s + 1];  // the pixels that join at this stage
             if (p1 > p0) {
                 // ---- greedy start: nearest free GT pixel (warp per new predicted pixel, lanes over offsets)
-                for (int pi = p0 + warp; pi < p1; pi += kSmWarps) {
+                for (int pi = p0 + warp; pi < p1; pi += kSwWarps) {
                     const int p = (int)ppix[pi];
                     const int py = p / w, px = p - py * w;
                     bool done = false, anyQ = false;
@@ -909,7 +913,7 @@ __global__ void __launch_bounds__(kSmThreads, 1) match_sweep_kernel(const __grid
                     phase++;
                     if (threadIdx.x == 0) { sCntA = 0; sEnds = 0; }
                     __syncthreads();
-                    for (int base = p0; base < p1; base += kSmThreads) {
+                    for (int base = p0; base < p1; base += kSwThreads) {
                         const int pi = base + threadIdx.x;
                         const bool fr = pi < p1 && mateP[pi] == kFree;
                         const unsigned m = __ballot_sync(MTE_FULL_MASK, fr);
@@ -919,7 +923,7 @@ __global__ void __launch_bounds__(kSmThreads, 1) match_sweep_kernel(const __grid
                         if (fr) { fa[wbase + __popc(m & ((1u << lane) - 1))] = (unsigned short)pi; rootP[pi] = (unsigned short)pi; }
                     }
                     // flag bytes of this stage's pixels (only roots use theirs)
-                    for (int i = (p0 >> 2) + threadIdx.x; i <= ((p1 - 1) >> 2); i += kSmThreads) rflagW[i] = 0u;
+                    for (int i = (p0 >> 2) + threadIdx.x; i <= ((p1 - 1) >> 2); i += kSwThreads) rflagW[i] = 0u;
                     __syncthreads();
                     const int nRoots = sCntA;
                     if (nRoots == 0) break;
@@ -928,7 +932,7 @@ __global__ void __launch_bounds__(kSmThreads, 1) match_sweep_kernel(const __grid
                     // stamp carries the tree (root) that claimed it: a tree that has found a free GT pixel stops
                     // growing, and a tree that found none WITHOUT ever running into another tree's vertices is closed
                     // under alternating reachability, hence dead, whatever the other trees of the phase do.
-                    for (int i = nRoots + threadIdx.x; i < p1; i += kSmThreads) fa[i] = kFree;  // unpublished slots
+                    for (int i = nRoots + threadIdx.x; i < p1; i += kSwThreads) fa[i] = kFree;  // unpublished slots
                     if (threadIdx.x == 0) { sHead = 0; sTail = nRoots; sPending = nRoots; }
                     __syncthreads();
                     tick(6);
@@ -1001,20 +1005,20 @@ __global__ void __launch_bounds__(kSmThreads, 1) match_sweep_kernel(const __grid
                     tick(7);
                     const int nEnds = min(sEnds, kEndsCap);
                     // wall off the trees that failed conclusively (all of them when the phase found nothing) ...
-                    for (int k = threadIdx.x; k < nQ; k += kSmThreads) {
+                    for (int k = threadIdx.x; k < nQ; k += kSwThreads) {
                         const unsigned st = stamp[k];
                         if (st != kDeadStamp && (st >> 16) == phase &&
                             (nEnds == 0 || !(rflag_get((int)(st & 0xFFFFu)) & (RF_FOUND | RF_BLOCKED))))
                             stamp[k] = kDeadStamp;
                     }
                     // ... and retire their roots (fa[0..nRoots) still holds them: the queue is append-only)
-                    for (int i = threadIdx.x; i < nRoots; i += kSmThreads) {
+                    for (int i = threadIdx.x; i < nRoots; i += kSwThreads) {
                         const int rp = fa[i];
                         if (nEnds == 0 || !(rflag_get(rp) & (RF_FOUND | RF_BLOCKED))) mateP[rp] = kFailed;
                     }
                     __syncthreads();
                     if (nEnds == 0) { tick(8); break; }
-                    for (int ei = threadIdx.x; ei < nEnds; ei += kSmThreads) {
+                    for (int ei = threadIdx.x; ei < nEnds; ei += kSwThreads) {
                         const int qEnd = ends[ei];
                         int q = qEnd;
                         bool ok = true;
@@ -1265,7 +1269,7 @@ static int launch(MatchP &P, const Layout &L, char *ws, double max_dist, const d
         if (SW.capP > 0) {
             int grid = kNumSMs;
             if (grid > P.N) grid = P.N;
-            match_sweep_kernel<<<grid, kSmThreads, SW.total, st>>>(P, pt, inParam ? 1 : 0, SW);
+            match_sweep_kernel<<<grid, kSwThreads, SW.total, st>>>(P, pt, inParam ? 1 : 0, SW);
             MTE_RETURN_IF_CUDA_ERROR();
             // the overflowed problems (usually none) go to the dense kernel
             P.problemList = P.overflowList;
