@@ -42,72 +42,109 @@ __device__ __forceinline__ unsigned char quantise<unsigned char>(unsigned char d
     return d;
 }
 
+// One CTA = one 128 x 32 tile.  Three phases through shared memory, four horizontally adjacent pixels per thread
+// and step in the two stencil phases (the first version spent ~300 instructions per pixel, most of them
+// recomputing the Sobel sums and walking the threshold list per pixel):
+//   A  quantise the tile + halo 2 (coordinates clamped = BORDER_REPLICATE) into u8
+//   B  Sobel3 + L1 magnitude for the tile + halo 1 from column sums shared by the four pixels; stored as one u16:
+//      magnitude (<= 2040, 11 bits) | NMS sector << 11 (0 horizontal, 1 vertical, 2 diagonal s=+1, 3 diagonal s=-1)
+//   C  NMS against the two neighbours of the sector; the surviving magnitude indexes a per-CTA table
+//      magnitude -> (first candidate level, first strong level) built once per launch (canny_lut_kernel)
+constexpr int QS = TW + 8;        // u8 row stride of the quantised tile (word aligned, halo 2 at columns 2..)
+constexpr int MS = TW + 4;        // u16 row stride of the magnitude tile (halo 1 at column 1..)
+constexpr int kMaxMag = 2040;     // |dx| + |dy| <= 2 * 4 * 255
+
+// magnitude -> (first candidate level | first strong level << 8), once per launch
+__global__ void __launch_bounds__(kThreads) canny_lut_kernel(const __grid_constant__ Thresholds thr,
+                                                             unsigned short *__restrict__ lut) {
+    const int v = blockIdx.x * kThreads + threadIdx.x;
+    if (v > kMaxMag) return;
+    int first_c = kNever, first_s = kNever;
+    for (int t = thr.n - 1; t >= 0; t--) {  // nested pairs: the last hit going down the list is the first index
+        if (v > thr.low[t]) first_c = t;
+        if (v > thr.high[t]) first_s = t;
+    }
+    lut[v] = (unsigned short)(first_c | (first_s << 8));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads) canny_nms_kernel(const T *__restrict__ depth, int N, int H, int W, T lo,
-                                                             T hi, T factor, const __grid_constant__ Thresholds thr,
+                                                             T hi, T factor, const unsigned short *__restrict__ glut,
                                                              unsigned char *__restrict__ cl,
                                                              unsigned char *__restrict__ E) {
-    __shared__ unsigned char q[TH + 4][TW + 4];
-    __shared__ unsigned short mag[TH + 2][TW + 4];
+    __shared__ __align__(16) unsigned char q[TH + 4][QS];
+    __shared__ __align__(16) unsigned short mag[TH + 2][MS];
+    __shared__ unsigned short lut[kMaxMag + 1];  // first_c | first_s << 8
     const int tilesX = ceil_div(W, TW), tilesY = ceil_div(H, TH);
     const int tile = blockIdx.x % (tilesX * tilesY), img = blockIdx.x / (tilesX * tilesY);
     const int x0 = (tile % tilesX) * TW, y0 = (tile / tilesX) * TH;
     const T *src = depth + (size_t)img * H * W;
 
-    // quantised image, halo 2, coordinates clamped (BORDER_REPLICATE)
+    for (int v = threadIdx.x; v <= kMaxMag; v += kThreads) lut[v] = glut[v];
+    // A: q[r][c] = pixel (y0 + r - 2, x0 + c - 4), columns 2 .. TW + 5 used
     for (int i = threadIdx.x; i < (TH + 4) * (TW + 4); i += kThreads) {
-        const int r = i / (TW + 4), c = i - r * (TW + 4);
-        const int y = min(max(y0 + r - 2, 0), H - 1), x = min(max(x0 + c - 2, 0), W - 1);
+        const int r = i / (TW + 4), c = i - r * (TW + 4) + 2;
+        const int y = min(max(y0 + r - 2, 0), H - 1), x = min(max(x0 + c - 4, 0), W - 1);
         q[r][c] = quantise<T>(src[(size_t)y * W + x], lo, hi, factor);
     }
     __syncthreads();
-    // L1 magnitude, halo 1; outside the image the magnitude is 0
-    for (int i = threadIdx.x; i < (TH + 2) * (TW + 2); i += kThreads) {
-        const int r = i / (TW + 2), c = i - r * (TW + 2);
-        const int y = y0 + r - 1, x = x0 + c - 1;
-        int m = 0;
-        if (y >= 0 && y < H && x >= 0 && x < W) {
-            const int a = q[r][c], b = q[r][c + 1], cc = q[r][c + 2];
-            const int d = q[r + 1][c], f = q[r + 1][c + 2];
-            const int g = q[r + 2][c], h = q[r + 2][c + 1], k = q[r + 2][c + 2];
-            const int dx = (cc + 2 * f + k) - (a + 2 * d + g);
-            const int dy = (g + 2 * h + k) - (a + 2 * b + cc);
-            m = abs(dx) + abs(dy);
+    // B: mag[r][c] = pixel (y0 + r - 1, x0 + c - 2); groups of 4 columns c = 4k .. 4k+3 cover columns 0 .. TW + 3
+    for (int i = threadIdx.x; i < (TH + 2) * (MS / 4); i += kThreads) {
+        const int r = i / (MS / 4), c = (i - r * (MS / 4)) * 4;
+        // q columns c+1 .. c+6 around the four centres c+2 .. c+5 (q column = mag column + 2), rows r .. r+2
+        int V[6], D[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const int a = q[r][c + 1 + k], m = q[r + 1][c + 1 + k], b = q[r + 2][c + 1 + k];
+            V[k] = a + 2 * m + b;   // vertical [1 2 1] column sum
+            D[k] = b - a;           // vertical difference
         }
-        mag[r][c] = (unsigned short)m;
+        unsigned short out[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int dx = V[k + 2] - V[k];
+            const int dy = D[k] + 2 * D[k + 1] + D[k + 2];
+            const int y = y0 + r - 1, x = x0 + c + k - 2;
+            int v = 0;
+            if (y >= 0 && y < H && x >= 0 && x < W) {  // outside the image the magnitude is 0
+                const int ax = abs(dx), ay = abs(dy) << 15;
+                const int tg22x = ax * TG22, tg67x = tg22x + (ax << 16);
+                const int sector = ay < tg22x ? 0 : (ay > tg67x ? 1 : (((dx ^ dy) < 0) ? 3 : 2));
+                v = (ax + abs(dy)) | (sector << 11);
+            }
+            out[k] = (unsigned short)v;
+        }
+        *reinterpret_cast<uint2 *>(&mag[r][c]) = make_uint2(out[0] | ((unsigned)out[1] << 16), out[2] | ((unsigned)out[3] << 16));
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < TH * TW; i += kThreads) {
-        const int r = i / TW, c = i - r * TW;
+    // C: four output pixels per thread and step; tile pixel (r, c) is mag[r + 1][c + 2]
+    const bool vec = (W % 4) == 0 && ((reinterpret_cast<uintptr_t>(cl) | reinterpret_cast<uintptr_t>(E)) & 3) == 0;
+    for (int i = threadIdx.x; i < TH * (TW / 4); i += kThreads) {
+        const int r = i / (TW / 4), c = (i - r * (TW / 4)) * 4;
         const int y = y0 + r, x = x0 + c;
         if (y >= H || x >= W) continue;
-        const int a = q[r + 1][c + 1], b = q[r + 1][c + 2], cc = q[r + 1][c + 3];
-        const int d = q[r + 2][c + 1], f = q[r + 2][c + 3];
-        const int g = q[r + 3][c + 1], h = q[r + 3][c + 2], k = q[r + 3][c + 3];
-        const int dx = (cc + 2 * f + k) - (a + 2 * d + g);
-        const int dy = (g + 2 * h + k) - (a + 2 * b + cc);
-        const int m = mag[r + 1][c + 1];
-        const int ax = abs(dx), ay = abs(dy) << 15;
-        const int tg22x = ax * TG22;
-        const int tg67x = tg22x + (ax << 16);
-        bool keep;
-        if (ay < tg22x) {
-            keep = m > mag[r + 1][c] && m >= mag[r + 1][c + 2];
-        } else if (ay > tg67x) {
-            keep = m > mag[r][c + 1] && m >= mag[r + 2][c + 1];
-        } else {
-            const int s = ((dx ^ dy) < 0) ? -1 : 1;
-            keep = m > mag[r][c + 1 - s] && m > mag[r + 2][c + 1 + s];
-        }
-        const int v = keep ? m : 0;
-        int first_c = kNever, first_s = kNever;
-        for (int t = thr.n - 1; t >= 0; t--) {  // nested pairs: the last hit going down is the first index
-            if (v > thr.low[t]) first_c = t;
-            if (v > thr.high[t]) first_s = t;
+        unsigned oc = 0, os = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned short *ctr = &mag[r + 1][c + 2 + k];
+            const int pv = *ctr, m = pv & 0x7FF, sector = pv >> 11;
+            // neighbour offsets in u16 elements: horizontal (-1, +1), vertical (-MS, +MS), diagonals (-MS - s, +MS + s)
+            const int off = sector == 0 ? 1 : (sector == 1 ? MS : (sector == 2 ? MS + 1 : MS - 1));
+            const int n1 = ctr[-off] & 0x7FF, n2 = ctr[off] & 0x7FF;
+            const bool keep = m > n1 && (sector >= 2 ? m > n2 : m >= n2);
+            const unsigned e = lut[keep ? m : 0];
+            oc |= (e & 0xFFu) << (8 * k);
+            os |= (e >> 8) << (8 * k);
         }
         const size_t o = (size_t)img * H * W + (size_t)y * W + x;
-        cl[o] = (unsigned char)first_c;
-        E[o] = (unsigned char)first_s;
+        if (vec) {
+            *reinterpret_cast<unsigned *>(cl + o) = oc;
+            *reinterpret_cast<unsigned *>(E + o) = os;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (x + k < W) { cl[o + k] = (unsigned char)(oc >> (8 * k)); E[o + k] = (unsigned char)(os >> (8 * k)); }
+        }
     }
 }
 
@@ -498,7 +535,7 @@ __global__ void canny_expand_kernel(const unsigned char *__restrict__ E, unsigne
 }
 
 struct Layout {
-    size_t offCl, offE, offActive, total;
+    size_t offCl, offE, offActive, offLut, total;
     int nTiles, tilesX, tilesY;
 };
 
@@ -512,6 +549,7 @@ static Layout layout(int N, int H, int W) {
     L.offCl = off; off += plane;
     L.offE = off; off += plane;
     L.offActive = off; off += hysteresis_scratch_bytes(N, H, W);
+    L.offLut = off; off += align_up((kMaxMag + 1) * sizeof(unsigned short), 256);
     L.total = off;
     return L;
 }
@@ -578,15 +616,17 @@ static int run_pairs(const void *depth, int dtype, int N, int H, int W, double m
     const int grid1 = L.nTiles;
     const double factor = 255.0 / max_depth;
 
+    unsigned short *lut = reinterpret_cast<unsigned short *>(ws + L.offLut);
+    canny_lut_kernel<<<ceil_div(kMaxMag + 1, kThreads), kThreads, 0, st>>>(thr, lut);
     if (dtype == MTE_F32)
         canny_nms_kernel<float><<<grid1, kThreads, 0, st>>>(static_cast<const float *>(depth), N, H, W, (float)min_depth,
-                                                           (float)max_depth, (float)factor, thr, cl, E);
+                                                           (float)max_depth, (float)factor, lut, cl, E);
     else if (dtype == MTE_F64)
         canny_nms_kernel<double><<<grid1, kThreads, 0, st>>>(static_cast<const double *>(depth), N, H, W, min_depth,
-                                                            max_depth, factor, thr, cl, E);
+                                                            max_depth, factor, lut, cl, E);
     else
         canny_nms_kernel<unsigned char><<<grid1, kThreads, 0, st>>>(static_cast<const unsigned char *>(depth), N, H, W,
-                                                                   0, 0, 0, thr, cl, E);
+                                                                   0, 0, 0, lut, cl, E);
     MTE_RETURN_IF_CUDA_ERROR();
 
     int rc = run_level_hysteresis(cl, E, N, H, W, thr.n, ws + L.offActive, st);
