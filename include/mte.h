@@ -98,6 +98,25 @@ int mte_edge_loss_bwd(const mte_loss_scale_t *scales_host, int n_scales, const m
                       const float *grad_loss, const void *ctx, void *workspace, size_t workspace_bytes,
                       mte_stream_t stream);
 
+/* Alternative loss types of GradLoss.forward (grad_loss.py:143-156; attention_loss2,
+ * losses/attention_loss.py:21-49), single scale, prediction already at the target
+ * size.  They build on the fused forward's side outputs: grad_map (the |directional
+ * response|, or the map itself when !is_grad) and stash.  loss_types is a bit set;
+ * MTE_LOSS_DICE is added to a base type (alone it is an error, as in the reference);
+ * with MTE_LOSS_CE, ce_loss points at loss_out[0] of mte_edge_loss_fwd (same weight)
+ * and the caller runs mte_edge_loss_bwd first, then this backward with accumulate=1.
+ * loss_out: device float[2] (both = weight * loss); ctx: device float[4]. */
+enum { MTE_LOSS_CE = 1, MTE_LOSS_ATTENTION = 2, MTE_LOSS_SPATIAL = 4, MTE_LOSS_DICE = 8 };
+size_t mte_edge_loss_alt_workspace_bytes(int B, int H, int W);
+int mte_edge_loss_alt_fwd(const float *grad_map, const float *edge, const float *mask, int B, int H, int W,
+                          int loss_types, int is_sigmoid, float sigmoid_thresh, float weight, const float *ce_loss,
+                          float *loss_out, float *ctx, void *workspace, size_t workspace_bytes, mte_stream_t stream);
+int mte_edge_loss_alt_bwd(const float *grad_map, const float *edge, const float *mask, const uint8_t *stash,
+                          const float *pred, int B, int H, int W, int loss_types, int is_grad, int is_sigmoid,
+                          int pred_is_inverse, float sigmoid_thresh, float weight, const float *grad_loss,
+                          const float *ctx, float *grad_pred, int accumulate, void *workspace,
+                          size_t workspace_bytes, mte_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * (2a) Depth -> edges for evaluation.
  * Replaces the array part of edge_from_depth (edge.py:81-88, twin

@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("MTE_LIB", os.path.join(_HERE, "libmte.so"))  # MTE_LI
 MTE_MAX_SCALES = 4
 MTE_WS_HEADER_BYTES = 65536
 MTE_F32, MTE_F64, MTE_U8 = 0, 1, 2
+MTE_LOSS_CE, MTE_LOSS_ATTENTION, MTE_LOSS_SPATIAL, MTE_LOSS_DICE = 1, 2, 4, 8
 
 
 class MteError(RuntimeError):
@@ -57,6 +58,10 @@ _SIGNATURES = {
     "mte_correspond_pixels": (_i, [_vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mte_thin_workspace_bytes": (_sz, [_i, _i, _i]),
     "mte_binary_thin": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "mte_edge_loss_alt_workspace_bytes": (_sz, [_i, _i, _i]),
+    "mte_edge_loss_alt_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mte_edge_loss_alt_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, C.c_float, C.c_float, _vp, _vp,
+                                   _vp, _i, _vp, _sz, _vp]),
     "mte_chamfer_workspace_bytes": (_sz, [_i, _i, _i]),
     "mte_chamfer_counts": (_i, [_vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _sz, _vp]),
 }

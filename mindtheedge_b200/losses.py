@@ -190,20 +190,97 @@ def edge_loss(output, gt_edge, gt_mask=None, is_grad=True, is_sigmoid=True, sigm
     return total, maps[0]
 
 
+def _loss_types(edge_loss_type: str) -> int:
+    """Bit set of the substrings GradLoss.forward looks for (grad_loss.py:140-156); a later base type overrides an
+    earlier one exactly as the chain of ``if`` statements does."""
+    t = 0
+    if "cross_entropy" in edge_loss_type:
+        t = _lib.MTE_LOSS_CE
+    if "attention_loss" in edge_loss_type:
+        t = _lib.MTE_LOSS_ATTENTION
+    if "spatially_adaptive" in edge_loss_type:
+        t = _lib.MTE_LOSS_SPATIAL
+    if t == 0:
+        raise ValueError(f"edge_loss_type={edge_loss_type!r} names no base loss (cross_entropy / attention_loss / "
+                         "spatially_adaptive); the reference raises NameError at the first call")
+    if "dice" in edge_loss_type:
+        t |= _lib.MTE_LOSS_DICE
+    return t
+
+
+class _AltEdgeLossFn(torch.autograd.Function):
+    """attention_loss / spatially_adaptive / +dice (grad_loss.py:143-156): the fused forward supplies the grad map and
+    the stash, ``mte_edge_loss_alt_fwd/bwd`` the type-specific sums and gradients."""
+
+    @staticmethod
+    def forward(ctx, cfg, pred):
+        edge, normal, mask, types, flags = cfg
+        is_grad, is_sigmoid, _inv, thresh, weight, p2n = flags
+        losses, saved, grad_maps, stash = torch.ops.mte.edge_loss_fwd([pred], [edge], normal, mask, [1.0], *flags)
+        B, _, H, W = edge.shape
+        dev = pred.device
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        actx = torch.empty(4, dtype=torch.float32, device=dev)
+        ws = runtime.workspace(dev, _lib.lib.mte_edge_loss_alt_workspace_bytes(B, H, W))
+        _lib.check(_lib.lib.mte_edge_loss_alt_fwd(
+            grad_maps[0].data_ptr(), edge.data_ptr(), mask[0].data_ptr() if mask else None, B, H, W, types,
+            int(is_sigmoid), thresh, weight, losses.data_ptr() if types & _lib.MTE_LOSS_CE else None, out.data_ptr(),
+            actx.data_ptr(), ws.data_ptr(), ws.numel(), runtime.current_stream_ptr(dev)), "mte_edge_loss_alt_fwd")
+        ctx.cfg = cfg
+        ctx.has_stash = len(stash) > 0
+        ctx.save_for_backward(pred, saved, actx, grad_maps[0], *stash)
+        ctx.mark_non_differentiable(grad_maps[0])
+        return out[0], grad_maps[0]
+
+    @staticmethod
+    def backward(ctx, grad_loss, _unused):
+        edge, normal, mask, types, flags = ctx.cfg
+        is_grad, is_sigmoid, _inv, thresh, weight, p2n = flags
+        pred, saved, actx, gmap, *stash = ctx.saved_tensors
+        B, _, H, W = edge.shape
+        dev = pred.device
+        gl = torch.zeros(2, dtype=torch.float32, device=dev)
+        gl[0] = grad_loss
+        accumulate = 0
+        if types & _lib.MTE_LOSS_CE:  # cross-entropy part through the fused backward, the rest is added to it
+            grad = torch.ops.mte.edge_loss_bwd(gl, saved, [pred], [edge], normal, mask, [gmap] if stash else [],
+                                               list(stash), [1.0], *flags)[0]
+            accumulate = 1
+        else:
+            grad = torch.empty_like(pred)
+        ws = runtime.workspace(dev, _lib.lib.mte_edge_loss_alt_workspace_bytes(B, H, W))
+        _lib.check(_lib.lib.mte_edge_loss_alt_bwd(
+            gmap.data_ptr(), edge.data_ptr(), mask[0].data_ptr() if mask else None,
+            stash[0].data_ptr() if stash else None, pred.data_ptr(), B, H, W, types, int(is_grad), int(is_sigmoid), 0,
+            thresh, weight, gl.data_ptr(), actx.data_ptr(), grad.data_ptr(), accumulate, ws.data_ptr(), ws.numel(),
+            runtime.current_stream_ptr(dev)), "mte_edge_loss_alt_bwd")
+        return None, grad
+
+
+def _alt_edge_loss(types, output, gt_edge, gt_mask, is_grad, is_sigmoid, sigmoid_thresh, gt_normals, weight, pos_to_neg):
+    pred = _prep(output, "prediction")
+    edge = _prep(gt_edge, "gt_edge")
+    if pred.shape != edge.shape:
+        raise NotImplementedError("the attention / dice loss types need the prediction at the target size")
+    if is_grad and gt_normals is None:
+        raise NotImplementedError("the attention / dice loss types need gt_normals when is_grad (directional path)")
+    normal = [_prep(gt_normals, "gt_normals")] if (gt_normals is not None and is_grad) else []
+    mask = [_prep(gt_mask, "gt_mask")] if gt_mask is not None else []
+    flags = (bool(is_grad), bool(is_sigmoid), False, float(sigmoid_thresh), float(weight), float(pos_to_neg))
+    return _AltEdgeLossFn.apply((edge, normal, mask, int(types), flags), pred)
+
+
 class GradLoss(nn.Module):
     """Same constructor and call signature as the reference ``GradLoss``
-    (``losses/grad_loss.py:97-122``).  ``edge_loss_type`` must contain
-    ``cross_entropy`` (the shipped configuration,
-    ``configs/train_packnet_san_kitti_with_edges.yaml:59-68``)."""
+    (``losses/grad_loss.py:97-122``).  ``cross_entropy`` (the shipped configuration,
+    ``configs/train_packnet_san_kitti_with_edges.yaml:59-68``) runs entirely in the fused streaming kernels;
+    ``attention_loss`` / ``spatially_adaptive`` / ``+dice`` (grad_loss.py:143-156) reuse their grad map and stash and
+    add pointwise kernels (single scale, prediction at the target size)."""
 
     def __init__(self, edge_loss_type, use_external_edges_for_loss=True, edge_loss_class_list_to_mask_out=[],
                  depth_edges_loss_weight=1.0, depth_edges_loss_pos_to_neg_weight=1.0):
         super().__init__()
-        if "cross_entropy" not in edge_loss_type or "dice" in edge_loss_type or \
-                "attention_loss" in edge_loss_type or "spatially_adaptive" in edge_loss_type:
-            raise NotImplementedError(
-                f"edge_loss_type={edge_loss_type!r}: only 'cross_entropy' runs on the sm_100a path "
-                "(the attention/dice variants are listed under SURVEY.md 8(f))")
+        self.loss_types = _loss_types(edge_loss_type)
         self.weight = depth_edges_loss_weight
         self.depth_edges_loss_pos_to_neg_weight = depth_edges_loss_pos_to_neg_weight
         self.edge_loss_type = edge_loss_type
@@ -213,5 +290,8 @@ class GradLoss(nn.Module):
 
     def forward(self, output, gt_edge, gt_mask=None, is_grad=True, is_sigmoid=True, sigmoid_thresh=4,
                 gt_normals=None):
+        if self.loss_types != _lib.MTE_LOSS_CE:
+            return _alt_edge_loss(self.loss_types, output, gt_edge, gt_mask, is_grad, is_sigmoid, sigmoid_thresh,
+                                  gt_normals, self.weight, self.depth_edges_loss_pos_to_neg_weight)
         return edge_loss(output, gt_edge, gt_mask, is_grad, is_sigmoid, sigmoid_thresh, gt_normals,
                          weight=self.weight, pos_to_neg=self.depth_edges_loss_pos_to_neg_weight)

@@ -76,6 +76,26 @@ def direction_index_torch(theta: torch.Tensor) -> torch.Tensor:
     return d
 
 
+def attention_loss2(output, target, mask=None, is_spatially_adaptive=False):
+    """losses/attention_loss.py:21-49."""
+    eps = 1e-14
+    if not is_spatially_adaptive:
+        num_pos = torch.sum(target == 1).float()
+        num_neg = torch.sum(target == 0).float()
+        alpha = num_neg / (num_pos + num_neg)
+    else:
+        box = torch.ones(1, 1, 15, 15, dtype=target.dtype, device=target.device)
+        pos = F.conv2d(target, box, padding=7) / 225
+        alpha = 1 - pos
+        alpha = torch.where(alpha >= (1.0 - eps), torch.full_like(alpha, 0.5), alpha)
+    p_clip = torch.clamp(output, min=eps, max=1.0 - eps)
+    w = target * alpha * (4 ** ((1.0 - p_clip) ** 0.5)) + (1.0 - target) * (1.0 - alpha) * (4 ** (p_clip ** 0.5))
+    w = w.detach()
+    if mask is not None:
+        w = w * mask
+    return torch.mean(F.binary_cross_entropy(output, target, w, reduction="none"))
+
+
 def edge_loss_torch(
     output: torch.Tensor,
     gt_edge: torch.Tensor,
@@ -87,11 +107,14 @@ def edge_loss_torch(
     *,
     weight: float = 1.0,
     pos_to_neg: float = 1.0,
+    edge_loss_type: str = "cross_entropy",
 ):
-    """``GradLoss('cross_entropy').forward`` on CPU (or any device) tensors -> (loss, grad_map).
+    """``GradLoss(edge_loss_type).forward`` on CPU (or any device) tensors -> (loss, grad_map).
 
     ``output`` may require grad; ``loss.backward()`` then gives the reference
-    gradient through plain autograd.
+    gradient through plain autograd.  Besides ``cross_entropy`` the type string may
+    name ``attention_loss`` / ``spatially_adaptive`` (losses/attention_loss.py:21-49)
+    and ``dice`` (grad_loss.py:150-156), combined as the reference's chain of ``if``s does.
     """
     H, W = gt_edge.shape[-2:]
     x = F.interpolate(output, size=(H, W), mode="bilinear")  # grad_loss.py:127
@@ -107,6 +130,19 @@ def edge_loss_torch(
     p = torch.sigmoid(g - sigmoid_thresh) if is_sigmoid else g
 
     e = gt_edge
+    if edge_loss_type != "cross_entropy":
+        base = None
+        if "cross_entropy" in edge_loss_type:
+            base = edge_loss_torch(output, gt_edge, gt_mask, is_grad, is_sigmoid, sigmoid_thresh, gt_normals,
+                                   weight=1.0, pos_to_neg=pos_to_neg)[0]
+        if "attention_loss" in edge_loss_type:
+            base = attention_loss2(p, e, gt_mask, False)
+        if "spatially_adaptive" in edge_loss_type:
+            base = attention_loss2(p, e, gt_mask, True)
+        if "dice" in edge_loss_type:  # grad_loss.py:150-156
+            base = base + 1000 * ((torch.sum(p ** 2) + torch.sum(e ** 2) + 0.0001) /
+                                  (2 * torch.sum(p * e) + 0.0001)) / e.numel()
+        return weight * base.mean(), g.detach()
     m = torch.ones_like(e) if gt_mask is None else gt_mask
     pos = -e * torch.log(p + EPS)
     neg = -(1 - e) * torch.log(1 - p + EPS)

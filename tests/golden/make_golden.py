@@ -107,6 +107,45 @@ def gen_edge_loss():
     print("edge_loss:", list(cases))
 
 
+def gen_edge_loss_alt():
+    """attention_loss / spatially_adaptive / +dice through the UNMODIFIED GradLoss.forward (grad_loss.py:143-156)."""
+    GradLoss = load_gradloss()
+    cases = {}
+
+    def run(name, ltype, depth, edge, mask, normal, is_grad=True, is_sigmoid=True, thresh=4, weight=10.0):
+        head = GradLoss(ltype, True, [], weight, 1.0)
+        x = depth.clone().requires_grad_(True)
+        loss, gmap = head(x, edge, mask, is_grad, is_sigmoid, thresh, normal)
+        loss.backward()
+        cases[name] = dict(
+            depth=depth.numpy(), edge=edge.numpy(), ltype=np.array(ltype),
+            mask=np.zeros(0, np.float32) if mask is None else mask.numpy(),
+            normal=np.zeros(0, np.float32) if normal is None else normal.numpy(),
+            attrs=np.array([is_grad, is_sigmoid, thresh, weight], np.float64),
+            loss=np.float32(loss.item()), grad_map=gmap.numpy(), dgrad=x.grad.numpy())
+
+    g = torch.Generator().manual_seed(321)
+    d, e, n = loss_inputs(2, 48, 64, 11)
+    e = torch.where(torch.rand(e.shape, generator=g) < 0.3, (e > 0).float(), e)   # some labels exactly 1 (num_pos)
+    m = (torch.rand(2, 1, 48, 64, generator=g) < 0.6).float()
+    run("attention", "attention_loss", d, e, None, n)
+    run("attention_mask", "attention_loss", d, e, m, n, weight=2.5, thresh=2)
+    run("spatial", "spatially_adaptive", d, e, None, n)
+    run("spatial_mask", "attention_loss_spatially_adaptive", d, e, m, n)
+    run("ce_dice", "cross_entropy_dice", d, e, None, n)
+    run("ce_dice_mask", "cross_entropy+dice", d, e, m, n, weight=3.0)
+    run("attention_dice", "attention_loss_dice", d, e, None, n)
+    prob = torch.rand(2, 1, 48, 64, generator=g) * 0.98 + 0.01
+    run("dee_attention", "attention_loss", prob, e, None, None, is_grad=False, is_sigmoid=False)
+    run("dee_spatial_dice", "spatially_adaptive_dice", prob, e, None, None, is_grad=False, is_sigmoid=False)
+    flat = {}
+    for k, c in cases.items():
+        for f, v in c.items():
+            flat[f"{k}/{f}"] = v
+    np.savez_compressed(os.path.join(HERE, "edge_loss_alt.npz"), **flat)
+    print("edge_loss_alt:", {k: float(c["loss"]) for k, c in cases.items()})
+
+
 def gen_canny():
     ref_edge = load_edge()
     out = {}
@@ -289,8 +328,13 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "chamfer":
         gen_chamfer()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "edge_loss_alt":
+        torch.manual_seed(0)
+        gen_edge_loss_alt()
+        sys.exit(0)
     torch.manual_seed(0)
     gen_edge_loss()
+    gen_edge_loss_alt()
     gen_canny()
     gen_dee()
     gen_pr()

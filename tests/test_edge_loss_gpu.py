@@ -164,3 +164,23 @@ def test_no_cpu_fallback():
     from mindtheedge_b200.losses import edge_loss
     with pytest.raises(_lib.MteError):
         edge_loss(torch.rand(1, 1, 8, 8), torch.rand(1, 1, 8, 8))
+
+
+ALT_CASES = load_cases("edge_loss_alt.npz")
+
+
+@pytest.mark.parametrize("name", sorted(ALT_CASES))
+def test_alt_loss_types_golden(name):
+    """attention_loss / spatially_adaptive / +dice (grad_loss.py:143-156) against the unmodified reference:
+    loss within 1e-5 relative, gradient and grad map within 1e-5 of their max."""
+    from mindtheedge_b200.losses import GradLoss
+    c = ALT_CASES[name]
+    is_grad, is_sigmoid, thresh, weight = c["attrs"]
+    head = GradLoss(str(c["ltype"]), True, [], float(weight), 1.0)
+    x = _t(c["depth"]).requires_grad_(True)
+    loss, gmap = head(x, _t(c["edge"]), _t(c["mask"]), bool(is_grad), bool(is_sigmoid), float(thresh), _t(c["normal"]))
+    loss.backward()
+    ref = float(c["loss"])
+    assert abs(loss.item() - ref) <= RTOL * abs(ref), (loss.item(), ref)
+    _plane_close(gmap.cpu().numpy(), c["grad_map"])
+    _plane_close(x.grad.cpu().numpy(), c["dgrad"])

@@ -66,6 +66,9 @@ def test_host_side_argument_checks_without_a_gpu():
     assert L.mte_pr_counts(256, 2, 256, 1, 8, 8, None, None, 300, 0.002, 0, 256, 256, 1 << 30, None) == -4
     assert L.mte_dee_workspace_bytes(2, 384, 1280) > 0 and L.mte_thin_workspace_bytes(2, 10, 10) > 0
     assert L.mte_dee_postprocess(None, 0, 1, 8, 8, 1, 1, 0.3, 0.7, None, None, 1, None, 0, None) == -1
+    assert L.mte_edge_loss_alt_workspace_bytes(2, 48, 64) > 2 * 2 * 48 * 64 * 4
+    assert L.mte_edge_loss_alt_fwd(256, 256, None, 1, 8, 8, 8, 1, 4.0, 1.0, None, 256, 256, 256, 1 << 20, None) == -4   # dice alone
+    assert L.mte_edge_loss_alt_fwd(256, 256, None, 1, 8, 8, 1, 1, 4.0, 1.0, None, 256, 256, 256, 1 << 20, None) == -4   # CE without its loss
     assert L.mte_chamfer_workspace_bytes(3, 384, 1280) > 3 * 384 * 1280 * 2 and L.mte_chamfer_workspace_bytes(0, 4, 4) == 0
     assert L.mte_chamfer_counts(None, None, 1, 8, 8, 5.0, None, None, None, 0, None) == -1
     assert L.mte_chamfer_counts(256, 256, 1, 8, 8, 5.0, 256, None, 256, 16, None) == -3
@@ -86,8 +89,10 @@ def test_no_cpu_fallback():
         pr_counts(x[0], x[0].to(torch.uint8), [0.5])
     with pytest.raises(_lib.MteError):
         dee_postprocess(x[0, 0])
-    with pytest.raises(NotImplementedError):
-        GradLoss("attention_loss")
+    with pytest.raises(ValueError):
+        GradLoss("dice")                      # no base loss: NameError in the reference (grad_loss.py:150-156)
+    with pytest.raises(_lib.MteError):
+        GradLoss("attention_loss_dice")(x, x, None, False, False)   # CPU tensors: no fallback for any loss type
     src = open(os.path.join(ROOT, "mindtheedge_b200", "losses.py")).read() + \
         open(os.path.join(ROOT, "mindtheedge_b200", "eval_depth_edges.py")).read()
     assert "import oracle" not in src and "from oracle" not in src

@@ -160,3 +160,22 @@ def test_chamfer_oracle_vs_reference_golden():
     d = (z["metrics_depth_u16"] / 256).astype(np.float32)
     g = np.unpackbits(z["metrics_gt"])[: H * W].reshape(H, W).astype(np.float64)
     assert np.array_equal(np.array(och.compute_edge_metrics(d, g, list(z["metrics_crop"]))), z["metrics_vals"])
+
+
+ALT_CASES = load_cases("edge_loss_alt.npz")
+
+
+@pytest.mark.parametrize("name", sorted(ALT_CASES))
+def test_alt_loss_oracle_vs_reference_golden(name):
+    """attention_loss / spatially_adaptive / +dice restatement against the unmodified GradLoss.forward."""
+    from oracle.edge_loss import edge_loss_torch
+    c = ALT_CASES[name]
+    is_grad, is_sigmoid, thresh, weight = c["attrs"]
+    t = lambda a: None if a.size == 0 else torch.from_numpy(a)
+    x = torch.from_numpy(c["depth"]).requires_grad_(True)
+    loss, gmap = edge_loss_torch(x, t(c["edge"]), t(c["mask"]), bool(is_grad), bool(is_sigmoid), float(thresh),
+                                 t(c["normal"]), weight=float(weight), edge_loss_type=str(c["ltype"]))
+    loss.backward()
+    assert abs(loss.item() - float(c["loss"])) <= 1e-6 * abs(float(c["loss"]))
+    assert np.array_equal(gmap.numpy(), c["grad_map"])
+    assert np.abs(x.grad.numpy() - c["dgrad"]).max() <= 1e-6 * np.abs(c["dgrad"]).max()
