@@ -766,34 +766,86 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
         __syncthreads();
         tick(-1);
 
-        // ---- pass 1: GT bitmap (one ballot per 32 window pixels) and the stage histogram of the predicted pixels
-        for (int base = 0; base < SL.nW * 32; base += 8 * kSwThreads) {
-            int stg[8];
-            bool isQ[8];
+        // ---- ONE pass over the window: GT bitmap (atomicOr per GT pixel), stage histogram, and the predicted pixels
+        //      appended unsorted as pixel | stage << 24 to a temporary list that borrows the mateP + claimP storage.
+        //      Level planes are read as 32-bit words (4 pixels) when the layout allows it.
+        unsigned *tmpList = reinterpret_cast<unsigned *>(mateP);  // capP entries (mateP and claimP are adjacent)
+        for (int i = threadIdx.x; i < SL.nW; i += kSwThreads) qbits[i] = 0u;
+        if (threadIdx.x == 0) sNP = 0;
+        __syncthreads();
+        auto emit = [&](int i, int stg, bool isQ) {  // window pixel i
+            if (isQ) atomicOr(&qbits[i >> 5], 1u << (i & 31));
+            if (stg < T) {
+                atomicAdd(&sStage[stg], 1);
+                const int slot = atomicAdd(&sNP, 1);
+                if (slot < SL.capP) tmpList[slot] = (unsigned)i | ((unsigned)stg << 24);
+            }
+        };
+        const unsigned char *lv = (const unsigned char *)P.pred + (size_t)img * P.H * P.W;
+        const bool words = levels && (P.W % 4) == 0 && ((reinterpret_cast<uintptr_t>(lv) | reinterpret_cast<uintptr_t>(gt)) & 3) == 0;
+        if (words) {
+            const int xa = P.x0 & ~3;                          // first word column
+            const int cpr = (P.x0 + w - xa + 3) >> 2;          // words per window row
+            const int nChunks = cpr * h;
+            for (int base = 0; base < nChunks; base += 4 * kSwThreads) {
+                unsigned lw[4], gw[4];
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int i = base + u * kSwThreads + threadIdx.x;
-                stg[u] = T; isQ[u] = false;
-                if (i < hw) {
-                    const int y = i / w, x = i - y * w;
-                    stg[u] = stage_of(img, P.y0 + y, P.x0 + x);
-                    isQ[u] = gt[(size_t)(P.y0 + y) * P.W + P.x0 + x] != 0;
+                for (int u = 0; u < 4; u++) {
+                    const int c = base + u * kSwThreads + threadIdx.x;
+                    lw[u] = 0xFFFFFFFFu; gw[u] = 0u;
+                    if (c < nChunks) {
+                        const int y = c / cpr, cx = xa + 4 * (c - y * cpr);
+                        const size_t o = (size_t)(P.y0 + y) * P.W + cx;
+                        lw[u] = *reinterpret_cast<const unsigned *>(lv + o);
+                        gw[u] = *reinterpret_cast<const unsigned *>(gt + o);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int c = base + u * kSwThreads + threadIdx.x;
+                    if (c >= nChunks) continue;
+                    const int y = c / cpr, cx = xa + 4 * (c - y * cpr);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int x = cx + k - P.x0;
+                        if (x < 0 || x >= w) continue;
+                        const int L = (lw[u] >> (8 * k)) & 0xFF;
+                        const bool isQ = ((gw[u] >> (8 * k)) & 0xFF) != 0;
+                        if (L < T || isQ) emit(y * w + x, L < T ? L : T, isQ);
+                    }
                 }
             }
+        } else {
+            for (int base = 0; base < hw; base += 4 * kSwThreads) {
+                int stg[4];
+                bool isQ[4];
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int i = base + u * kSwThreads + threadIdx.x;
-                if (base + u * kSwThreads >= SL.nW * 32) break;  // warp-uniform
-                const unsigned mq = __ballot_sync(MTE_FULL_MASK, isQ[u]);
-                if (lane == 0) {
-                    qbits[i >> 5] = mq;
-                    if (mq) atomicAdd(&sNQ, __popc(mq));
+                for (int u = 0; u < 4; u++) {
+                    const int i = base + u * kSwThreads + threadIdx.x;
+                    stg[u] = T; isQ[u] = false;
+                    if (i < hw) {
+                        const int y = i / w, x = i - y * w;
+                        stg[u] = stage_of(img, P.y0 + y, P.x0 + x);
+                        isQ[u] = gt[(size_t)(P.y0 + y) * P.W + P.x0 + x] != 0;
+                    }
                 }
-                if (stg[u] < T) atomicAdd(&sStage[stg[u]], 1);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = base + u * kSwThreads + threadIdx.x;
+                    if (i < hw && (stg[u] < T || isQ[u])) emit(i, stg[u], isQ[u]);
+                }
             }
         }
         __syncthreads();
+        {  // number of GT pixels = population of the bitmap
+            int c = 0;
+            for (int i = threadIdx.x; i < SL.nW; i += kSwThreads) c += __popc(qbits[i]);
+            c = __reduce_add_sync(MTE_FULL_MASK, c);
+            if (lane == 0 && c) atomicAdd(&sNQ, c);
+        }
+        __syncthreads();
         const int nQ = sNQ;
+        const int nPall = sNP;
         // stage offsets (T <= 254: one warp scans them)
         if (warp == 0) {
             int run = 0;
@@ -806,10 +858,8 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                 if (k < T) { sStage[k] = run + incl - c; sCursor[k] = run + incl - c; }
                 run += __shfl_sync(MTE_FULL_MASK, incl, 31);
             }
-            if (lane == 0) { sStage[T] = run; sNP = run; }
+            if (lane == 0) sStage[T] = run;
         }
-        __syncthreads();
-        const int nPall = sNP;
         if (nPall > SL.capP || nQ > SL.capQ || nQ >= 0xFFF0 || nPall >= 0xFFF0) {  // does not fit: per-problem kernels
             if (threadIdx.x == 0) {
                 const int at = (int)atomicAdd(P.overflowCount, (unsigned)T);
@@ -818,27 +868,14 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
             __syncthreads();
             continue;
         }
-        // ---- pass 2: predicted pixels grouped by stage (order inside a stage is arbitrary: counts do not depend on it)
-        for (int base = 0; base < hw; base += 8 * kSwThreads) {
-            int stg[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int i = base + u * kSwThreads + threadIdx.x;
-                stg[u] = T;
-                if (i < hw) {
-                    const int y = i / w, x = i - y * w;
-                    stg[u] = stage_of(img, P.y0 + y, P.x0 + x);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int i = base + u * kSwThreads + threadIdx.x;
-                if (stg[u] < T) {
-                    const int slot = atomicAdd(&sCursor[stg[u]], 1);
-                    ppix[slot] = (unsigned)i; mateP[slot] = kFree; claimP[slot] = 0;
-                }
-            }
+        __syncthreads();
+        // ---- predicted pixels grouped by stage (order inside a stage is arbitrary: counts do not depend on it)
+        for (int k = threadIdx.x; k < nPall; k += kSwThreads) {
+            const unsigned v = tmpList[k];
+            ppix[atomicAdd(&sCursor[v >> 24], 1)] = v & 0xFFFFFFu;
         }
+        __syncthreads();
+        for (int k = threadIdx.x; k < nPall; k += kSwThreads) { mateP[k] = kFree; claimP[k] = 0; }
         // ---- rank: exclusive prefix popcount over pairs of bitmap words
         {
             const int nW2 = (SL.nW + 1) >> 1;
