@@ -176,7 +176,7 @@ struct UfP {
     int *todo;            // [N] written by the shared-memory kernel: 1 = image left to the L2 kernel (nullptr = all)
     int cap;              // shared-memory kernel: candidate capacity
     unsigned long long *prof;  // optional per-section cycle counters (MTE_HYST_PROF)
-    unsigned oRank, oParent, oFlag, oEc;  // shared-memory kernel: byte offsets of its arrays behind the bitmap
+    unsigned oRank, oParent, oFlag, oEc, oWork;  // shared-memory kernel: byte offsets of its arrays behind the bitmap
 };
 
 // find with path halving (every visited node is re-pointed to its grandparent; lock-free safe: a node only
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_kernel(const UfP P) 
 // live in a compact global array in list order (coalesced) and are scattered to the plane at the end.  Images with
 // more candidates than fit (or planes whose bitmap does not fit) are left to the L2 kernel through P.todo.
 // ---------------------------------------------------------------------------
-constexpr unsigned short kNoCand = 0xFFFF;
+constexpr int kWorkCap = 4096;  // changed-word worklist entries of the flood (beyond that: one full sweep)
 
 __device__ __forceinline__ int ufs_find(volatile unsigned short *parent, int x) {
     int p = parent[x];
@@ -339,7 +339,7 @@ __device__ __forceinline__ int ufs_find(volatile unsigned short *parent, int x) 
 __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const UfP P) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ int sHist[256], sEnd[256], sScan[kUfThreads];
-    __shared__ int sMerged;
+    __shared__ int sCntA, sCntB, sFull;
     const int img = blockIdx.x;
     const int H = P.H, W = P.W, HW = H * W, T = P.T;
     const int nW = (HW + 31) >> 5, nW2 = (nW + 1) >> 1;
@@ -368,24 +368,97 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
     };
     for (int i = threadIdx.x; i < 256; i += kUfThreads) sHist[i] = 0;
     __syncthreads();
-    const bool vec = (HW % 16) == 0 && (reinterpret_cast<uintptr_t>(cl) & 15) == 0;
-    // ---- pass 1: candidate bitmap + histogram of first-candidate levels
+    const bool vec = (HW % 16) == 0 && (reinterpret_cast<uintptr_t>(cl) & 15) == 0 && (reinterpret_cast<uintptr_t>(E) & 15) == 0;
+    // ---- pass 1: bitmaps of the candidates (cbits) and of the pixels that are strong at some level (qbits = seed)
+    unsigned *cbits = reinterpret_cast<unsigned *>(dyn + P.oParent);   // borrowed until the flood is done
+    unsigned short *wlA = reinterpret_cast<unsigned short *>(dyn + P.oWork), *wlB = wlA + kWorkCap;
     for (int i0 = threadIdx.x * 16; i0 < nW * 32; i0 += kUfThreads * 16) {
-        unsigned char v[16];
-        if (i0 < HW) load16(v, cl, i0, HW, vec);
+        unsigned char v[16], sv[16];
+        if (i0 < HW) { load16(v, cl, i0, HW, vec); load16(sv, E, i0, HW, vec); }
         else {
 #pragma unroll
-            for (int k = 0; k < 16; k++) v[k] = (unsigned char)kNever;
+            for (int k = 0; k < 16; k++) { v[k] = (unsigned char)kNever; sv[k] = (unsigned char)kNever; }
         }
-        unsigned half = 0;
+        unsigned half = 0, shalf = 0;
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             half |= (v[k] != kNever ? 1u : 0u) << k;
-            const unsigned grp = __match_any_sync(__activemask(), (int)v[k]);
-            if (v[k] != kNever && (int)(__ffs(grp) - 1) == lane) atomicAdd(&sHist[v[k]], __popc(grp));
+            shalf |= (sv[k] != kNever ? 1u : 0u) << k;
         }
-        const unsigned hi = __shfl_down_sync(__activemask(), half, 1);
-        if (!(lane & 1)) qbits[i0 >> 5] = half | (hi << 16);
+        const unsigned hi = __shfl_down_sync(__activemask(), half, 1), shi = __shfl_down_sync(__activemask(), shalf, 1);
+        if (!(lane & 1)) { cbits[i0 >> 5] = half | (hi << 16); qbits[i0 >> 5] = (shalf | (shi << 16)) & (half | (hi << 16)); }
+    }
+    if (threadIdx.x == 0) { sCntA = 0; sCntB = 0; sFull = 0; }
+    __syncthreads();
+    // ---- flood: only candidates connected to a strong pixel can ever become edges (the edge sets of the pairs are
+    //      nested), and on noisy depth they are a fraction of the candidates (~6 k of ~30 k per KITTI image), so the
+    //      union-find below runs on that reachable set R only.  R grows from the strong pixels by bit-parallel
+    //      dilation restricted to the candidates: inside a word a Kogge-Stone occluded fill runs along the whole
+    //      horizontal run at once; a worklist of changed words keeps an iteration proportional to the frontier.
+    const int WPR = W >> 5;  // words per image row (the host only takes this kernel when W % 32 == 0)
+    auto hfill = [](unsigned seed, unsigned c) -> unsigned {
+        unsigned f = seed & c, m = c;
+        f |= m & (f << 1); m &= m << 1; f |= m & (f << 2); m &= m << 2; f |= m & (f << 4); m &= m << 4;
+        f |= m & (f << 8); m &= m << 8; f |= m & (f << 16);
+        m = c;
+        f |= m & (f >> 1); m &= m >> 1; f |= m & (f >> 2); m &= m >> 2; f |= m & (f >> 4); m &= m >> 4;
+        f |= m & (f >> 8); m &= m >> 8; f |= m & (f >> 16);
+        return f;
+    };
+    for (int i = threadIdx.x; i < nW; i += kUfThreads)
+        if (qbits[i]) { const int s = atomicAdd(&sCntA, 1); if (s < kWorkCap) wlA[s] = (unsigned short)i; else sFull = 1; }
+    __syncthreads();
+    for (int iter = 0;; iter++) {
+        const int nA = min(sCntA, kWorkCap);
+        const bool full = sFull != 0;
+        if (nA == 0 && !full) break;
+        __syncthreads();
+        if (threadIdx.x == 0) { sCntA = 0; sFull = 0; }
+        __syncthreads();
+        // (sCntB counts the next worklist; the lists swap roles every iteration)
+        const int nSrc = full ? nW : nA;
+        for (int k = threadIdx.x; k < nSrc; k += kUfThreads) {
+            const int wi = full ? k : (int)wlA[k];
+            const unsigned v = ((volatile unsigned *)qbits)[wi];
+            if (!v) continue;
+            const int r = wi / WPR, c = wi - r * WPR;
+            const unsigned h3 = v | (v << 1) | (v >> 1);
+#pragma unroll
+            for (int dr = -1; dr <= 1; dr++) {
+                const int rr = r + dr;
+                if (rr < 0 || rr >= H) continue;
+#pragma unroll
+                for (int dc = -1; dc <= 1; dc++) {
+                    const int cc = c + dc;
+                    if (cc < 0 || cc >= WPR) continue;
+                    const unsigned contrib = dc == 0 ? h3 : (dc < 0 ? ((v & 1u) << 31) : (v >> 31));
+                    if (!contrib) continue;
+                    const int ti = rr * WPR + cc;
+                    const unsigned cm = cbits[ti], cur = ((volatile unsigned *)qbits)[ti];
+                    if (!(contrib & cm & ~cur)) continue;
+                    const unsigned add = hfill(contrib | cur, cm) & ~cur;
+                    const unsigned old = atomicOr(&qbits[ti], add);
+                    if (add & ~old) {
+                        const int s2 = atomicAdd(&sCntB, 1);
+                        if (s2 < kWorkCap) wlB[s2] = (unsigned short)ti; else sFull = 1;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { sCntA = sCntB; sCntB = 0; }
+        unsigned short *tmp = wlA; wlA = wlB; wlB = tmp;
+        __syncthreads();
+    }
+    tick(0);
+    // ---- histogram of first-candidate levels over R (sparse: walk the set bits)
+    for (int wi = threadIdx.x; wi < nW; wi += kUfThreads) {
+        unsigned bits = qbits[wi];
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            atomicAdd(&sHist[cl[wi * 32 + b]], 1);
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -399,7 +472,6 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
     }
     __syncthreads();
     const int nCand = sEnd[254];
-    tick(0);
     if (P.prof && threadIdx.x == 0) atomicAdd(P.prof + 8, (unsigned long long)nCand);
     if (nCand > P.cap) {  // leave the image to the L2 kernel
         if (threadIdx.x == 0) P.todo[img] = 1;
@@ -430,6 +502,7 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
         int run = sScan[threadIdx.x];
         for (int k2 = w0; k2 < w1; k2++) { qrank[k2] = (unsigned short)run; run += pc2(k2); }
     }
+    // (the candidate bitmap is dead from here on: its storage becomes parent / edge level / flags)
     for (int i = threadIdx.x; i < nCand; i += kUfThreads) parent[i] = (unsigned short)i;
     for (int i = threadIdx.x; i < (nCand + 31) / 32; i += kUfThreads) flagW[i] = 0u;
     __syncthreads();
@@ -439,24 +512,18 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
         if (q & 32) r += __popc(qbits[(q >> 5) - 1]);
         return r;
     };
-    // ---- pass 2: candidates sorted by level, with their compact ids and strong levels
-    for (int i0 = threadIdx.x * 16; i0 < HW; i0 += kUfThreads * 16) {
-        unsigned char v[16];
-        load16(v, cl, i0, HW, vec);
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            const unsigned act = __activemask();
-            const unsigned grp = __match_any_sync(act, (int)v[k]);
-            const int leader = __ffs(grp) - 1;
-            int slot = 0;
-            if (v[k] != kNever && lane == leader) slot = atomicAdd(&sHist[v[k]], __popc(grp));
-            slot = __shfl_sync(act, slot, leader);
-            if (v[k] != kNever) {
-                const int at = slot + __popc(grp & ((1u << lane) - 1));
-                list[at] = i0 + k;
-                perm[qid(i0 + k)] = (unsigned short)at;
-                Ec[at] = E[i0 + k];
-            }
+    // ---- pass 2 (sparse): the pixels of R sorted by level, with their ids and strong levels
+    for (int wi = threadIdx.x; wi < nW; wi += kUfThreads) {
+        unsigned bits = qbits[wi];
+        int r = (int)qrank[wi >> 1] + ((wi & 1) ? __popc(qbits[wi - 1]) : 0);
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int px = wi * 32 + b;
+            const int at = atomicAdd(&sHist[cl[px]], 1);
+            list[at] = px;
+            perm[r++] = (unsigned short)at;
+            Ec[at] = E[px];
         }
     }
     __syncthreads();
@@ -584,17 +651,24 @@ int run_level_hysteresis(const unsigned char *cl, unsigned char *E, int N, int H
     }
     const long long HW = (long long)H * W;
     const long long nW = (HW + 31) / 32, nW2 = (nW + 1) / 2;
-    const long long fixed = align_up((size_t)nW * 4, 16) + align_up((size_t)nW2 * 2, 16) + 64;
-    long long cap = ((long long)budget - fixed) * 8 / 25;  // 2 B parent + 1 B edge level + 1 bit flag per candidate
+    // [reachable-set bitmap][rank][region X][flood worklists]; region X is the candidate bitmap during the flood,
+    // then parent (2 B) + edge level (1 B) + flag (1 bit) per pixel of the reachable set
+    const long long bitmapB = align_up((size_t)nW * 4, 16), rankB = align_up((size_t)nW2 * 2, 16);
+    const long long workB = 2 * kWorkCap * sizeof(unsigned short);
+    const long long fixed = bitmapB + rankB + workB + 64;
+    const long long regionX = (long long)budget - fixed;
+    long long cap = regionX * 8 / 25 - 64;
     if (cap > 65535) cap = 65535;
-    if (cap >= 4096 && !getenv("MTE_HYST_L2")) {
+    if (regionX >= bitmapB && cap >= 2048 && (W % 32) == 0 && nW < 65536 && !getenv("MTE_HYST_L2")) {
         cap &= ~31LL;
         P.cap = (int)cap;
-        P.oRank = (unsigned)align_up((size_t)nW * 4, 16);
-        P.oParent = P.oRank + (unsigned)align_up((size_t)nW2 * 2, 16);
+        P.oRank = (unsigned)bitmapB;
+        P.oParent = P.oRank + (unsigned)rankB;
         P.oFlag = P.oParent + (unsigned)align_up((size_t)cap * 2, 16);
         P.oEc = P.oFlag + (unsigned)align_up((size_t)cap / 8 + 4, 16);
-        const size_t smem = P.oEc + align_up((size_t)cap, 16);
+        const unsigned endX = P.oParent + (unsigned)(regionX & ~15LL);
+        P.oWork = endX;
+        const size_t smem = (size_t)endX + workB;
         P.todo = reinterpret_cast<int *>(w + 3 * align_up(px * 4, 256) + align_up(px, 256));
         canny_uf_hyst_smem_kernel<<<N, kUfThreads, smem, st>>>(P);
         MTE_RETURN_IF_CUDA_ERROR();

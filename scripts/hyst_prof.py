@@ -24,5 +24,5 @@ ws[off:off + 256].zero_()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); lv = canny_from_depth(d, pairs, want_edges=False, want_levels=True); e1.record(); torch.cuda.synchronize()
 prof = ws[off:off + 256].view(torch.int64).cpu().numpy()
-print("ms %.3f" % e0.elapsed_time(e1), "per image kcycles: pass1 %d rank+pass2 %d unite %d flags %d assign %d final %d; candidates/img %d" %
+print("ms %.3f" % e0.elapsed_time(e1), "per image kcycles: pass1+flood %d hist+rank+pass2 %d unite %d flags %d assign %d final %d; reachable candidates/img %d" %
       tuple(int(v) // n // (1000 if i < 6 else 1) for i, v in enumerate(list(prof[:6]) + [prof[8]])))
