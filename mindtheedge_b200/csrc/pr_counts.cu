@@ -993,49 +993,77 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                         }
                         my = __shfl_sync(MTE_FULL_MASK, my, 0);
                         if (my == -2) break;
-                        const int pi = my;
-                        const int root = rootP[pi];
-                        if (!(rflag_get(root) & RF_FOUND)) {
-                            const int p = (int)ppix[pi];
-                            const int py = p / w, px = p - py * w;
-                            const unsigned mine = ((unsigned)phase << 16) | (unsigned)root;
-                            for (int k = lane; k < noff; k += 32) {
-                                const short2 o = sOff[k];
-                                const int qy = py + o.y, qx = px + o.x;
-                                if (qy < 0 || qy >= h || qx < 0 || qx >= w) continue;
-                                const int q = qy * w + qx;
-                                if (!((qbits[q >> 5] >> (q & 31)) & 1u)) continue;
-                                const int qi = qid(q);
-                                unsigned st = stamp[qi];
-                                if (st == kDeadStamp) continue;
-                                if ((st >> 16) != phase) {
-                                    const unsigned old = atomicCAS(&stamp[qi], st, mine);
-                                    if (old == st) {  // claimed for this tree
-                                        parentQ[qi] = (unsigned short)pi;
-                                        const unsigned short mq = mateQ[qi];
-                                        if (mq == kFree) {
-                                            const int es = atomicAdd(&sEnds, 1);
-                                            if (es < kEndsCap) ends[es] = (unsigned short)qi;
-                                            rflag_or(root, RF_FOUND);
-                                        } else {
-                                            rootP[mq] = (unsigned short)root;
-                                            atomicAdd(&sPending, 1);
-                                            const int slot = atomicAdd(&sTail, 1);
-                                            __threadfence_block();
-                                            ((volatile unsigned short *)fa)[slot] = mq;
+                        int pi = my;
+                        for (;;) {  // a warp keeps ONE successor and goes on with it directly (chains along contours
+                                    // would otherwise pay a queue round trip per hop); the others are published
+                            const int root = rootP[pi];
+                            int keep = -1;
+                            if (!(rflag_get(root) & RF_FOUND)) {
+                                const int p = (int)ppix[pi];
+                                const int py = p / w, px = p - py * w;
+                                const unsigned mine = ((unsigned)phase << 16) | (unsigned)root;
+                                for (int k0 = 0; k0 < noff; k0 += 32) {
+                                    const int k = k0 + lane;
+                                    int succ = -1;
+                                    if (k < noff) {
+                                        const short2 o = sOff[k];
+                                        const int qy = py + o.y, qx = px + o.x;
+                                        if (qy >= 0 && qy < h && qx >= 0 && qx < w) {
+                                            const int q = qy * w + qx;
+                                            if ((qbits[q >> 5] >> (q & 31)) & 1u) {
+                                                const int qi = qid(q);
+                                                unsigned st = stamp[qi];
+                                                if (st != kDeadStamp) {
+                                                    bool claimed = false;
+                                                    if ((st >> 16) != phase) {
+                                                        const unsigned old = atomicCAS(&stamp[qi], st, mine);
+                                                        claimed = old == st;
+                                                        st = old;  // if somebody else got it first
+                                                    }
+                                                    if (claimed) {
+                                                        parentQ[qi] = (unsigned short)pi;
+                                                        const unsigned short mq = mateQ[qi];
+                                                        if (mq == kFree) {
+                                                            const int es = atomicAdd(&sEnds, 1);
+                                                            if (es < kEndsCap) ends[es] = (unsigned short)qi;
+                                                            rflag_or(root, RF_FOUND);
+                                                        } else {
+                                                            rootP[mq] = (unsigned short)root;
+                                                            succ = mq;
+                                                        }
+                                                    } else if (st != kDeadStamp && (st & 0xFFFFu) != (unsigned)root) {
+                                                        rflag_or(root, RF_BLOCKED);
+                                                    }
+                                                }
+                                            }
                                         }
-                                        continue;
                                     }
-                                    st = old;  // somebody else got it first
+                                    unsigned m = __ballot_sync(MTE_FULL_MASK, succ >= 0);
+                                    if (m && keep < 0) {
+                                        keep = __shfl_sync(MTE_FULL_MASK, succ, __ffs(m) - 1);
+                                        m &= m - 1;
+                                    }
+                                    if (m) {
+                                        int base = 0;
+                                        if (lane == 0) {
+                                            atomicAdd(&sPending, __popc(m));
+                                            base = atomicAdd(&sTail, __popc(m));
+                                        }
+                                        base = __shfl_sync(MTE_FULL_MASK, base, 0);
+                                        __threadfence_block();
+                                        if ((m >> lane) & 1u)
+                                            ((volatile unsigned short *)fa)[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)succ;
+                                    }
                                 }
-                                if (st != kDeadStamp && (st & 0xFFFFu) != (unsigned)root) rflag_or(root, RF_BLOCKED);
                             }
+                            if (P.stats && lane == 0) atomicAdd(P.stats + 2, 1u);
+                            if (keep < 0) break;
+                            pi = keep;
                         }
                         __syncwarp();
                         if (lane == 0) {
                             __threadfence_block();
                             atomicSub(&sPending, 1);
-                            if (P.stats) atomicAdd(P.stats + 2, 1u);
                         }
                     }
                     __syncthreads();
