@@ -909,39 +909,28 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
         for (int s = 0; s < T; s++) {
             const int p0 = sStage[s], p1 = sStage[s + 1];  // the pixels that join at this stage
             if (p1 > p0) {
-                // ---- greedy start: nearest free GT pixel (warp per new predicted pixel, lanes over offsets)
-                for (int pi = p0 + warp; pi < p1; pi += kSwWarps) {
+                // ---- greedy start: nearest free GT pixel, one THREAD per new predicted pixel walking the offsets nearest
+                //      first (most pixels succeed within the first few; any greedy start is a valid matching)
+                for (int pi = p0 + threadIdx.x; pi < p1; pi += kSwThreads) {
                     const int p = (int)ppix[pi];
                     const int py = p / w, px = p - py * w;
                     bool done = false, anyQ = false;
-                    for (int k0 = 0; k0 < noff && !done; k0 += 32) {
-                        const int k = k0 + lane;
-                        bool cand = false;
-                        int q = 0;
-                        if (k < noff) {
-                            const short2 o = sOff[k];
-                            const int qy = py + o.y, qx = px + o.x;
-                            if (qy >= 0 && qy < h && qx >= 0 && qx < w) {
-                                q = qy * w + qx;
-                                cand = (qbits[q >> 5] >> (q & 31)) & 1u;
-                            }
-                        }
-                        unsigned m = __ballot_sync(MTE_FULL_MASK, cand);
-                        anyQ |= m != 0;
-                        while (m && !done) {
-                            const int l = __ffs(m) - 1;
-                            m &= m - 1;
-                            int ok = 0;
-                            if (lane == l) {
-                                const int qi = qid(q);
-                                ok = cas16(&mateQ[qi], kFree, (unsigned short)pi) == kFree;
-                                if (ok) mateP[pi] = (unsigned short)qi;
-                            }
-                            done = __shfl_sync(MTE_FULL_MASK, ok, l) != 0;
+                    for (int k = 0; k < noff && !done; k++) {
+                        const short2 o = sOff[k];
+                        const int qy = py + o.y, qx = px + o.x;
+                        if (qy < 0 || qy >= h || qx < 0 || qx >= w) continue;
+                        const int q = qy * w + qx;
+                        if (!((qbits[q >> 5] >> (q & 31)) & 1u)) continue;
+                        anyQ = true;
+                        const int qi = qid(q);
+                        if (((volatile unsigned short *)mateQ)[qi] != kFree) continue;
+                        if (cas16(&mateQ[qi], kFree, (unsigned short)pi) == kFree) {
+                            mateP[pi] = (unsigned short)qi;
+                            done = true;
                         }
                     }
-                    if (done && lane == 0) atomicAdd(&sMatched, 1);
-                    if (!done && !anyQ && lane == 0) mateP[pi] = kDead;
+                    if (done) atomicAdd(&sMatched, 1);
+                    else if (!anyQ) mateP[pi] = kDead;
                 }
                 __syncthreads();
                 tick(5);
