@@ -212,7 +212,7 @@ static int make_plan(Plan &pl, const mte_loss_scale_t *sc, int n, const mte_loss
     P.totalUnits = (int)unitBase;
     // forward: persistent CTAs (2 per SM), every warp owns an equal contiguous range of strip rows (at least a few
     // rows each, so the window prologue is amortised)
-    pl.fwdGrid = kNumSMs * kRMinB;
+    pl.fwdGrid = kNumSMs * kRGridB;
     const int minRows = 4;
     if ((long long)pl.fwdGrid * kRWarps * minRows > unitBase) pl.fwdGrid = (int)((unitBase + kRWarps * minRows - 1) / (kRWarps * minRows));
     if (pl.fwdGrid < 1) pl.fwdGrid = 1;

@@ -52,7 +52,12 @@ constexpr int kBwdRH = 8;   // output rows per backward work item
 #ifndef MTE_BWD_D
 #define MTE_BWD_D 2
 #endif
-constexpr int kRWarps = MTE_LOSS_WARPS, kRThreads = kRWarps * 32, kRMinB = MTE_LOSS_MINB;
+#ifndef MTE_LOSS_GRIDB
+#define MTE_LOSS_GRIDB MTE_LOSS_MINB
+#endif
+// kRMinB caps the registers (launch bounds), kRGridB is the number of persistent CTAs launched per SM: launching
+// fewer than fit leaves room for the CTAs of the NEXT kernel to become resident early (programmatic dependent launch)
+constexpr int kRWarps = MTE_LOSS_WARPS, kRThreads = kRWarps * 32, kRMinB = MTE_LOSS_MINB, kRGridB = MTE_LOSS_GRIDB;
 #ifndef MTE_SEGCOST_F
 #define MTE_SEGCOST_F 4
 #endif
@@ -401,6 +406,9 @@ __device__ __forceinline__ float lg2_approx(float x) {  // arguments here are >=
 // ---- programmatic dependent launch (PDL): the kernels are launched with programmatic stream serialisation, so their
 // launch latency, CTA scheduling and index prologue overlap the tail of the previous kernel in the stream / graph;
 // pdl_wait() blocks until that kernel has completed and its writes are visible and precedes every global access.
+// (Measured on B200 inside the bench's CUDA graphs: no difference with MTE_NO_PDL=1 -- a 512-thread CTA at 96
+// registers leaves no room for a dependent CTA to become resident early, and register-capped variants that do leave
+// room lose more than the overlap gains.  Kept because it is free and helps behind short foreign kernels.)
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
