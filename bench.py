@@ -361,7 +361,7 @@ def bench_auc(args, rank, world, device, steps=None, warmup=None):
     rng = list(range(20, 241, 20))
     # weak scaling: every rank evaluates its own shard of 102 images (image i of the job -> rank i mod R),
     # counts are summed with one int64 all-reduce per evaluation
-    depths, gts = kitti_like_set(KITTI_N, 7000 + 1000 * rank)
+    depths, gts = kitti_like_set(KITTI_N, int(os.environ.get("MTE_BENCH_SEED", "7000")) + 1000 * rank)
     d_dev, g_dev = torch.from_numpy(depths).to(device), torch.from_numpy(gts).to(device)
     px_per_step = world * KITTI_N * KITTI_T * H0 * W0  # whole job
 

@@ -205,6 +205,20 @@ def all_reduce_counts(counts: torch.Tensor) -> torch.Tensor:
     return counts
 
 
+_REORDER = {}
+
+
+def _reorder_index(inv, device):
+    """Cached device index that maps the strictest-first sweep order back to the caller's threshold order (a fresh
+    pageable host -> device copy per call would synchronise the stream every evaluation)."""
+    key = (inv, str(device))
+    idx = _REORDER.get(key)
+    if idx is None:
+        idx = torch.tensor(inv, dtype=torch.long, device=device)
+        _REORDER[key] = idx
+    return idx
+
+
 def sweep_counts(depth: torch.Tensor, gt: torch.Tensor, edge_thresh_range, gt_crop, min_depth, max_depth,
                  max_dist=0.002, out=None) -> torch.Tensor:
     """Device part of ``pr_evaluation`` for a batch: depth [N,H,W] (already at GT size), gt [N,H,W]
@@ -214,8 +228,7 @@ def sweep_counts(depth: torch.Tensor, gt: torch.Tensor, edge_thresh_range, gt_cr
     pairs = [(int(edge_thresh_range[i] / 2), int(edge_thresh_range[i])) for i in order]
     levels = canny_from_depth(depth, pairs, min_depth, max_depth, want_edges=False, want_levels=True)
     c = pr_counts(levels, gt, n_levels=len(pairs), max_dist=max_dist, crop=gt_crop)
-    inv = torch.from_numpy(np.argsort(order)).to(c.device)
-    c = c[inv]
+    c = c[_reorder_index(tuple(int(v) for v in np.argsort(order)), c.device)]
     if out is not None:
         out += c
         return out
