@@ -767,9 +767,10 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
         tick(-1);
 
         // ---- ONE pass over the window: GT bitmap (atomicOr per GT pixel), stage histogram, and the predicted pixels
-        //      appended unsorted as pixel | stage << 24 to a temporary list that borrows the mateP + claimP storage.
-        //      Level planes are read as 32-bit words (4 pixels) when the layout allows it.
-        unsigned *tmpList = reinterpret_cast<unsigned *>(mateP);  // capP entries (mateP and claimP are adjacent)
+        //      appended unsorted as pixel | stage << 24 to a temporary list in this CTA's global arena (written once,
+        //      read once).  Level planes are read as 32-bit words (4 pixels) when the layout allows it.
+        unsigned *tmpList = reinterpret_cast<unsigned *>(P.arena + (size_t)blockIdx.x * P.arenaBytes);  // hw entries
+        unsigned *gpix = tmpList + hw;                                                                 // sorted by stage
         for (int i = threadIdx.x; i < SL.nW; i += kSwThreads) qbits[i] = 0u;
         if (threadIdx.x == 0) sNP = 0;
         __syncthreads();
@@ -778,7 +779,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
             if (stg < T) {
                 atomicAdd(&sStage[stg], 1);
                 const int slot = atomicAdd(&sNP, 1);
-                if (slot < SL.capP) tmpList[slot] = (unsigned)i | ((unsigned)stg << 24);
+                tmpList[slot] = (unsigned)i | ((unsigned)stg << 24);
             }
         };
         const unsigned char *lv = (const unsigned char *)P.pred + (size_t)img * P.H * P.W;
@@ -860,7 +861,8 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
             }
             if (lane == 0) sStage[T] = run;
         }
-        if (nPall > SL.capP || nQ > SL.capQ || nQ >= 0xFFF0 || nPall >= 0xFFF0) {  // does not fit: per-problem kernels
+        // the predicted side only has to hold the MATCHED pixels (<= nQ) plus a chunk of new ones (see below)
+        if (nQ > SL.capQ || nQ >= 0xFFF0 || SL.capP - nQ < 256) {  // does not fit: per-problem kernels
             if (threadIdx.x == 0) {
                 const int at = (int)atomicAdd(P.overflowCount, (unsigned)T);
                 for (int t = 0; t < T; t++) P.overflowList[at + t] = img * T + t;
@@ -872,10 +874,15 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
         // ---- predicted pixels grouped by stage (order inside a stage is arbitrary: counts do not depend on it)
         for (int k = threadIdx.x; k < nPall; k += kSwThreads) {
             const unsigned v = tmpList[k];
-            ppix[atomicAdd(&sCursor[v >> 24], 1)] = v & 0xFFFFFFu;
+            gpix[atomicAdd(&sCursor[v >> 24], 1)] = v & 0xFFFFFFu;
         }
         __syncthreads();
-        for (int k = threadIdx.x; k < nPall; k += kSwThreads) { mateP[k] = kFree; claimP[k] = 0; }
+        // Everything resident at once when it fits.  Otherwise ("compact" mode) the predicted arrays only ever hold the
+        // matched pixels plus one chunk of new ones: pixels whose search failed (or that have no GT pixel in range)
+        // can never be matched later (Kuhn), are never reached as somebody's mate, and are dropped after every chunk.
+        const bool compact = nPall > SL.capP;
+        if (!compact)
+            for (int k = threadIdx.x; k < nPall; k += kSwThreads) { ppix[k] = __ldcg(gpix + k); mateP[k] = kFree; claimP[k] = 0; }
         // ---- rank: exclusive prefix popcount over pairs of bitmap words
         {
             const int nW2 = (SL.nW + 1) >> 1;
@@ -906,8 +913,23 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
         tick(4);
 
         unsigned short phase = 0;
+        int nLive = 0;  // compact mode: matched pixels currently resident
         for (int s = 0; s < T; s++) {
-            const int p0 = sStage[s], p1 = sStage[s + 1];  // the pixels that join at this stage
+            const int G0 = sStage[s], G1 = sStage[s + 1];  // the pixels that join at this stage (positions in gpix)
+            int cur = G0;
+            do {
+            int p0 = G0, p1 = G1;  // resident index range of the new pixels; [0, p1) is everything resident
+            if (compact) {
+                const int n = min(G1 - cur, SL.capP - nLive);
+                p0 = nLive; p1 = nLive + n;
+                for (int k = threadIdx.x; k < n; k += kSwThreads) {
+                    ppix[p0 + k] = __ldcg(gpix + cur + k); mateP[p0 + k] = kFree; claimP[p0 + k] = 0;
+                }
+                cur += n;
+                __syncthreads();
+            } else {
+                cur = G1;
+            }
             if (p1 > p0) {
                 // ---- greedy start: nearest free GT pixel, one THREAD per new predicted pixel walking the offsets nearest
                 //      first (most pixels succeed within the first few; any greedy start is a valid matching)
@@ -1102,6 +1124,33 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                 }
             }
             __syncthreads();
+            if (compact) {
+                // ---- drop the pixels that are not matched (in place, stable, one block-wide round of kSwThreads
+                //      elements at a time: destinations never run ahead of the round being read) and re-point their mates
+                int kept = 0;
+                for (int base = 0; base < p1; base += kSwThreads) {
+                    const int i = base + threadIdx.x;
+                    unsigned px = 0;
+                    unsigned short mp = kDead;
+                    if (i < p1) { px = ppix[i]; mp = mateP[i]; }
+                    const bool keep = mp < kFailed;
+                    const unsigned bal = __ballot_sync(MTE_FULL_MASK, keep);
+                    if (lane == 0) sScan[warp] = __popc(bal);
+                    __syncthreads();
+                    int off = kept, tot = 0;
+                    for (int wv = 0; wv < kSwWarps; wv++) { const int c = sScan[wv]; if (wv < warp) off += c; tot += c; }
+                    if (keep) {
+                        const int d = off + __popc(bal & ((1u << lane) - 1u));
+                        ppix[d] = px; mateP[d] = mp; claimP[d] = 0;
+                        mateQ[mp] = (unsigned short)d;
+                    }
+                    kept += tot;
+                    __syncthreads();
+                }
+                nLive = kept;
+            }
+            } while (cur < G1);
+            __syncthreads();
             // ---- the count of this stage's threshold
             if (threadIdx.x == 0) {
                 const int t = levels ? s : T - 1 - s;
@@ -1110,7 +1159,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                 atomicAdd(c + 0, (unsigned long long)matched);
                 atomicAdd(c + 1, (unsigned long long)nQ);
                 atomicAdd(c + 2, (unsigned long long)matched);
-                atomicAdd(c + 3, (unsigned long long)p1);
+                atomicAdd(c + 3, (unsigned long long)G1);
             }
         }
         __syncthreads();
