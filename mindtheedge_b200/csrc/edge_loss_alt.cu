@@ -109,7 +109,7 @@ __global__ void alt_finalize_kernel(const AltP P) {
     const double numel = (double)P.n;
     double loss = 0.0;
     float alpha = 0.f;
-    if (P.types & MTE_LOSS_CE) loss = (double)*P.ceLoss / (double)P.weight;  // the fused kernel already applied the weight
+    if (P.types & MTE_LOSS_CE) loss = P.weight != 0.f ? (double)*P.ceLoss / (double)P.weight : 0.0;  // the fused kernel already applied the weight
     if (P.types & MTE_LOSS_ATTENTION) {
         alpha = (float)P.acc[ACC_NNEG] / ((float)P.acc[ACC_NPOS] + (float)P.acc[ACC_NNEG]);   // attention_loss.py:25-27
         loss = ((double)alpha * P.acc[ACC_SA] + (1.0 - (double)alpha) * P.acc[ACC_SB]) / numel;

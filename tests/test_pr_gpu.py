@@ -117,6 +117,38 @@ def test_soft_map_99_threshold_sweep_vs_oracle(dtype):
     assert np.array_equal(c, ref)
 
 
+@pytest.mark.parametrize("pred_density,gt_density", [(0.06, 0.015), (0.02, 0.08), (0.07, 0.04)])
+def test_sweep_matcher_capacity_paths_vs_oracle(pred_density, gt_density):
+    """KITTI crop window with more boundary pixels than the sweep matcher keeps in shared memory (~8.4 k per side):
+    many predicted pixels -> its compact mode (only matched pixels + a chunk resident); many GT pixels -> the image's
+    problems overflow to the per-problem kernels.  Counts of every threshold must still equal independent matchings."""
+    from mindtheedge_b200.eval_depth_edges import pr_counts
+    from oracle import pr_counts as opr
+    H, W, crop = 384, 1280, [44, 1197, 153, 371]
+    r = np.random.default_rng(int(1000 * pred_density + 100000 * gt_density))
+    gt = np.zeros((H, W), np.uint8)
+    for _ in range(int(gt_density * H * W / 150)):          # GT as random polylines (contours), not salt noise
+        y, x = int(r.integers(0, H)), int(r.integers(0, W))
+        for _ in range(150):
+            gt[y, x] = 1
+            y = int(np.clip(y + r.integers(-1, 2), 0, H - 1)); x = int(np.clip(x + r.integers(0, 2), 0, W - 1))
+    near = cv2.dilate(gt, np.ones((5, 5), np.uint8)) > 0
+    strength = np.where(near, r.random((H, W)), 0.0) * (r.random((H, W)) < pred_density / max(near.mean(), 1e-6) * 0.7)
+    strength = np.maximum(strength, (r.random((H, W)) < pred_density * 0.3) * r.random((H, W))).astype(np.float32)
+    thr = np.array([0.15, 0.3, 0.45, 0.6, 0.75, 0.9])
+    win = (slice(crop[2], crop[3]), slice(crop[0], crop[1]))
+    n_pred, n_gt = int((strength[win] >= thr[0]).sum()), int(gt[win].sum())
+    assert max(n_pred, n_gt) > 8500, (n_pred, n_gt)           # the case really exceeds the resident capacity
+    c = pr_counts(torch.from_numpy(strength)[None].cuda(), torch.from_numpy(gt)[None].cuda(), thr, max_dist=0.002,
+                  crop=crop).cpu().numpy()
+    ref = np.zeros((len(thr), 4), np.int64)
+    for t, v in enumerate(thr):
+        b = (strength[win].astype(np.float64) >= v).astype(np.uint8)
+        m = opr.match_count(b, np.ascontiguousarray(gt[win]), 0.002)
+        ref[t] = (m, n_gt, m, int(b.sum()))
+    assert np.array_equal(c, ref), (c.tolist(), ref.tolist())
+
+
 def test_kitti_size_sweep_vs_oracle():
     """Config 2 shape: 384x1280 planes, 12 Canny settings, KITTI crop, max_dist 0.002 -- bit-exact counts."""
     from mindtheedge_b200.eval_depth_edges import pr_evaluation_arrays
