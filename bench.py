@@ -468,6 +468,36 @@ def bench_auc(args, rank, world, device, steps=None, warmup=None):
     }
 
 
+def eager_gpu_loss_baseline(device, iters=10, warm=3):
+    """The reference's algorithm as plain eager PyTorch ON THE GPU (oracle port of GradLoss + autograd, the per-scale
+    loop of SemiSupEdgeModel.py:164-198, inv2depth included) at the headline shape: the like-for-like GPU baseline
+    SURVEY.md 8(d) asks for next to the CPU one.  Reported only; nothing of it is on the product path."""
+    from oracle.edge_loss import edge_loss_torch
+    data = loss_inputs(B_PER_GPU, 4242, device)
+    px = sum(B_PER_GPU * (H0 >> s) * (W0 >> s) for s in range(SCALES))
+
+    def step():
+        total = 0
+        for inv, edge, normal in data:
+            x = inv.clone().requires_grad_(True)
+            depth = 1.0 / x.clamp(min=1e-6)
+            l, _ = edge_loss_torch(depth, edge, None, True, True, 4, normal, weight=10.0)
+            total = total + l
+        (total / SCALES).backward()
+
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return px / (ms * 1e-3) / 1e6, ms
+
+
 def cpu_auc_baseline(n_images=4):
     from oracle import pr_counts as opr
     depths, gts = kitti_like_set(n_images, 7000)
@@ -562,6 +592,10 @@ def main():
                         f"thresholds in {dta:.1f} s"}
         if args.workload == "loss":
             line["cpu_baseline"] = cb
+            ve, mse = eager_gpu_loss_baseline(device)
+            line["eager_gpu_baseline"] = {"value": round(ve, 1), "unit": "Mpixel/s", "ms_per_step": round(mse, 3),
+                                          "kind": "port", "sample": "oracle port of GradLoss (eager PyTorch ops + autograd) "
+                                          "on the same B200, same shape as the headline, 10 timed steps"}
             if "auc_eval" in line:
                 line["auc_eval"]["cpu_baseline"] = ca
         else:
