@@ -117,6 +117,17 @@ int mte_edge_loss_alt_bwd(const float *grad_map, const float *edge, const float 
                           const float *ctx, float *grad_pred, int accumulate, void *workspace,
                           size_t workspace_bytes, mte_stream_t stream);
 
+/* Target preparation from the on-disk encoding.
+ * mte_decode_normals: u8 PNG value -> angle, (360.*(v/255.) - 180)*(pi/180) in float64 then
+ * float32 (packnet_code/packnet_sfm/datasets/gta_dataset.py:413, 421).
+ * mte_edge_resize_preserve: resize_depth_preserve (datasets/augmentations.py:58-100) of u8
+ * edge maps [B,h,w] to [B,H,W] (last valid source pixel in raster order wins) followed by
+ * the "/255 if max > 1" rule of resize_sample (:193-199) and the float32 cast. */
+int mte_decode_normals(const uint8_t *normal_u8, float *theta_out, size_t n, mte_stream_t stream);
+size_t mte_edge_resize_workspace_bytes(int B);
+int mte_edge_resize_preserve(const uint8_t *edge_u8, int B, int h, int w, float *edge_out, int H, int W,
+                             void *workspace, size_t workspace_bytes, mte_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * (2a) Depth -> edges for evaluation.
  * Replaces the array part of edge_from_depth (edge.py:81-88, twin

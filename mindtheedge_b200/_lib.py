@@ -62,6 +62,9 @@ _SIGNATURES = {
     "mte_edge_loss_alt_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mte_edge_loss_alt_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, C.c_float, C.c_float, _vp, _vp,
                                    _vp, _i, _vp, _sz, _vp]),
+    "mte_decode_normals": (_i, [_vp, _vp, _sz, _vp]),
+    "mte_edge_resize_workspace_bytes": (_sz, [_i]),
+    "mte_edge_resize_preserve": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _sz, _vp]),
     "mte_chamfer_workspace_bytes": (_sz, [_i, _i, _i]),
     "mte_chamfer_counts": (_i, [_vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _sz, _vp]),
 }

@@ -78,3 +78,14 @@ def load_utils_edge():
         sys.path.insert(0, REF)
     from packnet_code.packnet_sfm.utils import edge as ref_utils_edge
     return ref_utils_edge
+
+
+def load_augmentations():
+    """packnet_sfm/datasets/augmentations.py (resize_depth_preserve).  Needs the `yacs` stub of load_utils_edge and
+    `Image.ANTIALIAS`, which Pillow >= 10 removed (the module uses it as a default argument at import time)."""
+    from PIL import Image
+    if not hasattr(Image, "ANTIALIAS"):
+        Image.ANTIALIAS = Image.LANCZOS
+    load_utils_edge()
+    from packnet_code.packnet_sfm.datasets import augmentations as ref_aug
+    return ref_aug

@@ -275,6 +275,34 @@ def gen_pr():
     print("pr:", {k: v for k, v in out.items() if k.startswith("pr_") and np.size(v) < 8})
 
 
+def gen_targets():
+    """resize_depth_preserve + the /255 rule of resize_sample from the UNMODIFIED datasets/augmentations.py, the normal
+    decode expression of datasets/gta_dataset.py:413 and the float32 cast of to_tensor_sample."""
+    from _reference_loader import load_augmentations
+    A = load_augmentations()
+    r = np.random.default_rng(11)
+    out = {}
+    cases = [((48, 64), (48, 64)), ((48, 64), (24, 32)), ((96, 160), (24, 40)), ((37, 53), (20, 31)), ((24, 32), (48, 64)),
+             ((50, 70), (17, 70)), ((8, 8), (1, 1))]
+    for i, (hw, HW) in enumerate(cases):
+        e = ((r.random(hw) < 0.08) * r.integers(1, 256, hw)).astype(np.uint8)
+        if i == 5:
+            e = (e > 0).astype(np.uint8)          # 0/1 map: the "/255 if max > 1" rule must not fire
+        if i == 6:
+            e[:] = 0                               # nothing valid
+        ref = A.resize_depth_preserve(e, HW)[:, :, 0]
+        if np.max(ref) > 1:                        # resize_sample, augmentations.py:196-199
+            ref = ref / 255
+        out[f"edge_in{i}"] = e
+        out[f"edge_shape{i}"] = np.array(HW)
+        out[f"edge_out{i}"] = ref.astype(np.float32)   # to_tensor_sample: FloatTensor
+    out["n_edge"] = np.int64(len(cases))
+    v = np.arange(256, dtype=np.uint8)
+    out["theta"] = ((360. * (v / 255.) - 180) * (np.pi / 180)).astype(np.float32)   # gta_dataset.py:413
+    np.savez_compressed(os.path.join(HERE, "targets.npz"), **out)
+    print("targets:", len(cases), "edge cases + 256 angles")
+
+
 def gen_chamfer():
     """chamfer_distance of the UNMODIFIED packnet_sfm/utils/edge.py on synthetic edge maps (both directions), and
     the 9 light metrics of compute_edge_metrics restated around it (cv2.Canny + the reference chamfer_distance)."""
@@ -328,6 +356,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "chamfer":
         gen_chamfer()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "targets":
+        gen_targets()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "edge_loss_alt":
         torch.manual_seed(0)
         gen_edge_loss_alt()
@@ -339,3 +370,4 @@ if __name__ == "__main__":
     gen_dee()
     gen_pr()
     gen_chamfer()
+    gen_targets()

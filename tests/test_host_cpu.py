@@ -69,6 +69,9 @@ def test_host_side_argument_checks_without_a_gpu():
     assert L.mte_edge_loss_alt_workspace_bytes(2, 48, 64) > 2 * 2 * 48 * 64 * 4
     assert L.mte_edge_loss_alt_fwd(256, 256, None, 1, 8, 8, 8, 1, 4.0, 1.0, None, 256, 256, 256, 1 << 20, None) == -4   # dice alone
     assert L.mte_edge_loss_alt_fwd(256, 256, None, 1, 8, 8, 1, 1, 4.0, 1.0, None, 256, 256, 256, 1 << 20, None) == -4   # CE without its loss
+    assert L.mte_edge_resize_workspace_bytes(4) > 0 and L.mte_edge_resize_workspace_bytes(0) == 0
+    assert L.mte_decode_normals(None, None, 16, None) == -1
+    assert L.mte_edge_resize_preserve(256, 1, 8, 8, 256, 4, 4, 256, 16, None) == -3
     assert L.mte_chamfer_workspace_bytes(3, 384, 1280) > 3 * 384 * 1280 * 2 and L.mte_chamfer_workspace_bytes(0, 4, 4) == 0
     assert L.mte_chamfer_counts(None, None, 1, 8, 8, 5.0, None, None, None, 0, None) == -1
     assert L.mte_chamfer_counts(256, 256, 1, 8, 8, 5.0, 256, None, 256, 16, None) == -3

@@ -179,3 +179,13 @@ def test_alt_loss_oracle_vs_reference_golden(name):
     assert abs(loss.item() - float(c["loss"])) <= 1e-6 * abs(float(c["loss"]))
     assert np.array_equal(gmap.numpy(), c["grad_map"])
     assert np.abs(x.grad.numpy() - c["dgrad"]).max() <= 1e-6 * np.abs(c["dgrad"]).max()
+
+
+def test_targets_oracle_vs_reference_golden():
+    """oracle/targets.py against resize_depth_preserve + the /255 rule of the unmodified datasets/augmentations.py and
+    the normal decode expression of datasets/gta_dataset.py:413."""
+    from oracle import targets as ot
+    z = np.load(os.path.join(GOLDEN, "targets.npz"))
+    for i in range(int(z["n_edge"])):
+        assert np.array_equal(ot.edge_target(z[f"edge_in{i}"], tuple(z[f"edge_shape{i}"])), z[f"edge_out{i}"]), i
+    assert np.array_equal(ot.decode_normals(np.arange(256, dtype=np.uint8)), z["theta"])
