@@ -298,6 +298,48 @@ def bench_loss(args, rank, world, device):
     ms_e2e = max_over_ranks(e0.elapsed_time(e1), world, device) / n_e2e
     e2e_value = world * px_per_step / (ms_e2e * 1e-3) / 1e6
 
+    # the same step with the targets shipped in their on-disk u8 encoding and prepared on the device
+    # (mindtheedge_b200.targets): 4 + 1 + 1 bytes per pixel over PCIe instead of 12
+    from mindtheedge_b200.targets import prepare_targets
+    g8 = torch.Generator().manual_seed(77 + rank)
+    shapes = [(B_PER_GPU, H0 >> s, W0 >> s) for s in range(SCALES)]
+    n_px = sum(b * h * w for b, h, w in shapes)
+    h_inv = torch.empty(n_px, dtype=torch.float32).pin_memory()
+    h_u8 = torch.empty(2 * n_px, dtype=torch.uint8).pin_memory()
+    h_inv.copy_(1.0 / (torch.rand(n_px, generator=g8) * 79 + 1))
+    h_u8[:n_px].copy_(((torch.rand(n_px, generator=g8) < 0.015) * torch.randint(77, 256, (n_px,), generator=g8)).to(torch.uint8))
+    h_u8[n_px:].copy_(torch.randint(0, 256, (n_px,), generator=g8).to(torch.uint8))
+    d_inv = torch.empty(n_px, dtype=torch.float32, device=device)
+    d_u8 = torch.empty(2 * n_px, dtype=torch.uint8, device=device)
+    inv_v, e_v, n_v, o = [], [], [], 0
+    for b, h, w in shapes:
+        inv_v.append(d_inv[o:o + b * h * w].view(b, 1, h, w))
+        e_v.append(d_u8[o:o + b * h * w].view(b, h, w))
+        n_v.append(d_u8[n_px + o:n_px + o + b * h * w].view(b, h, w))
+        o += b * h * w
+
+    def e2e_u8_step():
+        d_inv.copy_(h_inv, non_blocking=True)
+        d_u8.copy_(h_u8, non_blocking=True)
+        edges, normals = prepare_targets(e_v, n_v)
+        inv = [t.requires_grad_(True) for t in inv_v]
+        total, _, _ = multiscale_edge_loss(inv, edges, None, normals, weight=10.0, pred_is_inverse=True)
+        total.backward()
+        loss_host.copy_(total.detach().reshape(1), non_blocking=True)
+        for t in inv:
+            t.grad = None
+            t.requires_grad_(False)
+
+    for _ in range(3):
+        e2e_u8_step()
+    barrier(world)
+    e0.record()
+    for _ in range(n_e2e):
+        e2e_u8_step()
+    e1.record()
+    barrier(world)
+    ms_u8 = max_over_ranks(e0.elapsed_time(e1), world, device) / n_e2e
+
     peak, peak_src = measured_peak_gbs()
     # roofline over the timed region itself: both kernels of a step, graph launch gaps included
     achieved = LOSS_BYTES_PER_PX * px_per_step / (ms_per_step * 1e-3) / 1e9
@@ -312,6 +354,10 @@ def bench_loss(args, rank, world, device):
                    "parallelism": f"dp{world} (batch-sharded, no data-path collective in the loss)"},
         "e2e": {"value": round(e2e_value, 1), "unit": "Mpixel/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e, 4), "api": "mindtheedge_b200.losses.multiscale_edge_loss + backward"},
+        "e2e_u8_targets": {"value": round(world * px_per_step / (ms_u8 * 1e-3) / 1e6, 1), "unit": "Mpixel/s",
+                           "h2d_bytes_per_step": 6 * n_px, "d2h_bytes_per_step": 4, "ms_per_step": round(ms_u8, 4),
+                           "api": "targets.prepare_targets (u8 edge / normal planes decoded on the device) + "
+                                  "multiscale_edge_loss + backward; extension, not the reference-facing call"},
         "gpu_launches": 2 * args.steps,
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": recorded_traffic("edge_loss_fwd_bwd"),

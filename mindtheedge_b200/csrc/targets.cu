@@ -62,15 +62,19 @@ __global__ void __launch_bounds__(kThreads) edge_resize_preserve_kernel(const un
     for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
         const int X = (int)(i % W), Y = (int)((i / W) % H), img = (int)(i / ((size_t)W * H));
         const unsigned char *src = in + (size_t)img * h * w;
-        int y0, y1, x0, x1;
-        source_range(Y, sy, h, y0, y1);
-        source_range(X, sx, w, x0, x1);
         int v = 0;
-        for (int y = y1; y >= y0 && v == 0; y--)          // last valid source pixel in raster order wins (:98)
-            for (int x = x1; x >= x0; x--) {
-                const int s = src[(size_t)y * w + x];
-                if (s > 0) { v = s; break; }
-            }
+        if (H == h && W == w) {                               // same shape: the scatter is the identity
+            v = src[(size_t)Y * w + X];
+        } else {
+            int y0, y1, x0, x1;
+            source_range(Y, sy, h, y0, y1);
+            source_range(X, sx, w, x0, x1);
+            for (int y = y1; y >= y0 && v == 0; y--)          // last valid source pixel in raster order wins (:98)
+                for (int x = x1; x >= x0; x--) {
+                    const int s = src[(size_t)y * w + x];
+                    if (s > 0) { v = s; break; }
+                }
+        }
         // "if np.max(sample[key]) > 1: sample[key] = sample[key] / 255" in float64, then FloatTensor
         out[i] = maxIn[img] > 1 ? (float)__ddiv_rn((double)v, 255.0) : (float)v;
     }
