@@ -16,8 +16,11 @@ e2e        the same metric through the public torch API with HOST buffers: pinne
            step's inputs and D2H of the loss inside the timed region;
 roofline   algorithmic bytes (32 B/px, SURVEY.md 8d) / measured step time vs MEASURED_PEAKS.json;
 cpu_baseline  the oracle port (same op chain as the reference, torch CPU, all host threads) on a
-           bounded sample, timed in the same run.
-`--impl reference` times that CPU port alone (rank 0 only).
+           bounded sample, timed in the same run;
+eager_gpu_baseline  the same port as eager PyTorch ops + autograd on the same GPU (SURVEY.md 8d);
+e2e_u8_targets      the e2e step with the targets shipped as u8 and prepared on the device (extension).
+`--impl reference` times that CPU port alone (rank 0 only).  The AUC workload evaluates the reference's
+bundled KITTI-DE GT edge maps (tests/golden/kitti_de_gt.npz) against synthetic predicted depth.
 """
 from __future__ import annotations
 
