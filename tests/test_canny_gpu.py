@@ -95,3 +95,21 @@ def test_long_weak_chain_crosses_many_tiles():
     got = canny_from_depth(torch.from_numpy(d).cuda(), [(20, 100)]).cpu().numpy()[0]
     assert ref[47:49, 600:].any()
     assert np.array_equal(got, ref)
+
+
+def test_hysteresis_fallback_when_reachable_set_exceeds_shared_memory():
+    """White-noise u8 plane at KITTI size with very low thresholds: > 100 k candidates connected to strong pixels, far
+    beyond what the shared-memory union-find holds (~40 k) -> the image is handed to the L2 kernel.  Bit-exact with
+    cv2.Canny for every pair, alongside an ordinary image in the same batch (which stays on the fast path)."""
+    import cv2
+    from mindtheedge_b200.edge import canny_from_depth
+    r = np.random.default_rng(5)
+    noise = r.integers(0, 256, (384, 1280)).astype(np.uint8)
+    smooth = cv2.GaussianBlur(r.integers(0, 256, (384, 1280)).astype(np.uint8), (9, 9), 3)
+    batch = torch.from_numpy(np.stack([noise, smooth])).cuda()
+    pairs = [(40, 80), (10, 20), (1, 2)]
+    edges = canny_from_depth(batch, pairs).cpu().numpy()
+    for t, (lo, hi) in enumerate(pairs):
+        for k, img in enumerate((noise, smooth)):
+            assert np.array_equal(edges[t, k], cv2.Canny(img, lo, hi)), (t, k)
+    assert int((edges[2, 0] > 0).sum()) > 60000
