@@ -1,0 +1,41 @@
+"""The raw ctypes bindings printed in INTEGRATION.md, executed as written (a maintainer of the reference would paste
+them): the S1 loss binding block must run against libmte.so and agree with the adapter."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _code_blocks():
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    return re.findall(r"```python\n(.*?)```", text, flags=re.S)
+
+
+def test_s1_raw_loss_binding_runs_and_matches_the_adapter():
+    from mindtheedge_b200.losses import GradLoss
+    block = next(b for b in _code_blocks() if "class _Fn(torch.autograd.Function)" in b)
+    ns = {}
+    cwd = os.getcwd()
+    os.chdir(ROOT)   # the snippet loads "mindtheedge_b200/libmte.so" relative to the repository root
+    try:
+        exec(block, ns)
+    finally:
+        os.chdir(cwd)
+    g = torch.Generator().manual_seed(0)
+    B, H, W = 2, 48, 64
+    depth = torch.round((torch.rand(B, 1, H, W, generator=g) * 79 + 1) * 64) / 64
+    edge = (torch.rand(B, 1, H, W, generator=g) < 0.05).float() * torch.rand(B, 1, H, W, generator=g).clamp(min=0.3)
+    normal = ((360 * torch.randint(0, 256, (B, 1, H, W), generator=g).float() / 255 - 180) * np.pi / 180).float()
+    x1 = depth.cuda().requires_grad_(True)
+    loss1, gmap1 = ns["_Fn"].apply(x1, edge.cuda(), normal.cuda(), 10.0)
+    loss1.backward()
+    x2 = depth.cuda().requires_grad_(True)
+    loss2, gmap2 = GradLoss("cross_entropy", True, [], 10.0, 1.0)(x2, edge.cuda(), None, True, True, 4, normal.cuda())
+    loss2.backward()
+    assert loss1.item() == loss2.item()
+    assert torch.equal(gmap1, gmap2) and torch.equal(x1.grad, x2.grad)
