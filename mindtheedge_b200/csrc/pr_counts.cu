@@ -731,11 +731,15 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
 
     auto rflag_get = [&](int pi) -> unsigned { return (((volatile unsigned *)rflagW)[pi >> 2] >> (8 * (pi & 3))) & 0xFFu; };
     auto rflag_or = [&](int pi, unsigned f) { atomicOr(&rflagW[pi >> 2], f << (8 * (pi & 3))); };
-    auto qid = [&](int q) -> int {  // rank is kept per 64 window pixels (two bitmap words)
-        const unsigned bits = qbits[q >> 5];
-        int r = (int)qrank[q >> 6] + __popc(bits & ((1u << (q & 31)) - 1u));
-        if (q & 32) r += __popc(qbits[(q >> 5) - 1]);
-        return r;
+    // Is window pixel q a GT pixel, and which id does it have?  The rank is kept per 64 window pixels (two bitmap
+    // words); the word pair and the rank are fetched together, before the bit is known: ONE shared-memory round trip
+    // on the chain of a hop instead of two (the bitmap is padded to whole 16-byte groups).
+    auto qprobe = [&](int q, int &qi) -> bool {
+        const uint2 b = *reinterpret_cast<const uint2 *>(qbits + ((q >> 6) << 1));
+        const int r0 = (int)qrank[q >> 6];
+        const unsigned word = (q & 32) ? b.y : b.x;
+        qi = r0 + __popc(word & ((1u << (q & 31)) - 1u)) + ((q & 32) ? __popc(b.x) : 0);
+        return (word >> (q & 31)) & 1u;
     };
     // stage at which window pixel (gy, gx) of image img joins the predicted set; T = never
     auto stage_of = [&](int img, int gy, int gx) -> int {
@@ -754,6 +758,9 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
         }
         return T - lo;  // lo == 0 (below every threshold, or NaN) -> T = never
     };
+    // resident predicted pixels are kept as y << 16 | x: the hop of an alternating chain then needs no division
+    auto pack_yx = [&](unsigned i) -> unsigned { const unsigned y = i / (unsigned)w; return (y << 16) | (i - y * (unsigned)w); };
+    const short2 off0 = sOff[min(lane, noff - 1)];  // lane's own entry of the first 32 offsets (all of them at KITTI radius)
 
     for (;;) {
         if (threadIdx.x == 0) sImage = (int)atomicAdd(P.nextProblem, 1u);
@@ -882,7 +889,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
         // can never be matched later (Kuhn), are never reached as somebody's mate, and are dropped after every chunk.
         const bool compact = nPall > SL.capP;
         if (!compact)
-            for (int k = threadIdx.x; k < nPall; k += kSwThreads) { ppix[k] = __ldcg(gpix + k); mateP[k] = kFree; claimP[k] = 0; }
+            for (int k = threadIdx.x; k < nPall; k += kSwThreads) { ppix[k] = pack_yx(__ldcg(gpix + k)); mateP[k] = kFree; claimP[k] = 0; }
         // ---- rank: exclusive prefix popcount over pairs of bitmap words
         {
             const int nW2 = (SL.nW + 1) >> 1;
@@ -923,7 +930,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                 const int n = min(G1 - cur, SL.capP - nLive);
                 p0 = nLive; p1 = nLive + n;
                 for (int k = threadIdx.x; k < n; k += kSwThreads) {
-                    ppix[p0 + k] = __ldcg(gpix + cur + k); mateP[p0 + k] = kFree; claimP[p0 + k] = 0;
+                    ppix[p0 + k] = pack_yx(__ldcg(gpix + cur + k)); mateP[p0 + k] = kFree; claimP[p0 + k] = 0;
                 }
                 cur += n;
                 __syncthreads();
@@ -934,17 +941,17 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                 // ---- greedy start: nearest free GT pixel, one THREAD per new predicted pixel walking the offsets nearest
                 //      first (most pixels succeed within the first few; any greedy start is a valid matching)
                 for (int pi = p0 + threadIdx.x; pi < p1; pi += kSwThreads) {
-                    const int p = (int)ppix[pi];
-                    const int py = p / w, px = p - py * w;
+                    const unsigned p = ppix[pi];
+                    const int py = (int)(p >> 16), px = (int)(p & 0xFFFFu);
                     bool done = false, anyQ = false;
                     for (int k = 0; k < noff && !done; k++) {
                         const short2 o = sOff[k];
                         const int qy = py + o.y, qx = px + o.x;
                         if (qy < 0 || qy >= h || qx < 0 || qx >= w) continue;
                         const int q = qy * w + qx;
-                        if (!((qbits[q >> 5] >> (q & 31)) & 1u)) continue;
+                        int qi;
+                        if (!qprobe(q, qi)) continue;
                         anyQ = true;
-                        const int qi = qid(q);
                         if (((volatile unsigned short *)mateQ)[qi] != kFree) continue;
                         if (cas16(&mateQ[qi], kFree, (unsigned short)pi) == kFree) {
                             mateP[pi] = (unsigned short)qi;
@@ -1005,25 +1012,29 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                         my = __shfl_sync(MTE_FULL_MASK, my, 0);
                         if (my == -2) break;
                         int pi = my;
+                        const int root = rootP[pi];  // a successor inherits the tree of its predecessor
+                        const unsigned mine = ((unsigned)phase << 16) | (unsigned)root;
                         for (;;) {  // a warp keeps ONE successor and goes on with it directly (chains along contours
-                                    // would otherwise pay a queue round trip per hop); the others are published
-                            const int root = rootP[pi];
+                                    // would otherwise pay a queue round trip per hop); the others are published.
+                                    // The hop is a chain of dependent shared-memory round trips, so everything whose
+                                    // address is known early is loaded early (position + tree flag together, mate next
+                                    // to the stamp: the matching does not change during a phase).
                             int keep = -1;
+                            const unsigned p = ppix[pi];
                             if (!(rflag_get(root) & RF_FOUND)) {
-                                const int p = (int)ppix[pi];
-                                const int py = p / w, px = p - py * w;
-                                const unsigned mine = ((unsigned)phase << 16) | (unsigned)root;
+                                const int py = (int)(p >> 16), px = (int)(p & 0xFFFFu);
                                 for (int k0 = 0; k0 < noff; k0 += 32) {
                                     const int k = k0 + lane;
                                     int succ = -1;
                                     if (k < noff) {
-                                        const short2 o = sOff[k];
+                                        const short2 o = k0 == 0 ? off0 : sOff[k];
                                         const int qy = py + o.y, qx = px + o.x;
                                         if (qy >= 0 && qy < h && qx >= 0 && qx < w) {
                                             const int q = qy * w + qx;
-                                            if ((qbits[q >> 5] >> (q & 31)) & 1u) {
-                                                const int qi = qid(q);
+                                            int qi;
+                                            if (qprobe(q, qi)) {
                                                 unsigned st = stamp[qi];
+                                                const unsigned short mq = mateQ[qi];
                                                 if (st != kDeadStamp) {
                                                     bool claimed = false;
                                                     if ((st >> 16) != phase) {
@@ -1033,7 +1044,6 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                                                     }
                                                     if (claimed) {
                                                         parentQ[qi] = (unsigned short)pi;
-                                                        const unsigned short mq = mateQ[qi];
                                                         if (mq == kFree) {
                                                             const int es = atomicAdd(&sEnds, 1);
                                                             if (es < kEndsCap) ends[es] = (unsigned short)qi;
