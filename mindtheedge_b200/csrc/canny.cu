@@ -13,6 +13,8 @@
 
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mte {
@@ -320,7 +322,12 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_kernel(const UfP P) 
 // component flags one bit each.  A find is then a few 30-cycle shared-memory hops instead of dependent L2 round
 // trips (the L2 kernel above spends its time there: ~2 x candidates finds per level).  Per-candidate edge levels
 // live in a compact global array in list order (coalesced) and are scattered to the plane at the end.  Images with
-// more candidates than fit (or planes whose bitmap does not fit) are left to the L2 kernel through P.todo.
+// more candidates than fit are left to the L2 kernel through P.todo.
+// Bitmap rows are padded to whole 32-bit words (row stride WP = 32 * ceil(W / 32) bits), so any W % 16 == 0 works.
+// BIG = true (planes whose bitmaps do not fit next to a useful number of candidates, e.g. DDAD 1216 x 1936): the two
+// bitmaps and the rank table live in the image's global scratch (L2-resident, a few hundred KB) instead; they are only
+// touched by independent, pipelined accesses (flood frontier, neighbour lookups), while the union-find chains --
+// the latency-critical part -- stay in shared memory.
 // ---------------------------------------------------------------------------
 constexpr int kWorkCap = 4096;  // changed-word worklist entries of the flood (beyond that: one full sweep)
 
@@ -336,13 +343,16 @@ __device__ __forceinline__ int ufs_find(volatile unsigned short *parent, int x) 
     return x;
 }
 
+template <bool BIG>
 __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const UfP P) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ int sHist[256], sEnd[256], sScan[kUfThreads];
     __shared__ int sCntA, sCntB, sFull;
+    using WL = typename std::conditional<BIG, unsigned, unsigned short>::type;  // worklist entry: a bitmap word index
     const int img = blockIdx.x;
     const int H = P.H, W = P.W, HW = H * W, T = P.T;
-    const int nW = (HW + 31) >> 5, nW2 = (nW + 1) >> 1;
+    const int WPR = (W + 31) >> 5, WP = WPR * 32;  // words / bits per bitmap row
+    const int nW = H * WPR, nW2 = (nW + 1) >> 1;
     const size_t base = (size_t)img * HW;
     const unsigned char *cl = P.cl + base;
     unsigned char *E = P.E + base;
@@ -352,8 +362,8 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
     // per-candidate state (parent, edge level, flag) is indexed by id in shared memory and the per-level passes touch
     // nothing else; only the neighbour lookup of step (i) goes raster rank -> id through a global table
     unsigned short *perm = reinterpret_cast<unsigned short *>(P.parent + base);
-    unsigned *qbits = reinterpret_cast<unsigned *>(dyn);
-    unsigned short *qrank = reinterpret_cast<unsigned short *>(dyn + P.oRank);
+    unsigned *qbits = BIG ? reinterpret_cast<unsigned *>(merged) : reinterpret_cast<unsigned *>(dyn);
+    unsigned short *qrank = BIG ? reinterpret_cast<unsigned short *>(qbits + 2 * nW) : reinterpret_cast<unsigned short *>(dyn + P.oRank);
     unsigned short *parent = reinterpret_cast<unsigned short *>(dyn + P.oParent);
     unsigned *flagW = reinterpret_cast<unsigned *>(dyn + P.oFlag);
     unsigned char *Ec = dyn + P.oEc;
@@ -368,13 +378,17 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
     };
     for (int i = threadIdx.x; i < 256; i += kUfThreads) sHist[i] = 0;
     __syncthreads();
-    const bool vec = (HW % 16) == 0 && (reinterpret_cast<uintptr_t>(cl) & 15) == 0 && (reinterpret_cast<uintptr_t>(E) & 15) == 0;
-    // ---- pass 1: bitmaps of the candidates (cbits) and of the pixels that are strong at some level (qbits = seed)
-    unsigned *cbits = reinterpret_cast<unsigned *>(dyn + P.oParent);   // borrowed until the flood is done
-    unsigned short *wlA = reinterpret_cast<unsigned short *>(dyn + P.oWork), *wlB = wlA + kWorkCap;
-    for (int i0 = threadIdx.x * 16; i0 < nW * 32; i0 += kUfThreads * 16) {
+    const bool vec = (reinterpret_cast<uintptr_t>(cl) & 15) == 0 && (reinterpret_cast<uintptr_t>(E) & 15) == 0;  // W % 16 == 0 (host)
+    // ---- pass 1: bitmaps of the candidates (cbits) and of the pixels that are strong at some level (qbits = seed),
+    //      one 16-pixel chunk (half a bitmap word; chunks never straddle a row) per thread and step
+    unsigned *cbits = BIG ? qbits + nW : reinterpret_cast<unsigned *>(dyn + P.oParent);   // smem: borrowed until the flood is done
+    WL *wlA = reinterpret_cast<WL *>(dyn + P.oWork), *wlB = wlA + kWorkCap;
+    const int HPR = WPR * 2;  // 16-pixel chunks per bitmap row
+    for (int hc = threadIdx.x; hc < H * HPR; hc += kUfThreads) {
+        const int y = hc / HPR, x0 = (hc - y * HPR) * 16;
+        const int i0 = hc * 16;  // bit index of the chunk
         unsigned char v[16], sv[16];
-        if (i0 < HW) { load16(v, cl, i0, HW, vec); load16(sv, E, i0, HW, vec); }
+        if (x0 < W) { load16(v, cl, y * W + x0, HW, vec); load16(sv, E, y * W + x0, HW, vec); }
         else {
 #pragma unroll
             for (int k = 0; k < 16; k++) { v[k] = (unsigned char)kNever; sv[k] = (unsigned char)kNever; }
@@ -395,7 +409,6 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
     //      union-find below runs on that reachable set R only.  R grows from the strong pixels by bit-parallel
     //      dilation restricted to the candidates: inside a word a Kogge-Stone occluded fill runs along the whole
     //      horizontal run at once; a worklist of changed words keeps an iteration proportional to the frontier.
-    const int WPR = W >> 5;  // words per image row (the host only takes this kernel when W % 32 == 0)
     auto hfill = [](unsigned seed, unsigned c) -> unsigned {
         unsigned f = seed & c, m = c;
         f |= m & (f << 1); m &= m << 1; f |= m & (f << 2); m &= m << 2; f |= m & (f << 4); m &= m << 4;
@@ -406,7 +419,7 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
         return f;
     };
     for (int i = threadIdx.x; i < nW; i += kUfThreads)
-        if (qbits[i]) { const int s = atomicAdd(&sCntA, 1); if (s < kWorkCap) wlA[s] = (unsigned short)i; else sFull = 1; }
+        if (qbits[i]) { const int s = atomicAdd(&sCntA, 1); if (s < kWorkCap) wlA[s] = (WL)i; else sFull = 1; }
     __syncthreads();
     for (int iter = 0;; iter++) {
         const int nA = min(sCntA, kWorkCap);
@@ -440,24 +453,26 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
                     const unsigned old = atomicOr(&qbits[ti], add);
                     if (add & ~old) {
                         const int s2 = atomicAdd(&sCntB, 1);
-                        if (s2 < kWorkCap) wlB[s2] = (unsigned short)ti; else sFull = 1;
+                        if (s2 < kWorkCap) wlB[s2] = (WL)ti; else sFull = 1;
                     }
                 }
             }
         }
         __syncthreads();
         if (threadIdx.x == 0) { sCntA = sCntB; sCntB = 0; }
-        unsigned short *tmp = wlA; wlA = wlB; wlB = tmp;
+        WL *tmp = wlA; wlA = wlB; wlB = tmp;
         __syncthreads();
     }
     tick(0);
     // ---- histogram of first-candidate levels over R (sparse: walk the set bits)
     for (int wi = threadIdx.x; wi < nW; wi += kUfThreads) {
         unsigned bits = qbits[wi];
+        if (!bits) continue;
+        const int y = wi / WPR, pbase = y * W + (wi - y * WPR) * 32;  // pixel of bit 0
         while (bits) {
             const int b = __ffs(bits) - 1;
             bits &= bits - 1;
-            atomicAdd(&sHist[cl[wi * 32 + b]], 1);
+            atomicAdd(&sHist[cl[pbase + b]], 1);
         }
     }
     __syncthreads();
@@ -515,11 +530,13 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
     // ---- pass 2 (sparse): the pixels of R sorted by level, with their ids and strong levels
     for (int wi = threadIdx.x; wi < nW; wi += kUfThreads) {
         unsigned bits = qbits[wi];
+        if (!bits) continue;
         int r = (int)qrank[wi >> 1] + ((wi & 1) ? __popc(qbits[wi - 1]) : 0);
+        const int y = wi / WPR, pbase = y * W + (wi - y * WPR) * 32;
         while (bits) {
             const int b = __ffs(bits) - 1;
             bits &= bits - 1;
-            const int px = wi * 32 + b;
+            const int px = pbase + b;
             const int at = atomicAdd(&sHist[cl[px]], 1);
             list[at] = px;
             perm[r++] = (unsigned short)at;
@@ -543,7 +560,7 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
                 const int yy = y + dy, xx = x + dx;
                 nid[d] = 0xFFFF;
                 if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-                const int q = yy * W + xx;
+                const int q = yy * WP + xx;  // bit index
                 if ((qbits[q >> 5] >> (q & 31)) & 1u) nid[d] = __ldcg(perm + qid(q));
             }
 #pragma unroll
@@ -635,42 +652,52 @@ int run_level_hysteresis(const unsigned char *cl, unsigned char *E, int N, int H
     P.todo = nullptr;
     P.cap = 0;
     P.prof = getenv("MTE_HYST_PROF") ? reinterpret_cast<unsigned long long *>(w + hysteresis_scratch_bytes(N, H, W) - 256) : nullptr;
-    // shared-memory kernel first when the plane's bitmap leaves room for a useful number of candidates
+    // shared-memory kernel first: bitmaps next to the per-candidate state when they leave room for a useful number of
+    // candidates, otherwise (BIG) bitmaps in the image's global scratch and only the per-candidate state resident
     static int budget = -1;
     if (budget < 0) {
         int dev = 0, optin = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         cudaFuncAttributes fa;
-        cudaFuncGetAttributes(&fa, canny_uf_hyst_smem_kernel);
+        cudaFuncGetAttributes(&fa, canny_uf_hyst_smem_kernel<false>);
         budget = optin - (int)fa.sharedSizeBytes - 1024;
-        if (budget > 0 && cudaFuncSetAttribute(canny_uf_hyst_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               budget) != cudaSuccess)
+        if (budget > 0 && (cudaFuncSetAttribute(canny_uf_hyst_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                budget) != cudaSuccess ||
+                           cudaFuncSetAttribute(canny_uf_hyst_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                budget) != cudaSuccess))
             budget = 0;
         cudaGetLastError();
     }
-    const long long HW = (long long)H * W;
-    const long long nW = (HW + 31) / 32, nW2 = (nW + 1) / 2;
+    const long long nW = (long long)H * ((W + 31) / 32), nW2 = (nW + 1) / 2;  // bitmap rows padded to whole words
     // [reachable-set bitmap][rank][region X][flood worklists]; region X is the candidate bitmap during the flood,
-    // then parent (2 B) + edge level (1 B) + flag (1 bit) per pixel of the reachable set
+    // then parent (2 B) + edge level (1 B) + flag (1 bit) per pixel of the reachable set.  BIG: region X only.
     const long long bitmapB = align_up((size_t)nW * 4, 16), rankB = align_up((size_t)nW2 * 2, 16);
-    const long long workB = 2 * kWorkCap * sizeof(unsigned short);
-    const long long fixed = bitmapB + rankB + workB + 64;
-    const long long regionX = (long long)budget - fixed;
-    long long cap = regionX * 8 / 25 - 64;
-    if (cap > 65535) cap = 65535;
-    if (regionX >= bitmapB && cap >= 2048 && (W % 32) == 0 && nW < 65536 && !getenv("MTE_HYST_L2")) {
+    if ((W % 16) == 0 && budget > 0 && nW * 32 < (1LL << 31) && !getenv("MTE_HYST_L2")) {
+        long long workB = 2 * kWorkCap * sizeof(unsigned short);
+        long long regionX = (long long)budget - (bitmapB + rankB + workB + 64);
+        long long cap = regionX * 8 / 25 - 64;
+        bool big = !(regionX >= bitmapB && cap >= 8192 && nW < 65536) || getenv("MTE_HYST_BIG");
+        unsigned oX = (unsigned)(bitmapB + rankB);
+        if (big) {
+            workB = 2 * kWorkCap * sizeof(unsigned);
+            regionX = (long long)budget - (workB + 64);
+            cap = regionX * 8 / 25 - 64;
+            oX = 0;
+        }
+        if (cap > 65535) cap = 65535;
         cap &= ~31LL;
         P.cap = (int)cap;
         P.oRank = (unsigned)bitmapB;
-        P.oParent = P.oRank + (unsigned)rankB;
+        P.oParent = oX;
         P.oFlag = P.oParent + (unsigned)align_up((size_t)cap * 2, 16);
         P.oEc = P.oFlag + (unsigned)align_up((size_t)cap / 8 + 4, 16);
         const unsigned endX = P.oParent + (unsigned)(regionX & ~15LL);
         P.oWork = endX;
         const size_t smem = (size_t)endX + workB;
         P.todo = reinterpret_cast<int *>(w + 3 * align_up(px * 4, 256) + align_up(px, 256));
-        canny_uf_hyst_smem_kernel<<<N, kUfThreads, smem, st>>>(P);
+        if (big) canny_uf_hyst_smem_kernel<true><<<N, kUfThreads, smem, st>>>(P);
+        else canny_uf_hyst_smem_kernel<false><<<N, kUfThreads, smem, st>>>(P);
         MTE_RETURN_IF_CUDA_ERROR();
     }
     canny_uf_hyst_kernel<<<N, kUfThreads, 0, st>>>(P);

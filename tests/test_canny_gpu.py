@@ -113,3 +113,24 @@ def test_hysteresis_fallback_when_reachable_set_exceeds_shared_memory():
         for k, img in enumerate((noise, smooth)):
             assert np.array_equal(edges[t, k], cv2.Canny(img, lo, hi)), (t, k)
     assert int((edges[2, 0] > 0).sum()) > 60000
+
+
+@pytest.mark.parametrize("force_big", [False, True])
+@pytest.mark.parametrize("shape", [(96, 1296), (64, 48), (200, 16), (384, 1280)])
+def test_hysteresis_padded_rows_and_global_bitmap_mode(shape, force_big, monkeypatch):
+    """Shared-memory hysteresis on widths that are multiples of 16 but not of 32 (bitmap rows padded to whole words,
+    the DDAD width 1936 is one) and with the bitmaps forced into the image's global scratch (the mode DDAD-size planes
+    take): bit-exact with cv2.Canny for every nested pair."""
+    from mindtheedge_b200.edge import canny_from_depth
+    from oracle.canny import quantise_depth
+    if force_big:
+        monkeypatch.setenv("MTE_HYST_BIG", "1")
+    H, W = shape
+    depths = np.stack([scene(H, W, 21 + k) for k in range(3)])
+    depths[2] = np.random.default_rng(9).uniform(0, 90, (H, W)).astype(np.float32)
+    pairs = [(int(t / 2), int(t)) for t in range(240, 19, -20)]
+    levels = canny_from_depth(torch.from_numpy(depths).cuda(), pairs, want_edges=False, want_levels=True).cpu().numpy()
+    for n in range(3):
+        q = quantise_depth(depths[n])
+        for k, (lo, hi) in enumerate(pairs):
+            assert np.array_equal((levels[n] <= k) * 255, cv2.Canny(q, lo, hi)), (n, k)
