@@ -83,11 +83,26 @@ __global__ void __launch_bounds__(kThreads) canny_nms_kernel(const T *__restrict
     const T *src = depth + (size_t)img * H * W;
 
     for (int v = threadIdx.x; v <= kMaxMag; v += kThreads) lut[v] = glut[v];
-    // A: q[r][c] = pixel (y0 + r - 2, x0 + c - 4), columns 2 .. TW + 5 used
-    for (int i = threadIdx.x; i < (TH + 4) * (TW + 4); i += kThreads) {
-        const int r = i / (TW + 4), c = i - r * (TW + 4) + 2;
-        const int y = min(max(y0 + r - 2, 0), H - 1), x = min(max(x0 + c - 4, 0), W - 1);
-        q[r][c] = quantise<T>(src[(size_t)y * W + x], lo, hi, factor);
+    // A: q[r][c] = pixel (y0 + r - 2, x0 + c - 4), columns 2 .. TW + 5 used.  Groups of four columns: one 128-bit
+    //    load and one 32-bit shared store when the group lies inside the image (fp32 planes with W % 4 == 0)
+    const bool vec4 = std::is_same<T, float>::value && (W % 4) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    for (int i = threadIdx.x; i < (TH + 4) * (QS / 4); i += kThreads) {
+        const int r = i / (QS / 4), c = (i - r * (QS / 4)) * 4;
+        const int y = min(max(y0 + r - 2, 0), H - 1), xg = x0 + c - 4;
+        const T *row = src + (size_t)y * W;
+        unsigned pk = 0;
+        if (vec4 && xg >= 0 && xg + 3 < W) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(row + xg));
+            pk = (unsigned)quantise<float>(v.x, (float)lo, (float)hi, (float)factor) |
+                 ((unsigned)quantise<float>(v.y, (float)lo, (float)hi, (float)factor) << 8) |
+                 ((unsigned)quantise<float>(v.z, (float)lo, (float)hi, (float)factor) << 16) |
+                 ((unsigned)quantise<float>(v.w, (float)lo, (float)hi, (float)factor) << 24);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                pk |= (unsigned)quantise<T>(row[min(max(xg + k, 0), W - 1)], lo, hi, factor) << (8 * k);
+        }
+        *reinterpret_cast<unsigned *>(&q[r][c]) = pk;
     }
     __syncthreads();
     // B: mag[r][c] = pixel (y0 + r - 1, x0 + c - 2); groups of 4 columns c = 4k .. 4k+3 cover columns 0 .. TW + 3
@@ -95,9 +110,16 @@ __global__ void __launch_bounds__(kThreads) canny_nms_kernel(const T *__restrict
         const int r = i / (MS / 4), c = (i - r * (MS / 4)) * 4;
         // q columns c+1 .. c+6 around the four centres c+2 .. c+5 (q column = mag column + 2), rows r .. r+2
         int V[6], D[6];
+        unsigned wq[3][2];  // the eight bytes c .. c+7 of the three rows as words (two loads instead of six)
+#pragma unroll
+        for (int rr = 0; rr < 3; rr++) {
+            wq[rr][0] = *reinterpret_cast<const unsigned *>(&q[r + rr][c]);
+            wq[rr][1] = *reinterpret_cast<const unsigned *>(&q[r + rr][c + 4]);
+        }
+        auto qb = [&](int rr, int k) -> int { return (int)((wq[rr][(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xFFu); };
 #pragma unroll
         for (int k = 0; k < 6; k++) {
-            const int a = q[r][c + 1 + k], m = q[r + 1][c + 1 + k], b = q[r + 2][c + 1 + k];
+            const int a = qb(0, k), m = qb(1, k), b = qb(2, k);
             V[k] = a + 2 * m + b;   // vertical [1 2 1] column sum
             D[k] = b - a;           // vertical difference
         }
