@@ -685,7 +685,7 @@ constexpr int kEndsCap = 2048;  // free GT pixels recorded per phase (further on
 
 struct SweepLayout {
     int nW, capP, capQ;
-    unsigned oBits, oRank, oPpix, oMateP, oClaimP, oFa, oRootP, oRflag, oMateQ, oParentQ, oStamp, oEnds, total;
+    unsigned oBits, oRank, oPpix, oMateP, oFa, oRootP, oRflag, oMateQ, oParentQ, oStamp, oEnds, total;
 };
 
 
@@ -706,7 +706,6 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
     unsigned short *qrank = reinterpret_cast<unsigned short *>(dyn + SL.oRank);
     unsigned *ppix = reinterpret_cast<unsigned *>(dyn + SL.oPpix);
     unsigned short *mateP = reinterpret_cast<unsigned short *>(dyn + SL.oMateP);
-    unsigned short *claimP = reinterpret_cast<unsigned short *>(dyn + SL.oClaimP);
     unsigned short *fa = reinterpret_cast<unsigned short *>(dyn + SL.oFa);
     unsigned short *mateQ = reinterpret_cast<unsigned short *>(dyn + SL.oMateQ);
     unsigned short *parentQ = reinterpret_cast<unsigned short *>(dyn + SL.oParentQ);
@@ -730,7 +729,9 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
     };
 
     auto rflag_get = [&](int pi) -> unsigned { return (((volatile unsigned *)rflagW)[pi >> 2] >> (8 * (pi & 3))) & 0xFFu; };
-    auto rflag_or = [&](int pi, unsigned f) { atomicOr(&rflagW[pi >> 2], f << (8 * (pi & 3))); };
+    auto rflag_or = [&](int pi, unsigned f) -> unsigned {  // returns the flags before the update
+        return (atomicOr(&rflagW[pi >> 2], f << (8 * (pi & 3))) >> (8 * (pi & 3))) & 0xFFu;
+    };
     // Is window pixel q a GT pixel, and which id does it have?  The rank is kept per 64 window pixels (two bitmap
     // words); the word pair and the rank are fetched together, before the bit is known: ONE shared-memory round trip
     // on the chain of a hop instead of two (the bitmap is padded to whole 16-byte groups).
@@ -889,7 +890,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
         // can never be matched later (Kuhn), are never reached as somebody's mate, and are dropped after every chunk.
         const bool compact = nPall > SL.capP;
         if (!compact)
-            for (int k = threadIdx.x; k < nPall; k += kSwThreads) { ppix[k] = pack_yx(__ldcg(gpix + k)); mateP[k] = kFree; claimP[k] = 0; }
+            for (int k = threadIdx.x; k < nPall; k += kSwThreads) { ppix[k] = pack_yx(__ldcg(gpix + k)); mateP[k] = kFree; }
         // ---- rank: exclusive prefix popcount over pairs of bitmap words
         {
             const int nW2 = (SL.nW + 1) >> 1;
@@ -930,7 +931,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                 const int n = min(G1 - cur, SL.capP - nLive);
                 p0 = nLive; p1 = nLive + n;
                 for (int k = threadIdx.x; k < n; k += kSwThreads) {
-                    ppix[p0 + k] = pack_yx(__ldcg(gpix + cur + k)); mateP[p0 + k] = kFree; claimP[p0 + k] = 0;
+                    ppix[p0 + k] = pack_yx(__ldcg(gpix + cur + k)); mateP[p0 + k] = kFree;
                 }
                 cur += n;
                 __syncthreads();
@@ -1045,9 +1046,13 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                                                     if (claimed) {
                                                         parentQ[qi] = (unsigned short)pi;
                                                         if (mq == kFree) {
-                                                            const int es = atomicAdd(&sEnds, 1);
-                                                            if (es < kEndsCap) ends[es] = (unsigned short)qi;
-                                                            rflag_or(root, RF_FOUND);
+                                                            // only the FIRST free GT pixel of a tree is recorded: trees are
+                                                            // vertex-disjoint, so the recorded paths are too and can be
+                                                            // flipped without a claim walk
+                                                            if (!(rflag_or(root, RF_FOUND) & RF_FOUND)) {
+                                                                const int es = atomicAdd(&sEnds, 1);
+                                                                if (es < kEndsCap) ends[es] = (unsigned short)qi;
+                                                            }
                                                         } else {
                                                             rootP[mq] = (unsigned short)root;
                                                             succ = mq;
@@ -1105,20 +1110,8 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                     __syncthreads();
                     if (nEnds == 0) { tick(8); break; }
                     for (int ei = threadIdx.x; ei < nEnds; ei += kSwThreads) {
-                        const int qEnd = ends[ei];
-                        int q = qEnd;
-                        bool ok = true;
-                        for (;;) {  // claim walk
-                            const int pi = parentQ[q];
-                            const unsigned short c = claimP[pi];
-                            if (c == phase || cas16(&claimP[pi], c, phase) != c) { ok = false; break; }
-                            const unsigned short mp = mateP[pi];
-                            if (mp == kFree) break;
-                            q = mp;
-                        }
-                        if (!ok) continue;
-                        q = qEnd;
-                        for (;;) {  // flip walk
+                        int q = ends[ei];
+                        for (;;) {  // flip walk (one path per tree, see above)
                             const int pi = parentQ[q];
                             const unsigned short prev = mateP[pi];
                             mateP[pi] = (unsigned short)q;
@@ -1151,7 +1144,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                     for (int wv = 0; wv < kSwWarps; wv++) { const int c = sScan[wv]; if (wv < warp) off += c; tot += c; }
                     if (keep) {
                         const int d = off + __popc(bal & ((1u << lane) - 1u));
-                        ppix[d] = px; mateP[d] = mp; claimP[d] = 0;
+                        ppix[d] = px; mateP[d] = mp;
                         mateQ[mp] = (unsigned short)d;
                     }
                     kept += tot;
@@ -1250,8 +1243,8 @@ static SweepLayout sweep_layout(int h, int w, int budget) {
     const long long hw = (long long)h * w;
     S.nW = (int)((hw + 31) / 32);
     const long long fixed = (long long)S.nW * 4 + (long long)S.nW + 2 * kEndsCap + 512;
-    // 13 B per predicted vertex, 8 B per GT vertex, equal capacities
-    const long long cap = (budget - fixed) / 21;
+    // 11 B per predicted vertex, 8 B per GT vertex, equal capacities
+    const long long cap = (budget - fixed) / 19;
     if (cap < 512) return S;
     S.capP = S.capQ = (int)(cap > 0xFFF0 ? 0xFFF0 : cap) & ~7;
     unsigned o = 0;
@@ -1260,7 +1253,6 @@ static SweepLayout sweep_layout(int h, int w, int budget) {
     S.oRank = take(((S.nW + 1) / 2) * 2);
     S.oPpix = take(S.capP * 4);
     S.oMateP = take(S.capP * 2);
-    S.oClaimP = take(S.capP * 2);
     S.oFa = take(S.capP * 2);
     S.oRootP = take(S.capP * 2);
     S.oRflag = take(S.capP + 4);

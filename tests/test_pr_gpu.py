@@ -119,7 +119,7 @@ def test_soft_map_99_threshold_sweep_vs_oracle(dtype):
 
 @pytest.mark.parametrize("pred_density,gt_density", [(0.06, 0.015), (0.02, 0.08), (0.07, 0.04)])
 def test_sweep_matcher_capacity_paths_vs_oracle(pred_density, gt_density):
-    """KITTI crop window with more boundary pixels than the sweep matcher keeps in shared memory (~8.4 k per side):
+    """KITTI crop window with more boundary pixels than the sweep matcher keeps in shared memory (~9.3 k per side):
     many predicted pixels -> its compact mode (only matched pixels + a chunk resident); many GT pixels -> the image's
     problems overflow to the per-problem kernels.  Counts of every threshold must still equal independent matchings."""
     from mindtheedge_b200.eval_depth_edges import pr_counts
@@ -138,7 +138,7 @@ def test_sweep_matcher_capacity_paths_vs_oracle(pred_density, gt_density):
     thr = np.array([0.15, 0.3, 0.45, 0.6, 0.75, 0.9])
     win = (slice(crop[2], crop[3]), slice(crop[0], crop[1]))
     n_pred, n_gt = int((strength[win] >= thr[0]).sum()), int(gt[win].sum())
-    assert max(n_pred, n_gt) > 8500, (n_pred, n_gt)           # the case really exceeds the resident capacity
+    assert max(n_pred, n_gt) > 9500, (n_pred, n_gt)           # the case really exceeds the resident capacity
     c = pr_counts(torch.from_numpy(strength)[None].cuda(), torch.from_numpy(gt)[None].cuda(), thr, max_dist=0.002,
                   crop=crop).cpu().numpy()
     ref = np.zeros((len(thr), 4), np.int64)
