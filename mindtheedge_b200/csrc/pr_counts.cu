@@ -1015,18 +1015,24 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                         int pi = my;
                         const int root = rootP[pi];  // a successor inherits the tree of its predecessor
                         const unsigned mine = ((unsigned)phase << 16) | (unsigned)root;
+                        unsigned p = ppix[pi];
+                        unsigned found = rflag_get(root) & RF_FOUND;
                         for (;;) {  // a warp keeps ONE successor and goes on with it directly (chains along contours
                                     // would otherwise pay a queue round trip per hop); the others are published.
                                     // The hop is a chain of dependent shared-memory round trips, so everything whose
-                                    // address is known early is loaded early (position + tree flag together, mate next
-                                    // to the stamp: the matching does not change during a phase).
+                                    // address is known early is loaded early: the mate and ITS position next to the
+                                    // stamp (the matching does not change during a phase), so the next hop starts with
+                                    // its probes; the "tree already found a free GT pixel" flag is only a hint to stop
+                                    // growing and is read one hop ahead, off the chain.
                             int keep = -1;
-                            const unsigned p = ppix[pi];
-                            if (!(rflag_get(root) & RF_FOUND)) {
+                            unsigned keepP = 0u;
+                            const unsigned foundNext = rflag_get(root) & RF_FOUND;
+                            if (!found) {
                                 const int py = (int)(p >> 16), px = (int)(p & 0xFFFFu);
                                 for (int k0 = 0; k0 < noff; k0 += 32) {
                                     const int k = k0 + lane;
                                     int succ = -1;
+                                    unsigned succP = 0u;
                                     if (k < noff) {
                                         const short2 o = k0 == 0 ? off0 : sOff[k];
                                         const int qy = py + o.y, qx = px + o.x;
@@ -1037,6 +1043,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                                                 unsigned st = stamp[qi];
                                                 const unsigned short mq = mateQ[qi];
                                                 if (st != kDeadStamp) {
+                                                    if (mq != kFree) succP = ppix[mq];
                                                     bool claimed = false;
                                                     if ((st >> 16) != phase) {
                                                         const unsigned old = atomicCAS(&stamp[qi], st, mine);
@@ -1067,6 +1074,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                                     unsigned m = __ballot_sync(MTE_FULL_MASK, succ >= 0);
                                     if (m && keep < 0) {
                                         keep = __shfl_sync(MTE_FULL_MASK, succ, __ffs(m) - 1);
+                                        keepP = __shfl_sync(MTE_FULL_MASK, succP, __ffs(m) - 1);
                                         m &= m - 1;
                                     }
                                     if (m) {
@@ -1085,6 +1093,8 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                             if (P.stats && lane == 0) atomicAdd(P.stats + 2, 1u);
                             if (keep < 0) break;
                             pi = keep;
+                            p = keepP;
+                            found = foundNext;
                         }
                         __syncwarp();
                         if (lane == 0) {
