@@ -676,7 +676,7 @@ __global__ void __launch_bounds__(kSmThreads, 1) match_smem_kernel(const __grid_
 // ---------------------------------------------------------------------------
 constexpr unsigned kDeadStamp = 0xFFFFFFFFu;   // GT stamp word: phase << 16 | root (predicted vertex id of the tree)
 constexpr unsigned short kFailed = 0xFFFD;     // predicted pixel whose search failed conclusively (Kuhn: for good)
-enum { RF_FOUND = 1u, RF_BLOCKED = 2u };
+enum { RF_FOUND = 1u, RF_CLASS_FOUND = 2u };
 #ifndef MTE_SWEEP_THREADS
 #define MTE_SWEEP_THREADS 512
 #endif
@@ -685,7 +685,7 @@ constexpr int kEndsCap = 2048;  // free GT pixels recorded per phase (further on
 
 struct SweepLayout {
     int nW, capP, capQ;
-    unsigned oBits, oRank, oPpix, oMateP, oFa, oRootP, oRflag, oMateQ, oParentQ, oStamp, oEnds, total;
+    unsigned oBits, oRank, oPpix, oMateP, oClassP, oFa, oRootP, oRflag, oMateQ, oParentQ, oStamp, oEnds, total;
 };
 
 
@@ -707,6 +707,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
     unsigned *ppix = reinterpret_cast<unsigned *>(dyn + SL.oPpix);
     unsigned short *mateP = reinterpret_cast<unsigned short *>(dyn + SL.oMateP);
     unsigned short *fa = reinterpret_cast<unsigned short *>(dyn + SL.oFa);
+    unsigned short *classP = reinterpret_cast<unsigned short *>(dyn + SL.oClassP);  // union-find over the roots of a phase
     unsigned short *mateQ = reinterpret_cast<unsigned short *>(dyn + SL.oMateQ);
     unsigned short *parentQ = reinterpret_cast<unsigned short *>(dyn + SL.oParentQ);
     unsigned *stamp = reinterpret_cast<unsigned *>(dyn + SL.oStamp);
@@ -731,6 +732,30 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
     auto rflag_get = [&](int pi) -> unsigned { return (((volatile unsigned *)rflagW)[pi >> 2] >> (8 * (pi & 3))) & 0xFFu; };
     auto rflag_or = [&](int pi, unsigned f) -> unsigned {  // returns the flags before the update
         return (atomicOr(&rflagW[pi >> 2], f << (8 * (pi & 3))) >> (8 * (pi & 3))) & 0xFFu;
+    };
+    // Trees of a phase that run into each other are put into one class (union-find over their roots, path halving,
+    // larger id under smaller): what one of them could not enter, the other explored, so a class none of whose trees
+    // found a free GT pixel is closed under alternating reachability as a whole (see the phase epilogue).
+    auto class_find = [&](int x) -> int {
+        volatile unsigned short *cp = classP;
+        int p = cp[x];
+        while (p != x) {
+            const int gp = cp[p];
+            if (gp == p) return p;
+            cp[x] = (unsigned short)gp;
+            x = gp;
+            p = cp[x];
+        }
+        return x;
+    };
+    auto class_union = [&](int a, int b) {
+        for (;;) {
+            a = class_find(a);
+            b = class_find(b);
+            if (a == b) return;
+            if (a < b) { const int t = a; a = b; b = t; }
+            if (cas16(&classP[a], (unsigned short)a, (unsigned short)b) == (unsigned short)a) return;
+        }
     };
     // Is window pixel q a GT pixel, and which id does it have?  The rank is kept per 64 window pixels (two bitmap
     // words); the word pair and the rank are fetched together, before the bit is known: ONE shared-memory round trip
@@ -976,7 +1001,11 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                         int wbase = 0;
                         if (lane == 0 && m) wbase = atomicAdd(&sCntA, __popc(m));
                         wbase = __shfl_sync(MTE_FULL_MASK, wbase, 0);
-                        if (fr) { fa[wbase + __popc(m & ((1u << lane) - 1))] = (unsigned short)pi; rootP[pi] = (unsigned short)pi; }
+                        if (fr) {
+                            fa[wbase + __popc(m & ((1u << lane) - 1))] = (unsigned short)pi;
+                            rootP[pi] = (unsigned short)pi;
+                            classP[pi] = (unsigned short)pi;
+                        }
                     }
                     // flag bytes of this stage's pixels (only roots use theirs)
                     for (int i = (p0 >> 2) + threadIdx.x; i <= ((p1 - 1) >> 2); i += kSwThreads) rflagW[i] = 0u;
@@ -986,8 +1015,10 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                     if (P.stats && threadIdx.x == 0) { atomicAdd(P.stats + 0, 1u); atomicAdd(P.stats + 3, (unsigned)nRoots); }
                     // asynchronous alternating forest (see match_smem_kernel); dead GT vertices are walls.  Every GT
                     // stamp carries the tree (root) that claimed it: a tree that has found a free GT pixel stops
-                    // growing, and a tree that found none WITHOUT ever running into another tree's vertices is closed
-                    // under alternating reachability, hence dead, whatever the other trees of the phase do.
+                    // growing; trees that run into each other's vertices are joined into a class.  The trees of a
+                    // class without any find have, between them, expanded everything reachable from their roots and
+                    // met no free GT pixel: the class is closed under alternating reachability, hence dead for good,
+                    // whatever the other trees of the phase do (a single tree that met nobody is the 1-tree case).
                     for (int i = nRoots + threadIdx.x; i < p1; i += kSwThreads) fa[i] = kFree;  // unpublished slots
                     if (threadIdx.x == 0) { sHead = 0; sTail = nRoots; sPending = nRoots; }
                     __syncthreads();
@@ -1017,6 +1048,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                         const unsigned mine = ((unsigned)phase << 16) | (unsigned)root;
                         unsigned p = ppix[pi];
                         unsigned found = rflag_get(root) & RF_FOUND;
+                        int lastOther = -1;  // the tree this lane last joined with root's (skips repeated unions)
                         for (;;) {  // a warp keeps ONE successor and goes on with it directly (chains along contours
                                     // would otherwise pay a queue round trip per hop); the others are published.
                                     // The hop is a chain of dependent shared-memory round trips, so everything whose
@@ -1065,7 +1097,8 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                                                             succ = mq;
                                                         }
                                                     } else if (st != kDeadStamp && (st & 0xFFFFu) != (unsigned)root) {
-                                                        rflag_or(root, RF_BLOCKED);
+                                                        const int other = (int)(st & 0xFFFFu);
+                                                        if (other != lastOther) { lastOther = other; class_union(root, other); }
                                                     }
                                                 }
                                             }
@@ -1105,17 +1138,26 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                     __syncthreads();
                     tick(7);
                     const int nEnds = min(sEnds, kEndsCap);
-                    // wall off the trees that failed conclusively (all of them when the phase found nothing) ...
+                    // a find anywhere in a class keeps the whole class alive (fa[0..nRoots) still holds the roots: the
+                    // queue is append-only)
+                    if (nEnds != 0) {
+                        for (int i = threadIdx.x; i < nRoots; i += kSwThreads) {
+                            const int rp = fa[i];
+                            if (rflag_get(rp) & RF_FOUND) rflag_or(class_find(rp), RF_CLASS_FOUND);
+                        }
+                        __syncthreads();
+                    }
+                    // wall off the classes that failed conclusively (all of them when the phase found nothing) ...
                     for (int k = threadIdx.x; k < nQ; k += kSwThreads) {
                         const unsigned st = stamp[k];
                         if (st != kDeadStamp && (st >> 16) == phase &&
-                            (nEnds == 0 || !(rflag_get((int)(st & 0xFFFFu)) & (RF_FOUND | RF_BLOCKED))))
+                            (nEnds == 0 || !(rflag_get(class_find((int)(st & 0xFFFFu))) & RF_CLASS_FOUND)))
                             stamp[k] = kDeadStamp;
                     }
-                    // ... and retire their roots (fa[0..nRoots) still holds them: the queue is append-only)
+                    // ... and retire their roots
                     for (int i = threadIdx.x; i < nRoots; i += kSwThreads) {
                         const int rp = fa[i];
-                        if (nEnds == 0 || !(rflag_get(rp) & (RF_FOUND | RF_BLOCKED))) mateP[rp] = kFailed;
+                        if (nEnds == 0 || !(rflag_get(class_find(rp)) & RF_CLASS_FOUND)) mateP[rp] = kFailed;
                     }
                     __syncthreads();
                     if (nEnds == 0) { tick(8); break; }
@@ -1253,8 +1295,8 @@ static SweepLayout sweep_layout(int h, int w, int budget) {
     const long long hw = (long long)h * w;
     S.nW = (int)((hw + 31) / 32);
     const long long fixed = (long long)S.nW * 4 + (long long)S.nW + 2 * kEndsCap + 512;
-    // 11 B per predicted vertex, 8 B per GT vertex, equal capacities
-    const long long cap = (budget - fixed) / 19;
+    // 13 B per predicted vertex, 8 B per GT vertex, equal capacities
+    const long long cap = (budget - fixed) / 21;
     if (cap < 512) return S;
     S.capP = S.capQ = (int)(cap > 0xFFF0 ? 0xFFF0 : cap) & ~7;
     unsigned o = 0;
@@ -1263,6 +1305,7 @@ static SweepLayout sweep_layout(int h, int w, int budget) {
     S.oRank = take(((S.nW + 1) / 2) * 2);
     S.oPpix = take(S.capP * 4);
     S.oMateP = take(S.capP * 2);
+    S.oClassP = take(S.capP * 2);
     S.oFa = take(S.capP * 2);
     S.oRootP = take(S.capP * 2);
     S.oRflag = take(S.capP + 4);
