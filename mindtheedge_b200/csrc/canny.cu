@@ -200,7 +200,7 @@ struct UfP {
     int *todo;            // [N] written by the shared-memory kernel: 1 = image left to the L2 kernel (nullptr = all)
     int cap;              // shared-memory kernel: candidate capacity
     unsigned long long *prof;  // optional per-section cycle counters (MTE_HYST_PROF)
-    unsigned oRank, oParent, oFlag, oEc, oWork;  // shared-memory kernel: byte offsets of its arrays behind the bitmap
+    unsigned oRank, oParent, oFlag, oEc, oPerm, oWork;  // shared-memory kernel: byte offsets of its arrays behind the bitmap
 };
 
 // find with path halving (every visited node is re-pointed to its grandparent; lock-free safe: a node only
@@ -382,8 +382,9 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
     int *merged = P.merged + base;
     // candidate ids are positions in the level-sorted list: "is a candidate at level t" is id < sEnd[t], the
     // per-candidate state (parent, edge level, flag) is indexed by id in shared memory and the per-level passes touch
-    // nothing else; only the neighbour lookup of step (i) goes raster rank -> id through a global table
-    unsigned short *perm = reinterpret_cast<unsigned short *>(P.parent + base);
+    // nothing else; the neighbour lookup of step (i) goes raster rank -> id through a table that is resident too (8
+    // scattered reads per candidate: from L2 they were a third of the unite pass)
+    unsigned short *perm = reinterpret_cast<unsigned short *>(dyn + P.oPerm);
     unsigned *qbits = BIG ? reinterpret_cast<unsigned *>(merged) : reinterpret_cast<unsigned *>(dyn);
     unsigned short *qrank = BIG ? reinterpret_cast<unsigned short *>(qbits + 2 * nW) : reinterpret_cast<unsigned short *>(dyn + P.oRank);
     unsigned short *parent = reinterpret_cast<unsigned short *>(dyn + P.oParent);
@@ -510,7 +511,11 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
     __syncthreads();
     const int nCand = sEnd[254];
     if (P.prof && threadIdx.x == 0) atomicAdd(P.prof + 8, (unsigned long long)nCand);
-    if (nCand > P.cap) {  // leave the image to the L2 kernel
+    // parked neighbour ids of the level passes: 16 B per candidate in the image's `merged` scratch (4 B per pixel),
+    // behind the global bitmaps when there are any
+    const size_t nidOff = BIG ? (((size_t)2 * nW * 4 + (size_t)nW2 * 2 + 15) & ~(size_t)15) : 0;
+    uint4 *nidBuf = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(merged) + nidOff);
+    if (nCand > P.cap || nidOff + (size_t)nCand * 16 > (size_t)HW * 4) {  // leave the image to the L2 kernel
         if (threadIdx.x == 0) P.todo[img] = 1;
         return;
     }
@@ -570,29 +575,62 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
     volatile unsigned short *vparent = parent;
     for (int t = 0; t < T; t++) {
         const int begin = t ? sEnd[t - 1] : 0, end = sEnd[t];
-        // (i) the pixels that become candidates at this level join their 8-neighbours that already are
+        // (i) the pixels that become candidates at this level join their 8-neighbours that already are.
+        //  (i-a) HOOK: a new pixel points straight at its first raster-preceding neighbour of the same level (W, NW, N,
+        //        NE).  New pixels are untouched singletons until this level, and the pointers run strictly backwards in
+        //        raster order, so plain stores build a forest: along a thin contour almost every same-level link is
+        //        made here without a find or a CAS (a level that holds most of the reachable set -- the strictest pair
+        //        on step edges -- otherwise has a thousand threads fighting over the roots of the same few chains:
+        //        0.75 M of 0.94 M unite cycles on the densest bench image).  The neighbour ids are parked in the
+        //        image's global scratch for (i-b).
         for (int k = begin + threadIdx.x; k < end; k += kUfThreads) {
             const int p = list[k];
             const int y = p / W, x = p - y * W;
-            int nid[8];
+            unsigned nid[8];
 #pragma unroll
             for (int d = 0; d < 8; d++) {  // all neighbour lookups first: the table reads overlap
                 const int dy = (d < 3) ? -1 : ((d < 5) ? 0 : 1);
                 const int dx = (d == 0 || d == 3 || d == 5) ? -1 : ((d == 1 || d == 6) ? 0 : 1);
                 const int yy = y + dy, xx = x + dx;
-                nid[d] = 0xFFFF;
+                nid[d] = 0xFFFFu;
                 if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
                 const int q = yy * WP + xx;  // bit index
-                if ((qbits[q >> 5] >> (q & 31)) & 1u) nid[d] = __ldcg(perm + qid(q));
+                if ((qbits[q >> 5] >> (q & 31)) & 1u) nid[d] = perm[qid(q)];
             }
+            // directions 0 NW, 1 N, 2 NE, 3 W precede the pixel in raster order
+            const int hookOrder[4] = {3, 0, 1, 2};
+            int hook = -1;
+#pragma unroll
+            for (int i = 3; i >= 0; i--)
+                if ((int)nid[hookOrder[i]] >= begin && (int)nid[hookOrder[i]] < end) hook = hookOrder[i];
+            if (hook >= 0) {
+                parent[k] = (unsigned short)nid[hook];
+                nid[hook] = 0xFFFFu;  // done
+            }
+            // same-level neighbours that FOLLOW the pixel unite from their own end
+#pragma unroll
+            for (int d = 4; d < 8; d++)
+                if ((int)nid[d] >= begin) nid[d] = 0xFFFFu;
+            nidBuf[k] = make_uint4(nid[0] | (nid[1] << 16), nid[2] | (nid[3] << 16), nid[4] | (nid[5] << 16), nid[6] | (nid[7] << 16));
+        }
+        __syncthreads();
+        //  a hook chain is as long as its contour; a few rounds of pointer jumping over a big level (plain loads and
+        //  stores: a node only ever moves to one of its ancestors) flatten it before the finds start
+        if (end - begin > kUfThreads) {
+            for (int round = 0; round < 6; round++) {
+                for (int k = begin + threadIdx.x; k < end; k += kUfThreads) vparent[k] = vparent[vparent[k]];
+                __syncthreads();
+            }
+        }
+        //  (i-b) the remaining links (earlier levels, junctions) by find + CAS
+        for (int k = begin + threadIdx.x; k < end; k += kUfThreads) {
+            const uint4 nb = __ldcg(nidBuf + k);
+            const unsigned nw[4] = {nb.x, nb.y, nb.z, nb.w};
 #pragma unroll
             for (int d = 0; d < 8; d++) {
-                if (nid[d] >= end) continue;  // not a candidate, or a candidate of a later level
-                if (nid[d] >= begin && nid[d] > k) continue;  // same level: the pair is united from its larger end
-#ifdef MTE_HYST_EXP
-                if (MTE_HYST_EXP == 1) continue;
-#endif
-                int a = k, b = nid[d];
+                const int n = (int)((nw[d >> 1] >> (16 * (d & 1))) & 0xFFFFu);
+                if (n >= end) continue;  // not a candidate, a candidate of a later level, or already dealt with
+                int a = k, b = n;
                 for (;;) {
                     a = ufs_find(vparent, a);
                     b = ufs_find(vparent, b);
@@ -605,6 +643,8 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
             }
         }
         __syncthreads();
+        if (P.prof && threadIdx.x == 0 && t < 12)  // per-level unite cycles | level size << 40 (scripts/hyst_levels.py, one image)
+            atomicAdd(P.prof + 16 + t, (unsigned long long)(clock64() - tk) + ((unsigned long long)(end - begin) << 40));
         tick(2);
         // (ii) flags follow the roots that were linked away (a node that ever carried a flag hands it to its current
         //      root: no list of merged roots, whose single shared counter serialised the unions); pixels that turn
@@ -693,18 +733,19 @@ int run_level_hysteresis(const unsigned char *cl, unsigned char *E, int N, int H
     }
     const long long nW = (long long)H * ((W + 31) / 32), nW2 = (nW + 1) / 2;  // bitmap rows padded to whole words
     // [reachable-set bitmap][rank][region X][flood worklists]; region X is the candidate bitmap during the flood,
-    // then parent (2 B) + edge level (1 B) + flag (1 bit) per pixel of the reachable set.  BIG: region X only.
+    // then parent (2 B) + edge level (1 B) + flag (1 bit) + rank -> id (2 B) per pixel of the reachable set.  BIG:
+    // region X only.
     const long long bitmapB = align_up((size_t)nW * 4, 16), rankB = align_up((size_t)nW2 * 2, 16);
     if ((W % 16) == 0 && budget > 0 && nW * 32 < (1LL << 31) && !getenv("MTE_HYST_L2")) {
         long long workB = 2 * kWorkCap * sizeof(unsigned short);
         long long regionX = (long long)budget - (bitmapB + rankB + workB + 64);
-        long long cap = regionX * 8 / 25 - 64;
+        long long cap = regionX * 8 / 41 - 64;
         bool big = !(regionX >= bitmapB && cap >= 8192 && nW < 65536) || getenv("MTE_HYST_BIG");
         unsigned oX = (unsigned)(bitmapB + rankB);
         if (big) {
             workB = 2 * kWorkCap * sizeof(unsigned);
             regionX = (long long)budget - (workB + 64);
-            cap = regionX * 8 / 25 - 64;
+            cap = regionX * 8 / 41 - 64;
             oX = 0;
         }
         if (cap > 65535) cap = 65535;
@@ -714,6 +755,7 @@ int run_level_hysteresis(const unsigned char *cl, unsigned char *E, int N, int H
         P.oParent = oX;
         P.oFlag = P.oParent + (unsigned)align_up((size_t)cap * 2, 16);
         P.oEc = P.oFlag + (unsigned)align_up((size_t)cap / 8 + 4, 16);
+        P.oPerm = P.oEc + (unsigned)align_up((size_t)cap, 16);
         const unsigned endX = P.oParent + (unsigned)(regionX & ~15LL);
         P.oWork = endX;
         const size_t smem = (size_t)endX + workB;

@@ -99,7 +99,7 @@ def test_long_weak_chain_crosses_many_tiles():
 
 def test_hysteresis_fallback_when_reachable_set_exceeds_shared_memory():
     """White-noise u8 plane at KITTI size with very low thresholds: > 100 k candidates connected to strong pixels, far
-    beyond what the shared-memory union-find holds (~40 k) -> the image is handed to the L2 kernel.  Bit-exact with
+    beyond what the shared-memory union-find holds (~25 k) -> the image is handed to the L2 kernel.  Bit-exact with
     cv2.Canny for every pair, alongside an ordinary image in the same batch (which stays on the fast path)."""
     import cv2
     from mindtheedge_b200.edge import canny_from_depth
