@@ -370,6 +370,7 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ int sHist[256], sEnd[256], sScan[kUfThreads];
     __shared__ int sCntA, sCntB, sFull;
+    __shared__ unsigned char sRep[256];
     using WL = typename std::conditional<BIG, unsigned, unsigned short>::type;  // worklist entry: a bitmap word index
     const int img = blockIdx.x;
     const int H = P.H, W = P.W, HW = H * W, T = P.T;
@@ -400,6 +401,24 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
         }
     };
     for (int i = threadIdx.x; i < 256; i += kUfThreads) sHist[i] = 0;
+    // sRep[m]: for a set m of neighbour positions (bit d: 0 NW, 1 N, 2 NE, 3 W, 4 E, 5 SW, 6 S, 7 SE), one representative
+    // (lowest position) per group of positions that are 8-adjacent to each other.  Neighbours from EARLIER levels that
+    // touch each other are already in one component, so a new pixel only has to join one of each group.
+    if (threadIdx.x < 256) {
+        const int m = threadIdx.x;
+        const int ny[8] = {-1, -1, -1, 0, 0, 1, 1, 1}, nx[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+        int lab[8];
+        for (int d = 0; d < 8; d++) lab[d] = d;
+        for (int it = 0; it < 8; it++)
+            for (int a = 0; a < 8; a++)
+                for (int b = 0; b < 8; b++)
+                    if (((m >> a) & 1) && ((m >> b) & 1) && abs(ny[a] - ny[b]) <= 1 && abs(nx[a] - nx[b]) <= 1 && lab[b] < lab[a])
+                        lab[a] = lab[b];
+        int r = 0;
+        for (int d = 0; d < 8; d++)
+            if (((m >> d) & 1) && lab[d] == d) r |= 1 << d;
+        sRep[m] = (unsigned char)r;
+    }
     __syncthreads();
     const bool vec = (reinterpret_cast<uintptr_t>(cl) & 15) == 0 && (reinterpret_cast<uintptr_t>(E) & 15) == 0;  // W % 16 == 0 (host)
     // ---- pass 1: bitmaps of the candidates (cbits) and of the pixels that are strong at some level (qbits = seed),
@@ -611,6 +630,14 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
 #pragma unroll
             for (int d = 4; d < 8; d++)
                 if ((int)nid[d] >= begin) nid[d] = 0xFFFFu;
+            // of the earlier-level neighbours that touch each other, one is enough
+            unsigned mOld = 0;
+#pragma unroll
+            for (int d = 0; d < 8; d++) mOld |= ((int)nid[d] < begin ? 1u : 0u) << d;
+            const unsigned drop = mOld & ~(unsigned)sRep[mOld];
+#pragma unroll
+            for (int d = 0; d < 8; d++)
+                if ((drop >> d) & 1u) nid[d] = 0xFFFFu;
             nidBuf[k] = make_uint4(nid[0] | (nid[1] << 16), nid[2] | (nid[3] << 16), nid[4] | (nid[5] << 16), nid[6] | (nid[7] << 16));
         }
         __syncthreads();
