@@ -508,12 +508,15 @@ def bench_auc(args, rank, world, device, steps=None, warmup=None):
         "e2e": {"value": round(px_per_step / (ms_e2e * 1e-3) / 1e6, 1), "unit": "Mpixel/s",
                 "h2d_bytes_per_step": int(depths.nbytes + gts.nbytes), "d2h_bytes_per_step": 12 * 4 * 8,
                 "ms_per_step": round(ms_e2e, 3), "auc": round(float(auc), 6)},
-        "gpu_launches_per_step": 5,
+        # canny_lut, canny_nms, canny_uf_hyst_smem, canny_uf_hyst (overflow images, exits at once when there are none),
+        # match_sweep, match (overflow problems, likewise)
+        "gpu_launches_per_step": 6,
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": recorded_traffic("auc_eval"),
-                     "kernel": "match_kernel (dominant) + canny_nms/hyst", "algorithmic_bytes_per_px": AUC_BYTES_PER_PX,
+                     "kernel": "match_sweep_kernel (dominant) + canny_uf_hyst_smem_kernel + canny_nms_kernel", "algorithmic_bytes_per_px": AUC_BYTES_PER_PX,
                      "peak_source": peak_src,
-                     "note": "the matcher is latency-bound graph work in L2, not an HBM stream"},
+                     "note": "matcher and hysteresis are latency-bound graph work in shared memory, one CTA per image: the step lasts "
+                             "as long as its slowest image (profiles/r01_notes.md), it is not an HBM stream"},
     }
 
 
