@@ -148,14 +148,25 @@ __global__ void __launch_bounds__(kThreads) canny_nms_kernel(const T *__restrict
         const int y = y0 + r, x = x0 + c;
         if (y >= H || x >= W) continue;
         unsigned oc = 0, os = 0;
+        // the 3 x 8 neighbourhood (u16 columns c .. c+7 of rows r .. r+2) as six 64-bit loads; the two neighbours of the
+        // sector are then SELECTED from registers (no data-dependent addresses, no branches)
+        unsigned nb[3][4];
+#pragma unroll
+        for (int rr = 0; rr < 3; rr++) {
+            const uint2 lo2 = *reinterpret_cast<const uint2 *>(&mag[r + rr][c]);
+            const uint2 hi2 = *reinterpret_cast<const uint2 *>(&mag[r + rr][c + 4]);
+            nb[rr][0] = lo2.x; nb[rr][1] = lo2.y; nb[rr][2] = hi2.x; nb[rr][3] = hi2.y;
+        }
+        auto at = [&](int rr, int j) -> int { return (int)((nb[rr][j >> 1] >> (16 * (j & 1))) & 0xFFFFu); };
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const unsigned short *ctr = &mag[r + 1][c + 2 + k];
-            const int pv = *ctr, m = pv & 0x7FF, sector = pv >> 11;
-            // neighbour offsets in u16 elements: horizontal (-1, +1), vertical (-MS, +MS), diagonals (-MS - s, +MS + s)
-            const int off = sector == 0 ? 1 : (sector == 1 ? MS : (sector == 2 ? MS + 1 : MS - 1));
-            const int n1 = ctr[-off] & 0x7FF, n2 = ctr[off] & 0x7FF;
-            const bool keep = m > n1 && (sector >= 2 ? m > n2 : m >= n2);
+            const int j = k + 2;  // centre column inside the 8
+            const int pv = at(1, j), m = pv & 0x7FF, sector = pv >> 11;
+            // sector 0: left / right, 1: up / down, 2: up-left / down-right, 3: up-right / down-left
+            const int a1 = sector == 0 ? at(1, j - 1) : (sector == 1 ? at(0, j) : (sector == 2 ? at(0, j - 1) : at(0, j + 1)));
+            const int a2 = sector == 0 ? at(1, j + 1) : (sector == 1 ? at(2, j) : (sector == 2 ? at(2, j + 1) : at(2, j - 1)));
+            const int n1 = a1 & 0x7FF, n2 = a2 & 0x7FF;
+            const bool keep = (m > n1) & ((m > n2) | ((sector < 2) & (m == n2)));
             const unsigned e = lut[keep ? m : 0];
             oc |= (e & 0xFFu) << (8 * k);
             os |= (e >> 8) << (8 * k);
