@@ -99,6 +99,32 @@ def test_matcher_oracle_vs_scipy():
     assert opr.match_count(np.zeros((5, 5)), np.ones((5, 5)), 0.1) == 0
 
 
+def test_min_cost_assignment_with_outliers_has_maximum_cardinality():
+    """Why the matcher is restated as a maximum-cardinality matching: py-bsds500's `correspond_pixels` solves
+    a min-cost perfect assignment in which every pixel may instead go to an outlier node at cost `outlier_cost * max_dist`
+    (100 x the largest real edge).  One more real pair replaces two outlier assignments by one edge that costs at most
+    `max_dist`, so the optimum always has the maximum number of real pairs.  Checked numerically with a dense assignment
+    solver on small random boundary maps: its number of real pairs equals the oracle's (and scipy's) matching size."""
+    from scipy.optimize import linear_sum_assignment
+    from oracle import pr_counts as opr
+    for k, (shape, md) in enumerate([((24, 30), 0.05), ((30, 30), 0.08), ((16, 48), 0.04), ((20, 20), 0.15)]):
+        pred, gt = random_boundary_maps(*shape, seed=40 + k)
+        R = opr.match_radius(shape, md)
+        P, Q = np.argwhere(pred != 0), np.argwhere(gt != 0)
+        n1, n2 = len(P), len(Q)
+        big, oc = 1e9, 100.0 * R
+        d = np.sqrt(((P[:, None, :] - Q[None, :, :]) ** 2).sum(-1))
+        cost = np.full((n1 + n2, n1 + n2), big)
+        cost[:n1, :n2] = np.where(d <= R, d, big)            # real edges within the radius
+        cost[:n1, n2:] = np.where(np.eye(n1) > 0, oc, big)   # predicted pixel i -> its outlier
+        cost[n1:, :n2] = np.where(np.eye(n2) > 0, oc, big)   # GT pixel j <- its outlier
+        cost[n1:, n2:] = 0.0                                 # outliers pair up for free
+        r, c = linear_sum_assignment(cost)
+        real = int(((r < n1) & (c < n2)).sum())
+        assert cost[r, c].max() < big
+        assert real == opr.match_count(pred, gt, md) == opr.match_count_scipy(pred, gt, md), (k, real)
+
+
 def test_pr_oracle_vs_reference_golden():
     from oracle import pr_counts as opr
     z = np.load(os.path.join(GOLDEN, "pr.npz"))
