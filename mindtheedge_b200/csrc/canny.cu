@@ -751,21 +751,16 @@ int run_level_hysteresis(const unsigned char *cl, unsigned char *E, int N, int H
     P.flag = reinterpret_cast<unsigned char *>(w + 3 * align_up(px * 4, 256));
     P.todo = nullptr;
     P.cap = 0;
-    P.prof = getenv("MTE_HYST_PROF") ? reinterpret_cast<unsigned long long *>(w + hysteresis_scratch_bytes(N, H, W) - 256) : nullptr;
+    P.prof = debug_knob("MTE_HYST_PROF") ? reinterpret_cast<unsigned long long *>(w + hysteresis_scratch_bytes(N, H, W) - 256) : nullptr;
     // shared-memory kernel first: bitmaps next to the per-candidate state when they leave room for a useful number of
     // candidates, otherwise (BIG) bitmaps in the image's global scratch and only the per-candidate state resident
-    static int budget = -1;
-    if (budget < 0) {
-        int dev = 0, optin = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    int budget;
+    {
         cudaFuncAttributes fa;
         cudaFuncGetAttributes(&fa, canny_uf_hyst_smem_kernel<false>);
-        budget = optin - (int)fa.sharedSizeBytes - 1024;
-        if (budget > 0 && (cudaFuncSetAttribute(canny_uf_hyst_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                budget) != cudaSuccess ||
-                           cudaFuncSetAttribute(canny_uf_hyst_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                budget) != cudaSuccess))
+        budget = dev_info().smemOptin - (int)fa.sharedSizeBytes - 1024;
+        if (budget > 0 && (opt_in_smem((const void *)canny_uf_hyst_smem_kernel<false>, budget) != cudaSuccess ||
+                           opt_in_smem((const void *)canny_uf_hyst_smem_kernel<true>, budget) != cudaSuccess))
             budget = 0;
         cudaGetLastError();
     }
@@ -774,11 +769,11 @@ int run_level_hysteresis(const unsigned char *cl, unsigned char *E, int N, int H
     // then parent (2 B) + edge level (1 B) + flag (1 bit) + rank -> id (2 B) per pixel of the reachable set.  BIG:
     // region X only.
     const long long bitmapB = align_up((size_t)nW * 4, 16), rankB = align_up((size_t)nW2 * 2, 16);
-    if ((W % 16) == 0 && budget > 0 && nW * 32 < (1LL << 31) && !getenv("MTE_HYST_L2")) {
+    if ((W % 16) == 0 && budget > 0 && nW * 32 < (1LL << 31) && !debug_knob("MTE_HYST_L2")) {
         long long workB = 2 * kWorkCap * sizeof(unsigned short);
         long long regionX = (long long)budget - (bitmapB + rankB + workB + 64);
         long long cap = regionX * 8 / 41 - 64;
-        bool big = !(regionX >= bitmapB && cap >= 8192 && nW < 65536) || getenv("MTE_HYST_BIG");
+        bool big = !(regionX >= bitmapB && cap >= 8192 && nW < 65536) || debug_knob("MTE_HYST_BIG");
         unsigned oX = (unsigned)(bitmapB + rankB);
         if (big) {
             workB = 2 * kWorkCap * sizeof(unsigned);
@@ -834,7 +829,7 @@ static int run_pairs(const void *depth, int dtype, int N, int H, int W, double m
 
     int rc = run_level_hysteresis(cl, E, N, H, W, thr.n, ws + L.offActive, st);
     if (rc) return rc;
-    int sms = kNumSMs;
+    int sms = num_sms();
     if (edges) {
         const size_t n = (size_t)N * H * W;
         const int g = (int)((n + 255) / 256 < (size_t)sms * 16 ? (n + 255) / 256 : (size_t)sms * 16);

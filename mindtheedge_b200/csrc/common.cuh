@@ -2,6 +2,11 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+
+#include <mutex>
+#include <utility>
+#include <vector>
 
 #include "../../include/mte.h"
 
@@ -15,7 +20,63 @@
 
 namespace mte {
 
-constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+// ---- per-device hardware facts (read-only after the first query; no algorithmic state) ---------------------
+// The library may be used on several devices of one process: everything that depends on the device (SM count,
+// shared-memory opt-in limit, the per-function MaxDynamicSharedMemorySize attribute) is keyed by the CURRENT
+// device's ordinal, never cached process-wide.
+struct DevInfo {
+    int sms;         // multiprocessor count (148 on B200: 2 dies x 74)
+    int smemOptin;   // cudaDevAttrMaxSharedMemoryPerBlockOptin
+};
+inline int current_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d;
+}
+inline DevInfo dev_info() {
+    constexpr int kMaxDev = 64;
+    static DevInfo cache[kMaxDev];
+    static bool have[kMaxDev];
+    static std::mutex mu;
+    const int d = current_device();
+    std::lock_guard<std::mutex> lock(mu);
+    if (d >= 0 && d < kMaxDev && have[d]) return cache[d];
+    DevInfo v{148, 232448};
+    cudaDeviceGetAttribute(&v.sms, cudaDevAttrMultiProcessorCount, d);
+    cudaDeviceGetAttribute(&v.smemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d);
+    if (v.sms < 1) v.sms = 1;
+    if (d >= 0 && d < kMaxDev) { cache[d] = v; have[d] = true; }
+    return v;
+}
+inline int num_sms() { return dev_info().sms; }
+
+// Raise a kernel's dynamic shared-memory limit ONCE PER (function, device): the attribute is per device, so a
+// process-wide "done" flag would leave the second GPU of a process at the 48 KB default.
+inline cudaError_t opt_in_smem(const void *func, int bytes) {
+    static std::mutex mu;
+    static std::vector<std::pair<const void *, long long>> done;  // (function, device << 32 | bytes)
+    const int d = current_device();
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto &e : done)
+        if (e.first == func && (int)(e.second >> 32) == d) {
+            if ((int)(e.second & 0xffffffffLL) >= bytes) return cudaSuccess;
+            const cudaError_t r = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            if (r == cudaSuccess) e.second = ((long long)d << 32) | (unsigned)bytes;
+            return r;
+        }
+    const cudaError_t r = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (r == cudaSuccess) done.emplace_back(func, ((long long)d << 32) | (unsigned)bytes);
+    return r;
+}
+
+// Tuning / diagnostic switches exist ONLY in builds made with -DMTE_DEBUG_KNOBS (scripts/ use them through
+// MTE_NVCC_DEFS); the release library never reads the environment, so no call's result or algorithm can depend on
+// process-global state.
+#ifdef MTE_DEBUG_KNOBS
+inline const char *debug_knob(const char *name) { return getenv(name); }
+#else
+inline const char *debug_knob(const char *) { return nullptr; }
+#endif
 
 // Start of every workspace: self-resetting tickets / flags (256 B), then, inside the zero-initialised 64 KB
 // header, the per-image accumulators of the edge-loss forward at kWsAccumOffset.

@@ -222,7 +222,7 @@ static int run(const T *prob, int N, int H, int W, int do_nms, int do_hyst, doub
     MTE_RETURN_IF_CUDA_ERROR();
     if (!wantVal) return MTE_OK;
     const size_t n = (size_t)N * H * W;
-    const int grid = (int)((n + 255) / 256 < (size_t)kNumSMs * 16 ? (n + 255) / 256 : (size_t)kNumSMs * 16);
+    const int grid = (int)((n + 255) / 256 < (size_t)num_sms() * 16 ? (n + 255) / 256 : (size_t)num_sms() * 16);
     if (do_hyst) {
         int rc = canny::run_level_hysteresis(cl, E, N, H, W, 1, ws + L.offActive, st);
         if (rc) return rc;

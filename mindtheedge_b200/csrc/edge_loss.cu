@@ -138,7 +138,7 @@ static int validate(const mte_loss_scale_t *sc, int n) {
 
 // Lay out CTAs / workspace.  bwd == true uses the overlapped 30-lane strips.
 static bool can_use_stash(const mte_loss_scale_t *sc, int n, const mte_loss_attrs_t *at) {
-    if (!at || !at->is_grad || getenv("MTE_LOSS_NO_STASH")) return false;
+    if (!at || !at->is_grad || debug_knob("MTE_LOSS_NO_STASH")) return false;
     for (int i = 0; i < n; i++) {
         if (!sc[i].stash || !sc[i].grad_map || !sc[i].normal) return false;
         if (sc[i].h != sc[i].H || sc[i].w != sc[i].W) return false;
@@ -194,8 +194,8 @@ static int make_plan(Plan &pl, const mte_loss_scale_t *sc, int n, const mte_loss
     // measured on B200 (profiles/r01_notes.md): the forward (per-CTA reduction epilogue) likes ~2 resident waves,
     // the backward (no epilogue) only needs enough CTAs for the hardware scheduler to balance the tail
     int waves = bwd ? kBwdCtaWaves : kFwdCtaWaves;
-    if (const char *e = getenv("MTE_CTA_WAVES")) waves = atoi(e) > 0 ? atoi(e) : waves;  // tuning knob
-    const int cap = kNumSMs * 2 * waves;
+    if (const char *e = debug_knob("MTE_CTA_WAVES")) waves = atoi(e) > 0 ? atoi(e) : waves;  // tuning knob
+    const int cap = num_sms() * 2 * waves;
     if (cta > cap) {
         const double shrink = (double)cap / (double)cta;
         cta = 0;
@@ -212,7 +212,7 @@ static int make_plan(Plan &pl, const mte_loss_scale_t *sc, int n, const mte_loss
     P.totalUnits = (int)unitBase;
     // forward: persistent CTAs (2 per SM), every warp owns an equal contiguous range of strip rows (at least a few
     // rows each, so the window prologue is amortised)
-    pl.fwdGrid = kNumSMs * kRGridB;
+    pl.fwdGrid = num_sms() * kRGridB;
     const int minRows = 4;
     if ((long long)pl.fwdGrid * kRWarps * minRows > unitBase) pl.fwdGrid = (int)((unitBase + kRWarps * minRows - 1) / (kRWarps * minRows));
     if (pl.fwdGrid < 1) pl.fwdGrid = 1;
@@ -322,13 +322,13 @@ extern "C" int mte_edge_loss_bwd(const mte_loss_scale_t *sc, int n, const mte_lo
         if (pl.resized[i] && at->pred_is_inverse) return MTE_ERR_ARG;
     if (!at->is_grad) {
         if (pl.hasMask)
-            edge_loss_bwd_pointwise_kernel<true><<<kNumSMs * 8, kThreads, 0, st>>>(P, at->is_sigmoid, at->pred_is_inverse);
+            edge_loss_bwd_pointwise_kernel<true><<<num_sms() * 8, kThreads, 0, st>>>(P, at->is_sigmoid, at->pred_is_inverse);
         else
-            edge_loss_bwd_pointwise_kernel<false><<<kNumSMs * 8, kThreads, 0, st>>>(P, at->is_sigmoid, at->pred_is_inverse);
+            edge_loss_bwd_pointwise_kernel<false><<<num_sms() * 8, kThreads, 0, st>>>(P, at->is_sigmoid, at->pred_is_inverse);
     } else {
         const int mode = pl.hasNormal ? MODE_DIR : MODE_MAG;
         if (can_use_stash(sc, n, at)) {
-            if (pl.vec && !getenv("MTE_LOSS_BWD_OLD")) {
+            if (pl.vec && !debug_knob("MTE_LOSS_BWD_OLD")) {
                 P.totalCtas = pl.fwdGrid;  // persistent grid over the cost-balanced unit ranges
                 launch_bwd_ring_v4(P, pl.hasMask, at->pred_is_inverse != 0, at->is_sigmoid != 0, st);
             } else if (pl.vec) launch_bwd_stash_v4(P, pl.hasMask, at->pred_is_inverse != 0, at->is_sigmoid != 0, st);

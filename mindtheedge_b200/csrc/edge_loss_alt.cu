@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(kThreads) alt_scatter_kernel(const float *__re
 
 static int grid_for(size_t n) {
     const size_t b = (n + kThreads - 1) / kThreads;
-    return (int)(b < (size_t)kNumSMs * 8 ? (b ? b : 1) : (size_t)kNumSMs * 8);
+    return (int)(b < (size_t)num_sms() * 8 ? (b ? b : 1) : (size_t)num_sms() * 8);
 }
 
 }  // namespace alt

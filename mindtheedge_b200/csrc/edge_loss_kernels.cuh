@@ -25,7 +25,7 @@ constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kAcc = 8;
 enum { A_WP = 0, A_WN, A_SPU, A_SNU, A_SPM, A_SNM, A_SUMM, A_FLAGS };
-enum { F_HAS0 = 1u, F_HAS1 = 2u, F_OTHER = 4u };
+enum { F_HAS0 = 1u, F_HAS1 = 2u, F_OTHER = 4u, F_NONFINITE = 8u };
 enum { MODE_NONE = 0, MODE_MAG = 1, MODE_DIR = 2 };
 
 #ifndef MTE_FWD_MINB
@@ -139,7 +139,13 @@ __device__ __forceinline__ float rcp_rn_normal(float d) {
     e = fmaf(-d, r, 1.0f);
     return fmaf(r, e, r);
 }
-__device__ __forceinline__ float inv_to_depth(float v) { return rcp_rn_normal(fmaxf(v, 1e-6f)); }
+// torch.clamp(min=1e-6) keeps a NaN (utils/depth.py:104-121), fmaxf would swallow it: max.NaN propagates
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float inv_to_depth(float v) { return rcp_rn_normal(fmax_nan(v, 1e-6f)); }
 
 // Forward: the loss is a mean over millions of terms; MUFU-accuracy sigmoid is far inside 1e-5.
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -256,18 +262,19 @@ static __device__ __forceinline__ void finalize_loss(const LossP &P, double *sLo
         const double npix = (double)S.H * (double)S.W;
         double sumM = 0.0;
         unsigned fl = 0;
-        if (MASK) {  // the mask's value set and sum decide the normaliser before the per-image pass
-            for (int base = 0; base < S.B; base += 32) {
-                const int i = base + lane;
-                const unsigned long long *a = P.accum + (size_t)(S.imgBase + i) * kAcc;
-                const bool in = i < S.B;
-                const double sm = in ? (double)(long long)__ldcg(a + A_SUMM) / kFix : 0.0;
-                fl |= in ? (unsigned)__ldcg(a + A_FLAGS) : 0u;
-                sumM += sm;
-            }
-            sumM = warp_sum(sumM);
-            fl = warp_or(fl);
+        // the mask's value set and sum decide the normaliser before the per-image pass; the non-finite flag (a NaN /
+        // Inf anywhere in the scale's inputs or sums: the reference's loss is NaN then) rides in the same word
+        for (int base = 0; base < S.B; base += 32) {
+            const int i = base + lane;
+            const unsigned long long *a = P.accum + (size_t)(S.imgBase + i) * kAcc;
+            const bool in = i < S.B;
+            if (MASK) sumM += in ? (double)(long long)__ldcg(a + A_SUMM) / kFix : 0.0;
+            fl |= in ? (unsigned)__ldcg(a + A_FLAGS) : 0u;
         }
+        if (MASK) sumM = warp_sum(sumM);
+        fl = warp_or(fl);
+        const bool nonFinite = (fl & F_NONFINITE) != 0u;
+        fl &= ~(unsigned)F_NONFINITE;
         // grad_loss.py:183-187: the mask only masks when its value set is exactly {0,1}
         const bool binary = MASK && fl == (F_HAS0 | F_HAS1);
         // one image per lane; the three sums are independent butterflies (they overlap), the degenerate
@@ -288,7 +295,7 @@ static __device__ __forceinline__ void finalize_loss(const LossP &P, double *sLo
                 wnSum += wn;
 #pragma unroll
                 for (int q = 0; q < kAcc; q++)
-                    if (MASK || q == A_WP || q == A_SPU || q == A_SNU) a[q] = 0ull;  // leave the accumulators clean
+                    if (MASK || q == A_WP || q == A_SPU || q == A_SNU || q == A_FLAGS) a[q] = 0ull;  // leave the accumulators clean
             }
         }
         acc = warp_sum(acc);
@@ -301,7 +308,7 @@ static __device__ __forceinline__ void finalize_loss(const LossP &P, double *sLo
         }
         acc *= (double)kLn2;
         const double valid = binary ? sumM : npix * (double)S.B;
-        const double lossK = (double)P.weight * (acc / valid);
+        const double lossK = nonFinite ? (double)__int_as_float(0x7fc00000) : (double)P.weight * (acc / valid);
         if (lane == 0) {
             sLoss[k] = lossK;
             P.lossOut[1 + k] = (float)lossK;
@@ -414,7 +421,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 template <typename K>
 static void launch_pdl(K kernel, int grid, int block, int smem, cudaStream_t st, const LossP &P) {
-    static const bool noPdl = getenv("MTE_NO_PDL") != nullptr;
+    const bool noPdl = debug_knob("MTE_NO_PDL") != nullptr;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3((unsigned)block);
@@ -463,7 +470,8 @@ __host__ __device__ constexpr int fwd_smem_bytes(int vec, int mode, bool mask) {
 // at strip ends.  A segment streams its rows through a 3-row register window fed by the shared-memory row ring.
 template <int VEC, int MODE, bool MASK, bool INV, bool SIG>
 __device__ __forceinline__ void fwd_segment(const LossP &P, const ScaleP &S, int img, int strip, int row0, int nrows,
-                                            int lane, unsigned char *ring, float (&la)[kAcc - 1], unsigned &lflags) {
+                                            int lane, unsigned char *ring, float (&la)[kAcc - 1], unsigned &lflags,
+                                            float &poison) {
     constexpr int D = fwd_ring_depth(MODE, MASK);
     constexpr int NPL = fwd_planes(MODE, MASK);
     constexpr unsigned PLB = 32 * VEC * 4;     // bytes of one plane row in a slot
@@ -516,6 +524,12 @@ __device__ __forceinline__ void fwd_segment(const LossP &P, const ScaleP &S, int
         }
     };
 
+    // x * 0 is NaN exactly when x is NaN or +-Inf: one FFMA per loaded pixel carries "a non-finite prediction was
+    // seen" to the end of the segment (the reference's conv2d turns any such pixel into a NaN loss: 0 * inf)
+    auto taint = [&](const float (&x)[VEC]) {
+#pragma unroll
+        for (int v = 0; v < VEC; v++) poison = fmaf(x[v], 0.f, poison);
+    };
     PRow<VEC> win[3];  // win[d % 3] holds depth row row0 - OFF + d
     float xa[VEC], xc[VEC];
 #pragma unroll
@@ -542,6 +556,8 @@ __device__ __forceinline__ void fwd_segment(const LossP &P, const ScaleP &S, int
         pad_x(xc, row0);
         to_depth(xa);
         to_depth(xc);
+        taint(xa);
+        taint(xc);
         prep_row<VEC, MODE>(win[0], xa);
         prep_row<VEC, MODE>(win[1], xc);
     }
@@ -564,6 +580,7 @@ __device__ __forceinline__ void fwd_segment(const LossP &P, const ScaleP &S, int
                 PRow<VEC> &dn = win[(MODE == MODE_NONE) ? 0 : (u + 2) % 3];
                 pad_x(xn, row0 + j + OFF);
                 to_depth(xn);
+                taint(xn);
                 prep_row<VEC, MODE>(dn, xn);
                 const PRow<VEC> &up = win[(MODE == MODE_NONE) ? 0 : u % 3];
                 const PRow<VEC> &mid = win[(MODE == MODE_NONE) ? 0 : (u + 1) % 3];
@@ -666,20 +683,22 @@ __global__ void __launch_bounds__(kRThreads, kRMinB) edge_loss_fwd_kernel(const 
 #pragma unroll
         for (int k = 0; k < kAcc - 1; k++) la[k] = 0.f;
         unsigned lflags = 0;
-        fwd_segment<VEC, MODE, MASK, INV, SIG>(P, S, img, strip, row0, nrows, lane, ring, la, lflags);
+        float poison = 0.f;
+        fwd_segment<VEC, MODE, MASK, INV, SIG>(P, S, img, strip, row0, nrows, lane, ring, la, lflags, poison);
+        bool bad = __any_sync(MTE_FULL_MASK, !(poison == 0.f));
         // order-independent accumulation: warp tree (fixed) -> 2^32 fixed point -> integer atomics
         unsigned long long *acc = P.accum + (size_t)(S.imgBase + img) * kAcc;
 #pragma unroll
         for (int k = 0; k < kAcc - 1; k++) {
             if (MASK || k == A_WP || k == A_SPU || k == A_SNU) {
                 const float v = warp_sum(la[k]);
+                bad = bad || !isfinite(v);  // __double2ll_rn(NaN / Inf) would be a finite garbage contribution
                 if (lane == 0) atomicAdd(acc + k, (unsigned long long)__double2ll_rn((double)v * kFix));
             }
         }
-        if (MASK) {
-            lflags = warp_or(lflags);
-            if (lane == 0 && lflags) atomicOr(acc + A_FLAGS, (unsigned long long)lflags);
-        }
+        if (MASK) lflags = warp_or(lflags);
+        if (bad) lflags |= F_NONFINITE;
+        if (lane == 0 && lflags) atomicOr(acc + A_FLAGS, (unsigned long long)lflags);
     }
     // the last CTA to leave finalises (its warps share the scales)
     __shared__ double sLoss[MTE_MAX_SCALES];
@@ -1193,11 +1212,7 @@ __global__ void __launch_bounds__(kRThreads, kRMinB) edge_loss_bwd_ring_kernel(c
 template <bool MASK, bool INV, bool SIG>
 static void launch_bwd_ring_one(const LossP &P, cudaStream_t st) {
     constexpr int smem = bwd_smem_bytes(MASK, INV);
-    static bool optedIn = false;
-    if (!optedIn) {
-        cudaFuncSetAttribute(edge_loss_bwd_ring_kernel<MASK, INV, SIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        optedIn = true;
-    }
+    opt_in_smem((const void *)edge_loss_bwd_ring_kernel<MASK, INV, SIG>, smem);
     launch_pdl(edge_loss_bwd_ring_kernel<MASK, INV, SIG>, P.totalCtas, kRThreads, smem, st, P);
 }
 
@@ -1205,11 +1220,7 @@ static void launch_bwd_ring_one(const LossP &P, cudaStream_t st) {
 template <int VEC, int MODE, bool MASK, bool INV, bool SIG>
 static void launch_fwd_one(const LossP &P, cudaStream_t st) {
     constexpr int smem = fwd_smem_bytes(VEC, MODE, MASK);
-    static bool optedIn = false;
-    if (!optedIn) {
-        cudaFuncSetAttribute(edge_loss_fwd_kernel<VEC, MODE, MASK, INV, SIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        optedIn = true;
-    }
+    opt_in_smem((const void *)edge_loss_fwd_kernel<VEC, MODE, MASK, INV, SIG>, smem);
     launch_pdl(edge_loss_fwd_kernel<VEC, MODE, MASK, INV, SIG>, P.totalCtas, kRThreads, smem, st, P);
 }
 

@@ -948,6 +948,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
         unsigned short phase = 0;
         int nLive = 0;  // compact mode: matched pixels currently resident
         for (int s = 0; s < T; s++) {
+            const long long tStage = (P.stats && threadIdx.x == 0) ? clock64() : 0;
             const int G0 = sStage[s], G1 = sStage[s + 1];  // the pixels that join at this stage (positions in gpix)
             int cur = G0;
             do {
@@ -1207,6 +1208,10 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
             } while (cur < G1);
             __syncthreads();
             // ---- the count of this stage's threshold
+            if (P.stats && threadIdx.x == 0) {  // profiling (debug builds): cycles >> 8 and new pixels per stage
+                atomicAdd(P.stats + 9 + min(s, 11), (unsigned)((clock64() - tStage) >> 8));
+                if (s == 0) atomicAdd(P.stats + 21, (unsigned)(G1 - G0));
+            }
             if (threadIdx.x == 0) {
                 const int t = levels ? s : T - 1 - s;
                 const int matched = sMatched;
@@ -1325,7 +1330,7 @@ static Layout layout(int nProblems, int h, int w, int T) {
     L.offThr = off; off += align_up(sizeof(double) * (size_t)(T > 0 ? T : 1), 256);
     L.offOverflow = off; off += align_up(sizeof(int) * (size_t)(nProblems > 0 ? nProblems : 1), 256);
     L.arenaBytes = align_up(arena_bytes(h, w), 256);
-    int n = kNumSMs * kCtasPerSm;
+    int n = num_sms() * kCtasPerSm;
     if (n > nProblems) n = nProblems;
     if (n < 1) n = 1;
     L.nArenas = n;
@@ -1378,8 +1383,8 @@ static int launch(MatchP &P, const Layout &L, char *ws, double max_dist, const d
     P.arena = ws + L.offArena;
     P.arenaBytes = L.arenaBytes;
     WsHeader *hdr = reinterpret_cast<WsHeader *>(ws);
-    P.truncate = getenv("MTE_MATCH_TRUNCATE") ? 1 : 0;
-    P.stats = getenv("MTE_MATCH_STATS") ? hdr->pad : nullptr;
+    P.truncate = debug_knob("MTE_MATCH_TRUNCATE") ? 1 : 0;
+    P.stats = debug_knob("MTE_MATCH_STATS") ? hdr->pad : nullptr;
     P.nextProblem = hdr->ticket + 4;
     P.doneCtas = hdr->ticket + 5;
     P.overflowCount = hdr->ticket + 6;
@@ -1387,45 +1392,35 @@ static int launch(MatchP &P, const Layout &L, char *ws, double max_dist, const d
     P.problemList = nullptr;
     P.listCount = nullptr;
     // shared-memory kernel first (one CTA per SM, ~200 KB of state), the dense L2 kernel mops up what did not fit
-    static int smemBudget = -1;
-    if (smemBudget < 0) {
-        int dev = 0, optin = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    int smemBudget;
+    {
         cudaFuncAttributes fa;
         cudaFuncGetAttributes(&fa, match_smem_kernel);
-        smemBudget = optin - (int)fa.sharedSizeBytes - 1024;
-        if (smemBudget > 0 &&
-            cudaFuncSetAttribute(match_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBudget) != cudaSuccess)
-            smemBudget = 0;
+        smemBudget = dev_info().smemOptin - (int)fa.sharedSizeBytes - 1024;
+        if (smemBudget > 0 && opt_in_smem((const void *)match_smem_kernel, smemBudget) != cudaSuccess) smemBudget = 0;
         cudaGetLastError();
     }
     const SmemLayout SL = smem_layout(P.h, P.w, smemBudget);
-    const bool useSmem = SL.capP > 0 && tb.n <= kSmemTableOff && !getenv("MTE_MATCH_DENSE");
+    const bool useSmem = SL.capP > 0 && tb.n <= kSmemTableOff && !debug_knob("MTE_MATCH_DENSE");
     // threshold sweeps (level planes; strength maps with ascending thresholds): one CTA per image solves all T nested
     // problems incrementally; what does not fit falls through to the per-problem kernels via the overflow list
     bool sweep = useSmem && P.counts && !P.matchA && !P.matchB && P.inMode != IN_BINARY && P.T > 1 &&
-                 !getenv("MTE_MATCH_NO_SWEEP");
+                 !debug_knob("MTE_MATCH_NO_SWEEP");
     if (sweep && P.inMode != IN_LEVELS)
         for (int t = 1; t < P.T; t++)
             if (!(thr_host[t] > thr_host[t - 1])) sweep = false;
     if (sweep) {
-        static int sweepBudget = -1;
-        if (sweepBudget < 0) {
-            int dev = 0, optin = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        int sweepBudget;
+        {
             cudaFuncAttributes fa;
             cudaFuncGetAttributes(&fa, match_sweep_kernel);
-            sweepBudget = optin - (int)fa.sharedSizeBytes - 1024;
-            if (sweepBudget > 0 &&
-                cudaFuncSetAttribute(match_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sweepBudget) != cudaSuccess)
-                sweepBudget = 0;
+            sweepBudget = dev_info().smemOptin - (int)fa.sharedSizeBytes - 1024;
+            if (sweepBudget > 0 && opt_in_smem((const void *)match_sweep_kernel, sweepBudget) != cudaSuccess) sweepBudget = 0;
             cudaGetLastError();
         }
         const SweepLayout SW = sweep_layout(P.h, P.w, sweepBudget);
         if (SW.capP > 0) {
-            int grid = kNumSMs;
+            int grid = num_sms();
             if (grid > P.N) grid = P.N;
             match_sweep_kernel<<<grid, kSwThreads, SW.total, st>>>(P, pt, inParam ? 1 : 0, SW);
             MTE_RETURN_IF_CUDA_ERROR();
@@ -1438,7 +1433,7 @@ static int launch(MatchP &P, const Layout &L, char *ws, double max_dist, const d
         }
     }
     if (useSmem) {
-        int grid = kNumSMs;
+        int grid = num_sms();
         if (grid > P.nProblems) grid = P.nProblems;
         match_smem_kernel<<<grid, kSmThreads, SL.total, st>>>(P, pt, inParam ? 1 : 0, SL);
         MTE_RETURN_IF_CUDA_ERROR();

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kThreads) edge_resize_preserve_kernel(const un
 
 static int grid_for(size_t n) {
     const size_t b = (n + kThreads - 1) / kThreads;
-    return (int)(b < (size_t)kNumSMs * 8 ? (b ? b : 1) : (size_t)kNumSMs * 8);
+    return (int)(b < (size_t)num_sms() * 8 ? (b ? b : 1) : (size_t)num_sms() * 8);
 }
 
 }  // namespace targets

@@ -33,6 +33,29 @@ __all__ = ["canny_from_depth", "edge_from_depth", "edge_from_depth_cfg", "Canny"
 _DT = {torch.float32: _lib.MTE_F32, torch.float64: _lib.MTE_F64, torch.uint8: _lib.MTE_U8}
 
 
+def _canny_from_depth_cuda(depth, lows, highs, min_depth, max_depth, want_edges, want_levels):
+    """CUDA implementation of ``mte::canny_from_depth``: depth [N,H,W] -> (edges [T,N,H,W] or empty, levels [N,H,W]
+    or empty), both uint8."""
+    with runtime.on_device(depth) as dev:
+        d = depth.contiguous()
+        N, H, W = d.shape
+        T = len(lows)
+        lo = (C.c_int32 * T)(*[int(v) for v in lows])
+        hi = (C.c_int32 * T)(*[int(v) for v in highs])
+        edges = torch.empty((T, N, H, W) if want_edges else (0,), dtype=torch.uint8, device=dev)
+        levels = torch.empty((N, H, W) if want_levels else (0,), dtype=torch.uint8, device=dev)
+        ws = runtime.workspace(dev, _lib.lib.mte_canny_workspace_bytes(N, H, W, T))
+        runtime.call("mte_canny_from_depth", dev, d.data_ptr(), _DT[d.dtype], N, H, W, float(min_depth),
+                     float(max_depth), lo, hi, T, edges.data_ptr() if want_edges else None,
+                     levels.data_ptr() if want_levels else None, ws.data_ptr(), ws.numel(),
+                     runtime.current_stream_ptr(dev))
+    return edges, levels
+
+
+runtime.define_op("canny_from_depth(Tensor depth, int[] lows, int[] highs, float min_depth, float max_depth, "
+                  "bool want_edges, bool want_levels) -> (Tensor, Tensor)", _canny_from_depth_cuda)
+
+
 def canny_from_depth(depth: torch.Tensor, pairs: Sequence[Tuple[int, int]], min_depth: float = 0.0,
                      max_depth: float = 80.0, *, want_edges: bool = True, want_levels: bool = False):
     """depth: CUDA tensor [N,H,W] (or [H,W]) of float32/float64 metres, or uint8
@@ -40,7 +63,7 @@ def canny_from_depth(depth: torch.Tensor, pairs: Sequence[Tuple[int, int]], min_
 
     Returns ``edges`` uint8 [T,N,H,W] in {0,255} and/or ``levels`` uint8 [N,H,W]
     (index of the first pair at which the pixel is an edge, 255 = never; needs
-    nested pairs, strictest first)."""
+    nested pairs, strictest first).  Runs as the torch custom op ``mte::canny_from_depth``."""
     runtime.require_cuda(depth, "depth")
     if depth.dtype not in _DT:
         raise _lib.MteError(f"unsupported depth dtype {depth.dtype}")
@@ -48,19 +71,12 @@ def canny_from_depth(depth: torch.Tensor, pairs: Sequence[Tuple[int, int]], min_
     d = depth.unsqueeze(0) if squeeze else depth
     if d.dim() != 3:
         raise _lib.MteError("depth must be [N,H,W] or [H,W]")
-    d = d.contiguous()
-    N, H, W = d.shape
-    T = len(pairs)
-    lows = (C.c_int32 * T)(*[int(np.floor(p[0])) for p in pairs])
-    highs = (C.c_int32 * T)(*[int(np.floor(p[1])) for p in pairs])
-    dev = d.device
-    edges = torch.empty((T, N, H, W), dtype=torch.uint8, device=dev) if want_edges else None
-    levels = torch.empty((N, H, W), dtype=torch.uint8, device=dev) if want_levels else None
-    ws = runtime.workspace(dev, _lib.lib.mte_canny_workspace_bytes(N, H, W, T))
-    _lib.check(_lib.lib.mte_canny_from_depth(
-        d.data_ptr(), _DT[d.dtype], N, H, W, float(min_depth), float(max_depth), lows, highs, T,
-        runtime.ptr(edges), runtime.ptr(levels), ws.data_ptr(), ws.numel(), runtime.current_stream_ptr(dev)),
-        "mte_canny_from_depth")
+    lows = [int(np.floor(p[0])) for p in pairs]
+    highs = [int(np.floor(p[1])) for p in pairs]
+    edges, levels = torch.ops.mte.canny_from_depth(d, lows, highs, float(min_depth), float(max_depth),
+                                                   bool(want_edges), bool(want_levels))
+    edges = edges if want_edges else None
+    levels = levels if want_levels else None
     if squeeze:
         edges = None if edges is None else edges[:, 0]
         levels = None if levels is None else levels[0]
@@ -126,24 +142,33 @@ def Canny(image: np.ndarray, threshold1, threshold2) -> np.ndarray:
 # ---------------------------------------------------------------------------
 # in-training "light" edge metric
 # ---------------------------------------------------------------------------
+def _chamfer_counts_cuda(pred, gt, thresh, want_map):
+    with runtime.on_device(pred, gt) as dev:
+        pred, gt = pred.contiguous(), gt.contiguous()
+        N, H, W = pred.shape
+        out = torch.empty((N, 4), dtype=torch.float64, device=dev)
+        cond = torch.empty((N, H, W) if want_map else (0,), dtype=torch.int8, device=dev)
+        ws = runtime.workspace(dev, _lib.lib.mte_chamfer_workspace_bytes(N, H, W))
+        runtime.call("mte_chamfer_counts", dev, pred.data_ptr(), gt.data_ptr(), N, H, W, float(thresh),
+                     out.data_ptr(), cond.data_ptr() if want_map else None, ws.data_ptr(), ws.numel(),
+                     runtime.current_stream_ptr(dev))
+    return out, cond
+
+
+runtime.define_op("chamfer_counts(Tensor pred, Tensor gt, float thresh, bool want_map) -> (Tensor, Tensor)",
+                  _chamfer_counts_cuda)
+
+
 def chamfer_counts(pred: torch.Tensor, gt: torch.Tensor, edge_to_edge_thresh: float = 5, want_map: bool = False):
     """pred, gt: CUDA uint8 [N,H,W] edge maps (set = value/255 > 0.5).
     -> float64 [N,4] on the device: sum of the exact Euclidean distances from every pred pixel to the nearest
     gt pixel, number of pred pixels, number of pred pixels closer than the threshold, 0; and, with ``want_map``,
-    the int8 [N,H,W] map (-1 not a pred pixel, 1 close, 0 not)."""
+    the int8 [N,H,W] map (-1 not a pred pixel, 1 close, 0 not).  Torch custom op ``mte::chamfer_counts``."""
     runtime.require_cuda(pred, "pred")
     runtime.require_cuda(gt, "gt")
     if pred.dtype != torch.uint8 or gt.dtype != torch.uint8 or pred.shape != gt.shape or pred.dim() != 3:
         raise _lib.MteError("chamfer_counts expects two uint8 [N,H,W] maps of the same shape")
-    pred, gt = pred.contiguous(), gt.contiguous()
-    N, H, W = pred.shape
-    dev = pred.device
-    out = torch.empty((N, 4), dtype=torch.float64, device=dev)
-    cond = torch.empty((N, H, W), dtype=torch.int8, device=dev) if want_map else None
-    ws = runtime.workspace(dev, _lib.lib.mte_chamfer_workspace_bytes(N, H, W))
-    _lib.check(_lib.lib.mte_chamfer_counts(pred.data_ptr(), gt.data_ptr(), N, H, W, float(edge_to_edge_thresh),
-                                           out.data_ptr(), runtime.ptr(cond), ws.data_ptr(), ws.numel(),
-                                           runtime.current_stream_ptr(dev)), "mte_chamfer_counts")
+    out, cond = torch.ops.mte.chamfer_counts(pred, gt, float(edge_to_edge_thresh), bool(want_map))
     return (out, cond) if want_map else out
 
 

@@ -23,6 +23,8 @@ Differences from the reference wiring, none of which changes a count:
 from __future__ import annotations
 
 import ctypes as C
+import os
+from collections import namedtuple
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -32,7 +34,7 @@ from . import _lib, runtime
 from .edge import canny_from_depth, read_depth_file
 
 __all__ = [
-    "pr_counts", "correspond_pixels_batch", "evaluate_boundaries", "evaluate_boundaries_bin",
+    "EvalResult", "_pred_eval", "pr_counts", "correspond_pixels_batch", "evaluate_boundaries", "evaluate_boundaries_bin",
     "compute_rec_prec_f1", "pr_evaluation", "pr_evaluation_arrays", "mean_recall_at_precision_range",
     "shard_indices", "all_reduce_counts", "sweep_counts",
 ]
@@ -43,10 +45,49 @@ _DT = {torch.float32: _lib.MTE_F32, torch.float64: _lib.MTE_F64, torch.uint8: _l
 # ---------------------------------------------------------------------------
 # tensor-level ops
 # ---------------------------------------------------------------------------
+def _pr_counts_cuda(pred, gt, thresholds, n_levels, max_dist, crop):
+    """CUDA implementation of ``mte::pr_counts`` -> int64 [T,4] (count_r, sum_r, count_p, sum_p)."""
+    with runtime.on_device(pred, gt) as dev:
+        pred, gt = pred.contiguous(), gt.contiguous()
+        N, H, W = pred.shape
+        if pred.dtype == torch.uint8:
+            T, thr = int(n_levels), None
+        else:
+            t = np.ascontiguousarray(np.asarray(thresholds, dtype=np.float64))
+            T = int(t.shape[0])
+            thr = t.ctypes.data_as(C.POINTER(C.c_double))
+        out = torch.zeros((T, 4), dtype=torch.int64, device=dev)
+        cr = None if len(crop) == 0 else (C.c_int32 * 4)(*[int(v) for v in crop])
+        ws = runtime.workspace(dev, _lib.lib.mte_pr_workspace_bytes(N, H, W, T, float(max_dist)))
+        runtime.call("mte_pr_counts", dev, pred.data_ptr(), _DT[pred.dtype], gt.data_ptr(), N, H, W, cr, thr, T,
+                     float(max_dist), 0, out.data_ptr(), ws.data_ptr(), ws.numel(), runtime.current_stream_ptr(dev))
+    return out
+
+
+def _correspond_pixels_cuda(a, b, max_dist, want_maps):
+    with runtime.on_device(a, b) as dev:
+        a, b = a.contiguous(), b.contiguous()
+        Pn, h, w = a.shape
+        ma = torch.empty(a.shape if want_maps else (0,), dtype=torch.uint8, device=dev)
+        mb = torch.empty(b.shape if want_maps else (0,), dtype=torch.uint8, device=dev)
+        cnt = torch.empty(Pn, dtype=torch.int64, device=dev)
+        ws = runtime.workspace(dev, _lib.lib.mte_match_workspace_bytes(Pn, h, w, float(max_dist)))
+        runtime.call("mte_correspond_pixels", dev, a.data_ptr(), b.data_ptr(), Pn, h, w, float(max_dist),
+                     ma.data_ptr() if want_maps else None, mb.data_ptr() if want_maps else None, cnt.data_ptr(),
+                     ws.data_ptr(), ws.numel(), runtime.current_stream_ptr(dev))
+    return ma, mb, cnt
+
+
+runtime.define_op("pr_counts(Tensor pred, Tensor gt, float[] thresholds, int n_levels, float max_dist, int[] crop) "
+                  "-> Tensor", _pr_counts_cuda)
+runtime.define_op("correspond_pixels(Tensor a, Tensor b, float max_dist, bool want_maps) -> (Tensor, Tensor, Tensor)",
+                  _correspond_pixels_cuda)
+
+
 def pr_counts(pred: torch.Tensor, gt: torch.Tensor, thresholds=None, *, n_levels: Optional[int] = None,
               max_dist: float = 0.0075, crop: Optional[Sequence[int]] = None,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Counts for a batch of images, one GT map each.
+    """Counts for a batch of images, one GT map each (torch custom op ``mte::pr_counts``).
 
     pred  [N,H,W] CUDA: float32/float64 strength map (``pred >= thresholds[t]``) or uint8 level
           plane from ``canny_from_depth(..., want_levels=True)`` (edge at t iff level <= t; give
@@ -61,48 +102,31 @@ def pr_counts(pred: torch.Tensor, gt: torch.Tensor, thresholds=None, *, n_levels
         pred, gt = pred.unsqueeze(0), gt.unsqueeze(0)
     if pred.dtype not in _DT:
         raise _lib.MteError(f"unsupported pred dtype {pred.dtype}")
-    pred = pred.contiguous()
-    gt = gt.contiguous()
     if gt.dtype != torch.uint8:
         gt = (gt != 0).to(torch.uint8)
     if gt.shape != pred.shape:
         raise _lib.MteError("pred and gt must have the same [N,H,W] shape")
-    N, H, W = pred.shape
-    dev = pred.device
     if pred.dtype == torch.uint8:
         if n_levels is None:
             raise _lib.MteError("n_levels is required with a uint8 level plane")
-        T, thr = int(n_levels), None
+        thr = []
     else:
-        t = np.ascontiguousarray(np.asarray(thresholds, dtype=np.float64))
-        T = int(t.shape[0])
-        thr = t.ctypes.data_as(C.POINTER(C.c_double))
+        thr = [float(v) for v in np.asarray(thresholds, dtype=np.float64)]
+    c = torch.ops.mte.pr_counts(pred, gt, thr, int(n_levels or 0), float(max_dist),
+                                [] if crop is None else [int(v) for v in crop])
     if out is None:
-        out = torch.zeros((T, 4), dtype=torch.int64, device=dev)
-    cr = None if crop is None or len(crop) == 0 else (C.c_int32 * 4)(*[int(v) for v in crop])
-    ws = runtime.workspace(dev, _lib.lib.mte_pr_workspace_bytes(N, H, W, T, float(max_dist)))
-    _lib.check(_lib.lib.mte_pr_counts(pred.data_ptr(), _DT[pred.dtype], gt.data_ptr(), N, H, W, cr, thr, T,
-                                      float(max_dist), 0, out.data_ptr(), ws.data_ptr(), ws.numel(),
-                                      runtime.current_stream_ptr(dev)), "mte_pr_counts")
+        return c
+    out += c
     return out
 
 
 def correspond_pixels_batch(a: torch.Tensor, b: torch.Tensor, max_dist: float = 0.0075, want_maps: bool = True):
-    """Maximum matching between boundary maps a[k], b[k] ([P,h,w] uint8 CUDA).
-    -> (match_a, match_b, count int64[P])."""
+    """Maximum matching between boundary maps a[k], b[k] ([P,h,w] uint8 CUDA; torch custom op
+    ``mte::correspond_pixels``).  -> (match_a, match_b, count int64[P])."""
     runtime.require_cuda(a, "a")
-    a = a.contiguous()
-    b = b.contiguous()
-    Pn, h, w = a.shape
-    dev = a.device
-    ma = torch.empty_like(a) if want_maps else None
-    mb = torch.empty_like(b) if want_maps else None
-    cnt = torch.empty(Pn, dtype=torch.int64, device=dev)
-    ws = runtime.workspace(dev, _lib.lib.mte_match_workspace_bytes(Pn, h, w, float(max_dist)))
-    _lib.check(_lib.lib.mte_correspond_pixels(a.data_ptr(), b.data_ptr(), Pn, h, w, float(max_dist),
-                                              runtime.ptr(ma), runtime.ptr(mb), cnt.data_ptr(), ws.data_ptr(),
-                                              ws.numel(), runtime.current_stream_ptr(dev)), "mte_correspond_pixels")
-    return ma, mb, cnt
+    runtime.require_cuda(b, "b")
+    ma, mb, cnt = torch.ops.mte.correspond_pixels(a, b, float(max_dist), bool(want_maps))
+    return (ma, mb, cnt) if want_maps else (None, None, cnt)
 
 
 # ---------------------------------------------------------------------------
@@ -132,10 +156,13 @@ def evaluate_boundaries(predicted_boundaries, gt_boundaries, thresholds=99, max_
     sum_p = np.zeros(T)
     d_pred = torch.from_numpy(pred).cuda()
     if not apply_thinning and len(gt_boundaries) == 1:
-        gt = torch.from_numpy(np.ascontiguousarray(np.asarray(gt_boundaries[0]) != 0).astype(np.uint8)).cuda()
+        g_np = np.asarray(gt_boundaries[0])
+        gt = torch.from_numpy(np.ascontiguousarray(g_np != 0).astype(np.uint8)).cuda()
         c = pr_counts(d_pred[None], gt[None], thresholds, max_dist=max_dist).cpu().numpy()
-        return (c[:, 0].astype(np.float64), c[:, 1].astype(np.float64), c[:, 2].astype(np.float64),
-                c[:, 3].astype(np.float64), thresholds)
+        # the matcher sees "non-zero = boundary", but sum_r is gt.sum() (eval_depth_edges.py:138): for maps that are
+        # not 0/1 (255-valued, soft, or multiplied by a fractional mask image) the two differ
+        sum_r[:] = float(g_np.sum())
+        return (c[:, 0].astype(np.float64), sum_r, c[:, 2].astype(np.float64), c[:, 3].astype(np.float64), thresholds)
     # general path (thinning and/or several GT maps): binarise per threshold, thin, match against every GT
     from .bsds import thin as _thin
     thr_dev = torch.from_numpy(np.asarray(thresholds, dtype=np.float64)).cuda()
@@ -179,6 +206,52 @@ def mean_recall_at_precision_range(arr, small_lim=0.0, large_lim=1.0):
     interp_y[interp_y < 0] = 0
     interp_y[interp_y > 1] = 1
     return np.mean(interp_y)
+
+
+EvalResult = namedtuple('EvalResult', ['count_r_overall', 'sum_r_overall',
+                                       'count_p_overall', 'sum_p_overall',
+                                       'count_r_best', 'sum_r_best',
+                                       'count_p_best', 'sum_p_best',
+                                       'used_thresholds', 'recall', 'precision'])
+
+
+def _crop_or_mask(crop):
+    """``_pred_eval``'s ``crop`` argument (eval_depth_edges.py:182-189): the ``str()`` of a ``[x0,x1,y0,y1]`` list (or
+    ``[]``), or the path of a mask IMAGE whose channel 0 / 255 multiplies both maps.  -> (crop list or None, mask)"""
+    import ast
+    import cv2
+    if isinstance(crop, str):
+        path = crop.split("\n")[0]
+        if os.path.exists(path):
+            return None, cv2.imread(path)[:, :, 0] / 255
+        crop = ast.literal_eval(crop)
+    return list(crop), None
+
+
+def _pred_eval(pred_path, gt_path, crop):
+    """Drop-in for eval_depth_edges.py:179-230: one predicted edge image against one GT edge image, binarised at
+    0.5, cropped (or multiplied by a mask image), ``evaluate_boundaries(thresholds=1, apply_thinning=False,
+    max_dist=0.002)`` -> ``EvalResult``."""
+    import cv2
+    crop, mask = _crop_or_mask(crop)
+
+    def load(path):
+        im = cv2.imread(path.split("\n")[0])[:, :, 0] / 255
+        im[im > 0.5] = 1.0
+        im[im < 0.5] = 0.0
+        if mask is not None:
+            return im * mask
+        if len(crop) > 0:
+            return im[crop[2]:crop[3], crop[0]:crop[1]]
+        return im
+
+    pred, gt_b = load(pred_path), load(gt_path)
+    count_r, sum_r, count_p, sum_p, used_thresholds = evaluate_boundaries(
+        pred, [gt_b], thresholds=1, apply_thinning=False, max_dist=0.002)
+    rec, prec, f1 = compute_rec_prec_f1(count_r, sum_r, count_p, sum_p)
+    best_ndx = np.argmax(f1)
+    return EvalResult(count_r, sum_r, count_p, sum_p, count_r[best_ndx], sum_r[best_ndx], count_p[best_ndx],
+                      sum_p[best_ndx], used_thresholds, rec, prec)
 
 
 def _dist_info():
@@ -236,14 +309,20 @@ def sweep_counts(depth: torch.Tensor, gt: torch.Tensor, edge_thresh_range, gt_cr
 
 
 def pr_evaluation_arrays(depths: Sequence[np.ndarray], gts: Sequence[np.ndarray], edge_thresh_range=None,
-                         gt_crop=(44, 1197, 153, 371), min_depth=0.0, max_depth=80.0, batch: int = 32):
+                         gt_crop=(44, 1197, 153, 371), min_depth=0.0, max_depth=80.0, batch: int = 32,
+                         mask: Optional[np.ndarray] = None):
     """Array-level ``pr_evaluation``: predicted depth maps (any size; resized to the GT size on the
     host with cv2.INTER_LINEAR as edge.py:76-78 does) and GT edge images (uint8, >127 = edge).
-    Images are sharded over ``torch.distributed`` ranks when initialised.
-    -> (precision_vec, recall_vec, counts int64[T,4])"""
+    Images are sharded over ``torch.distributed`` ranks when initialised.  ``mask`` is the mask-image branch of
+    ``_pred_eval`` (eval_depth_edges.py:182-186, 198-200, 209-210): a float plane in [0,1] that multiplies both maps
+    instead of the crop.
+    -> (precision_vec, recall_vec, counts int64[T,4]; with a mask the sum_r column is returned separately as float64,
+    see ``_masked_evaluation``)"""
     import cv2
     if edge_thresh_range is None:
         edge_thresh_range = list(range(20, 241, 20))
+    if mask is not None:
+        return _masked_evaluation(depths, gts, edge_thresh_range, np.asarray(mask), min_depth, max_depth, batch)
     rank, world = _dist_info()
     dev = torch.device("cuda", torch.cuda.current_device())
     counts = torch.zeros((len(edge_thresh_range), 4), dtype=torch.int64, device=dev)
@@ -274,6 +353,54 @@ def pr_evaluation_arrays(depths: Sequence[np.ndarray], gts: Sequence[np.ndarray]
     return [float(p) for p in prec], [float(r) for r in rec], counts
 
 
+def _masked_evaluation(depths, gts, edge_thresh_range, mask, min_depth, max_depth, batch):
+    """``pr_evaluation`` with a mask image instead of a crop.  Per image and Canny setting the reference evaluates
+    ``pred * mask`` (binarised again at ``>= 0.5`` by ``thresholds=1``) against ``gt * mask`` (boundary where non-zero)
+    on the FULL plane, so: predicted pixel kept iff ``mask >= 0.5``, GT pixel kept iff ``mask != 0``, the matching
+    radius is that of the uncropped plane, and ``sum_r`` is the fractional ``(gt * mask).sum()`` (float64, summed per
+    image, then over images in list order -- eval_depth_edges.py:138, 299)."""
+    import cv2
+    rank, world = _dist_info()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    T = len(edge_thresh_range)
+    counts = torch.zeros((T, 4), dtype=torch.int64, device=dev)
+    keep_p = torch.from_numpy(np.ascontiguousarray(mask >= 0.5)).to(dev)
+    keep_g = torch.from_numpy(np.ascontiguousarray(mask != 0)).to(dev)
+    order = np.argsort(-np.asarray(edge_thresh_range), kind="stable")
+    pairs = [(int(edge_thresh_range[i] / 2), int(edge_thresh_range[i])) for i in order]
+    mine = shard_indices(len(depths), rank, world)
+    sum_r = 0.0
+    H, W = mask.shape
+    for s0 in range(0, len(mine), batch):
+        chunk = mine[s0:s0 + batch]
+        dep = []
+        for i in chunk:
+            d = np.asarray(depths[i])
+            if d.shape != (H, W):
+                d = cv2.resize(d, (W, H), interpolation=cv2.INTER_LINEAR)
+            dep.append(d if d.dtype == np.float32 else d.astype(np.float64))
+        if len({d.dtype for d in dep}) > 1:
+            dep = [d.astype(np.float64) for d in dep]
+        gb = [(np.asarray(gts[i]) > 127) for i in chunk]
+        for g in gb:
+            sum_r = sum_r + (g.astype(np.float64) * mask).sum()
+        d_dev = torch.from_numpy(np.stack(dep)).to(dev)
+        g_dev = torch.from_numpy(np.stack(gb)).to(dev)
+        levels = canny_from_depth(d_dev, pairs, min_depth, max_depth, want_edges=False, want_levels=True)
+        levels = torch.where(keep_p[None], levels, torch.full_like(levels, 255))
+        c = pr_counts(levels, (g_dev & keep_g[None]).to(torch.uint8), n_levels=T, max_dist=0.002, crop=None)
+        counts += c[_reorder_index(tuple(int(v) for v in np.argsort(order)), c.device)]
+    all_reduce_counts(counts)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([sum_r], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        sum_r = float(t.item())
+    c = counts.cpu().numpy().astype(np.float64)
+    rec, prec, _ = compute_rec_prec_f1(c[:, 0], np.full(T, sum_r), c[:, 2], c[:, 3])
+    return [float(p) for p in prec], [float(r) for r in rec], counts
+
+
 def pr_evaluation(edge_list, pred_list, edge_thresh_range=None, gt_crop=[44, 1197, 153, 371], min_depth=0.0,
                   max_depth=80.0, save_folder="temp_output", num_workers=4):
     """Drop-in for eval_depth_edges.py:232-348 -> (precision_vec, recall_vec).
@@ -286,5 +413,8 @@ def pr_evaluation(edge_list, pred_list, edge_thresh_range=None, gt_crop=[44, 119
         edge_gt_list = edge_gt_list[0:len(edge_gt_list):int(ratio)]
     gts = [cv2.imread(p.split("\n")[0])[:, :, 0] for p in edge_gt_list]
     depths = [read_depth_file(p.split("\n")[0]) for p in depth_pred_list]
-    prec, rec, _ = pr_evaluation_arrays(depths, gts, edge_thresh_range, gt_crop, min_depth, max_depth)
+    # gt_crop is handed to _pred_eval as str(gt_crop) (:291-294): a path to an existing mask image selects the
+    # mask branch
+    crop, mask = _crop_or_mask(gt_crop if isinstance(gt_crop, str) else list(gt_crop))
+    prec, rec, _ = pr_evaluation_arrays(depths, gts, edge_thresh_range, crop, min_depth, max_depth, mask=mask)
     return prec, rec

@@ -63,7 +63,7 @@ def _attrs(is_grad, is_sigmoid, pred_is_inverse, sigmoid_thresh, weight, pos_to_
 # ---------------------------------------------------------------------------
 # PyTorch custom ops (schemas) backed by the C ABI
 # ---------------------------------------------------------------------------
-_LIBDEF = torch.library.Library("mte", "DEF")
+_LIBDEF = runtime.LIBDEF
 _LIBDEF.define(
     "edge_loss_fwd(Tensor[] pred, Tensor[] edge, Tensor[] normal, Tensor[] mask, float[] scale_weights, "
     "bool is_grad, bool is_sigmoid, bool pred_is_inverse, float sigmoid_thresh, float weight, float pos_to_neg) "
@@ -76,7 +76,7 @@ _LIBDEF.define(
 
 def _edge_loss_fwd_cuda(pred, edge, normal, mask, scale_weights, is_grad, is_sigmoid, pred_is_inverse,
                         sigmoid_thresh, weight, pos_to_neg):
-    dev = pred[0].device
+    dev = runtime.same_device(pred, edge, normal, mask)
     n = len(pred)
     grad_maps = [torch.empty_like(e) for e in edge]
     # 1 byte/px side output (picked direction + sign of the response) that lets the backward skip the stencil
@@ -86,29 +86,28 @@ def _edge_loss_fwd_cuda(pred, edge, normal, mask, scale_weights, is_grad, is_sig
     at = _attrs(is_grad, is_sigmoid, pred_is_inverse, sigmoid_thresh, weight, pos_to_neg)
     losses = torch.empty(1 + n, dtype=torch.float32, device=dev)
     ctx = torch.empty(_lib.lib.mte_edge_loss_ctx_bytes(sc, n) // 4, dtype=torch.float32, device=dev)
-    nbytes = _lib.lib.mte_edge_loss_workspace_bytes(sc, n)
-    ws = runtime.workspace(dev, nbytes)
-    _lib.check(_lib.lib.mte_edge_loss_fwd(sc, n, C.byref(at), losses.data_ptr(), ctx.data_ptr(), ws.data_ptr(),
-                                          ws.numel(), runtime.current_stream_ptr(dev)), "mte_edge_loss_fwd")
+    with torch.cuda.device(dev):
+        ws = runtime.workspace(dev, _lib.lib.mte_edge_loss_workspace_bytes(sc, n))
+        runtime.call("mte_edge_loss_fwd", dev, sc, n, C.byref(at), losses.data_ptr(), ctx.data_ptr(), ws.data_ptr(),
+                     ws.numel(), runtime.current_stream_ptr(dev))
     return losses, ctx, grad_maps, stash
 
 
 def _edge_loss_bwd_cuda(grad_losses, ctx, pred, edge, normal, mask, grad_maps, stash, scale_weights, is_grad,
                         is_sigmoid, pred_is_inverse, sigmoid_thresh, weight, pos_to_neg):
-    dev = pred[0].device
+    dev = runtime.same_device(grad_losses, ctx, pred, edge, normal, mask, grad_maps, stash)
     n = len(pred)
     grads = [torch.empty_like(p) for p in pred]
     sc = _scales_struct(pred, edge, normal, mask, grad_maps if stash else None, grads, scale_weights, stash)
     at = _attrs(is_grad, is_sigmoid, pred_is_inverse, sigmoid_thresh, weight, pos_to_neg)
-    nbytes = _lib.lib.mte_edge_loss_workspace_bytes(sc, n)
-    ws = runtime.workspace(dev, nbytes)
-    _lib.check(_lib.lib.mte_edge_loss_bwd(sc, n, C.byref(at), grad_losses.data_ptr(), ctx.data_ptr(),
-                                          ws.data_ptr(), ws.numel(), runtime.current_stream_ptr(dev)),
-               "mte_edge_loss_bwd")
+    with torch.cuda.device(dev):
+        ws = runtime.workspace(dev, _lib.lib.mte_edge_loss_workspace_bytes(sc, n))
+        runtime.call("mte_edge_loss_bwd", dev, sc, n, C.byref(at), grad_losses.data_ptr(), ctx.data_ptr(),
+                     ws.data_ptr(), ws.numel(), runtime.current_stream_ptr(dev))
     return grads
 
 
-_LIBIMPL = torch.library.Library("mte", "IMPL", "CUDA")
+_LIBIMPL = runtime.LIBIMPL
 _LIBIMPL.impl("edge_loss_fwd", _edge_loss_fwd_cuda)
 _LIBIMPL.impl("edge_loss_bwd", _edge_loss_bwd_cuda)
 
@@ -221,11 +220,12 @@ class _AltEdgeLossFn(torch.autograd.Function):
         dev = pred.device
         out = torch.empty(2, dtype=torch.float32, device=dev)
         actx = torch.empty(4, dtype=torch.float32, device=dev)
-        ws = runtime.workspace(dev, _lib.lib.mte_edge_loss_alt_workspace_bytes(B, H, W))
-        _lib.check(_lib.lib.mte_edge_loss_alt_fwd(
-            grad_maps[0].data_ptr(), edge.data_ptr(), mask[0].data_ptr() if mask else None, B, H, W, types,
-            int(is_sigmoid), thresh, weight, losses.data_ptr() if types & _lib.MTE_LOSS_CE else None, out.data_ptr(),
-            actx.data_ptr(), ws.data_ptr(), ws.numel(), runtime.current_stream_ptr(dev)), "mte_edge_loss_alt_fwd")
+        with torch.cuda.device(dev):
+            ws = runtime.workspace(dev, _lib.lib.mte_edge_loss_alt_workspace_bytes(B, H, W))
+            runtime.call("mte_edge_loss_alt_fwd", dev,
+                         grad_maps[0].data_ptr(), edge.data_ptr(), mask[0].data_ptr() if mask else None, B, H, W, types,
+                         int(is_sigmoid), thresh, weight, losses.data_ptr() if types & _lib.MTE_LOSS_CE else None,
+                         out.data_ptr(), actx.data_ptr(), ws.data_ptr(), ws.numel(), runtime.current_stream_ptr(dev))
         ctx.cfg = cfg
         ctx.has_stash = len(stash) > 0
         ctx.save_for_backward(pred, saved, actx, grad_maps[0], *stash)
@@ -248,12 +248,13 @@ class _AltEdgeLossFn(torch.autograd.Function):
             accumulate = 1
         else:
             grad = torch.empty_like(pred)
-        ws = runtime.workspace(dev, _lib.lib.mte_edge_loss_alt_workspace_bytes(B, H, W))
-        _lib.check(_lib.lib.mte_edge_loss_alt_bwd(
-            gmap.data_ptr(), edge.data_ptr(), mask[0].data_ptr() if mask else None,
-            stash[0].data_ptr() if stash else None, pred.data_ptr(), B, H, W, types, int(is_grad), int(is_sigmoid), 0,
-            thresh, weight, gl.data_ptr(), actx.data_ptr(), grad.data_ptr(), accumulate, ws.data_ptr(), ws.numel(),
-            runtime.current_stream_ptr(dev)), "mte_edge_loss_alt_bwd")
+        with torch.cuda.device(dev):
+            ws = runtime.workspace(dev, _lib.lib.mte_edge_loss_alt_workspace_bytes(B, H, W))
+            runtime.call("mte_edge_loss_alt_bwd", dev,
+                         gmap.data_ptr(), edge.data_ptr(), mask[0].data_ptr() if mask else None,
+                         stash[0].data_ptr() if stash else None, pred.data_ptr(), B, H, W, types, int(is_grad),
+                         int(is_sigmoid), 0, thresh, weight, gl.data_ptr(), actx.data_ptr(), grad.data_ptr(), accumulate,
+                         ws.data_ptr(), ws.numel(), runtime.current_stream_ptr(dev))
         return None, grad
 
 

@@ -18,28 +18,42 @@ __all__ = ["dee_postprocess", "non_max_suppression", "hysteresis", "edge_normals
 _DT = {torch.float32: _lib.MTE_F32, torch.float64: _lib.MTE_F64}
 
 
+def _dee_postprocess_cuda(prob, normals, nms, hysteresis, t_low, t_high, out_f64):
+    with runtime.on_device(prob) as dev:
+        p = prob.contiguous()
+        N, H, W = p.shape
+        want_edges = nms or hysteresis
+        out_dtype = torch.float64 if out_f64 else torch.float32
+        nrm = torch.empty((N, H, W) if normals else (0,), dtype=torch.uint8, device=dev)
+        out = torch.empty((N, H, W) if want_edges else (0,), dtype=out_dtype, device=dev)
+        ws = runtime.workspace(dev, _lib.lib.mte_dee_workspace_bytes(N, H, W))
+        runtime.call("mte_dee_postprocess", dev, p.data_ptr(), _DT[p.dtype], N, H, W, int(nms), int(hysteresis),
+                     float(t_low), float(t_high), nrm.data_ptr() if normals else None,
+                     out.data_ptr() if want_edges else None, _DT[out_dtype], ws.data_ptr(), ws.numel(),
+                     runtime.current_stream_ptr(dev))
+    return nrm, out
+
+
+runtime.define_op("dee_postprocess(Tensor prob, bool normals, bool nms, bool hysteresis, float t_low, float t_high, "
+                  "bool out_f64) -> (Tensor, Tensor)", _dee_postprocess_cuda)
+
+
 def dee_postprocess(prob: torch.Tensor, *, normals: bool = True, nms: bool = True, hysteresis: bool = True,
                     t_low: float = 0.3, t_high: float = 0.7, out_dtype: torch.dtype = torch.float64):
     """prob: CUDA float32/float64 [N,H,W] (or [H,W]) edge-probability maps.
 
     Returns ``(normals_u8 or None, edges or None)``: ``normals_u8`` is the quantised
     ``atan2(-sobel_y, sobel_x)`` plane; ``edges`` the NMS / hysteresis output (``out_dtype``; the
-    reference yields float64 as soon as NMS has run)."""
+    reference yields float64 as soon as NMS has run).  Torch custom op ``mte::dee_postprocess``."""
     runtime.require_cuda(prob, "prob")
-    if prob.dtype not in _DT:
-        raise _lib.MteError(f"unsupported dtype {prob.dtype}")
+    if prob.dtype not in _DT or out_dtype not in _DT:
+        raise _lib.MteError(f"unsupported dtype {prob.dtype} / {out_dtype}")
     squeeze = prob.dim() == 2
-    p = (prob.unsqueeze(0) if squeeze else prob).contiguous()
-    N, H, W = p.shape
-    dev = p.device
-    want_edges = nms or hysteresis
-    nrm = torch.empty((N, H, W), dtype=torch.uint8, device=dev) if normals else None
-    out = torch.empty((N, H, W), dtype=out_dtype, device=dev) if want_edges else None
-    ws = runtime.workspace(dev, _lib.lib.mte_dee_workspace_bytes(N, H, W))
-    _lib.check(_lib.lib.mte_dee_postprocess(
-        p.data_ptr(), _DT[p.dtype], N, H, W, int(nms), int(hysteresis), float(t_low), float(t_high),
-        runtime.ptr(nrm), runtime.ptr(out), _DT[out_dtype], ws.data_ptr(), ws.numel(),
-        runtime.current_stream_ptr(dev)), "mte_dee_postprocess")
+    p = prob.unsqueeze(0) if squeeze else prob
+    nrm, out = torch.ops.mte.dee_postprocess(p, bool(normals), bool(nms), bool(hysteresis), float(t_low),
+                                             float(t_high), out_dtype == torch.float64)
+    nrm = nrm if normals else None
+    out = out if (nms or hysteresis) else None
     if squeeze:
         nrm = None if nrm is None else nrm[0]
         out = None if out is None else out[0]

@@ -13,6 +13,7 @@ eval_depth_edges goldens use the oracle stand-in for `bsds_metric.bsds`; they pi
 the arithmetic around the matcher (binarise, crop, threshold grid, sums, P/R),
 not the matcher itself.
 """
+import glob
 import os
 import sys
 import tempfile
@@ -275,6 +276,56 @@ def gen_pr():
     print("pr:", {k: v for k, v in out.items() if k.startswith("pr_") and np.size(v) < 8})
 
 
+def gen_pr_mask():
+    """The mask-image branch of _pred_eval (eval_depth_edges.py:182-186, 198-200, 209-210) through the UNMODIFIED
+    pr_evaluation / _pred_eval: gt_crop is the path of a mask PNG with values 0 / 127 (< 0.5) / 128 (>= 0.5) / 255."""
+    from oracle import pr_counts as opr, thin as othin
+    import types
+    cp = types.ModuleType("correspond_pixels")
+    cp.correspond_pixels = opr.correspond_pixels
+    th = types.ModuleType("thin")
+    th.binary_thin = othin.binary_thin
+    ede = load_eval_depth_edges(th, cp)
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        H, W = 120, 260
+        mask = np.full((H, W), 255, np.uint8)
+        mask[:, :40] = 0
+        mask[:30, :] = 127
+        mask[60:90, 100:200] = 128
+        mask[100:, 200:] = 64
+        mp = os.path.join(tmp, "mask.png")
+        cv2.imwrite(mp, mask)
+        out["mask"] = mask
+        gts, preds = [], []
+        for i in range(2):
+            g, d = synth_gt_and_depth(H, W, 700 + i)
+            gp = os.path.join(tmp, f"gt{i}.png")
+            cv2.imwrite(gp, g.astype(np.uint8) * 255)
+            dp = os.path.join(tmp, f"pred{i}.npy")
+            np.save(dp, d)
+            gts.append(gp)
+            preds.append(dp)
+            out[f"gt{i}"] = np.packbits(g)
+            out[f"depth_u16_{i}"] = np.round(d * 256).astype(np.uint16)
+        out["shape"] = np.array([H, W])
+        rng = [40, 120, 240]
+        pv, rv = ede.pr_evaluation(gts, preds, edge_thresh_range=rng, gt_crop=mp,
+                                   save_folder=os.path.join(tmp, "out"), num_workers=1)
+        out["range"] = np.array(rng)
+        out["precision"] = np.array(pv, np.float64)
+        out["recall"] = np.array(rv, np.float64)
+        # _pred_eval itself on the last setting's predicted edge image of scene 0 (JPEG on disk), mask and list crop
+        pe = sorted(glob.glob(os.path.join(tmp, "out", "*_pred_canny_edge.jpeg")))[0]
+        out["pred_edge0"] = cv2.imread(pe)[:, :, 0]
+        for tag, crop in (("mask", mp), ("crop", str([10, 250, 8, 112])), ("nocrop", "[]")):
+            r = ede._pred_eval(pe, gts[0], crop)
+            out[f"pe_{tag}"] = np.array([r.count_r_overall[0], r.sum_r_overall[0], r.count_p_overall[0],
+                                         r.sum_p_overall[0], r.recall[0], r.precision[0]], np.float64)
+    np.savez_compressed(os.path.join(HERE, "pr_mask.npz"), **out)
+    print("pr_mask:", out["precision"], out["recall"], out["pe_mask"], out["pe_crop"])
+
+
 def gen_targets():
     """resize_depth_preserve + the /255 rule of resize_sample from the UNMODIFIED datasets/augmentations.py, the normal
     decode expression of datasets/gta_dataset.py:413 and the float32 cast of to_tensor_sample."""
@@ -356,6 +407,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "chamfer":
         gen_chamfer()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "pr_mask":
+        gen_pr_mask()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "targets":
         gen_targets()
         sys.exit(0)
@@ -369,5 +423,6 @@ if __name__ == "__main__":
     gen_canny()
     gen_dee()
     gen_pr()
+    gen_pr_mask()
     gen_chamfer()
     gen_targets()

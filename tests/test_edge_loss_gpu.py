@@ -113,6 +113,72 @@ def _sign_ambiguous(depth, normal):
     return ndimage.binary_dilation(risky, structure=np.ones((1, 3, 3), bool))[:, None]
 
 
+@pytest.mark.parametrize("inverse", [False, True])
+def test_config1_raw_depth_parity(inverse):
+    """BASELINE.json config 1 / SURVEY.md 8(d), exactly: B=4 x 384x1280, RAW U(1,80) fp32 depth (seed 0, no grid
+    snapping), soft edges (seed 1), u8-decoded normals (seed 2), mask=None, cross_entropy, weight 10, T=4; depth entry
+    and inverse-depth entry (inv2depth fused).  Loss within 1e-5 relative; grad map within 1e-5 of its max; EVERY
+    gradient pixel outside 1e-5 of max|grad| must be sign-ambiguous (|c| within fp32 rounding of 0, where sign(c) --
+    and with it the gradient of |c| -- depends on the summation order of the 3x3 stencil in any fp32 implementation)."""
+    from mindtheedge_b200.losses import multiscale_edge_loss
+    from oracle.edge_loss import edge_loss_torch
+    B, H, W = 4, 384, 1280
+    depth = torch.rand(B, 1, H, W, generator=torch.Generator().manual_seed(0)) * 79 + 1
+    g1 = torch.Generator().manual_seed(1)
+    edge = (torch.rand(B, 1, H, W, generator=g1) < 0.015).float() * torch.rand(B, 1, H, W, generator=g1).clamp(min=0.3)
+    k = torch.randint(0, 256, (B, 1, H, W), generator=torch.Generator().manual_seed(2)).float()
+    normal = ((360 * k / 255 - 180) * np.pi / 180).float()
+    if inverse:
+        x0 = 1.0 / depth
+        seen = 1.0 / x0.clamp(min=1e-6)     # the depth both implementations see (utils/depth.py:104-121)
+    else:
+        x0, seen = depth, depth
+    xr = x0.clone().requires_grad_(True)
+    dr = 1.0 / xr.clamp(min=1e-6) if inverse else xr
+    lr, gr = edge_loss_torch(dr, edge, None, True, True, 4, normal, weight=10.0)
+    lr.backward()
+    xg = x0.cuda().requires_grad_(True)
+    total, _, maps = multiscale_edge_loss([xg], [edge.cuda()], None, [normal.cuda()], scale_weights=[1.0], weight=10.0,
+                                          pred_is_inverse=inverse)
+    total.backward()
+    rel = abs(total.item() - lr.item()) / abs(lr.item())
+    assert rel <= RTOL, (total.item(), lr.item(), rel)
+    _plane_close(maps[0].cpu().numpy(), gr.numpy())
+    got, ref = xg.grad.cpu().numpy(), xr.grad.numpy()
+    bad = np.abs(got - ref) > RTOL * float(np.abs(ref).max())
+    amb = _sign_ambiguous(seen.numpy(), normal.numpy())
+    assert not (bad & ~amb).any(), (int(bad.sum()), int((bad & ~amb).sum()))
+    assert bad.sum() <= 64, int(bad.sum())   # a handful of pixels out of 1.97 M, not a tolerance in disguise
+    print(f"config1 inverse={inverse}: loss rel err {rel:.2e}, grad pixels out of tol {int(bad.sum())} "
+          f"(all sign-ambiguous), ambiguous set {int(amb.sum())}")
+
+
+def test_nan_and_inf_inputs_give_nan_loss():
+    """The reference's loss is NaN as soon as the prediction holds a NaN or an Inf (conv2d: 0 * inf) or a target is NaN;
+    the fixed-point accumulators must not turn that into a finite number."""
+    from mindtheedge_b200.losses import edge_loss, multiscale_edge_loss
+    depth, edge, normal = _inputs(2, 40, 128, seed=5)
+    for what in ("nan_pred", "inf_pred", "nan_edge", "nan_inv"):
+        d, e = depth.clone(), edge.clone()
+        if what == "nan_pred":
+            d[1, 0, 17, 33] = float("nan")
+        elif what == "inf_pred":
+            d[0, 0, 3, 100] = float("inf")
+        elif what == "nan_edge":
+            e[1, 0, 39, 127] = float("nan")
+        if what == "nan_inv":
+            x = 1.0 / d
+            x[0, 0, 0, 0] = float("nan")
+            total, _, _ = multiscale_edge_loss([x.cuda()], [e.cuda()], None, [normal.cuda()], scale_weights=[1.0],
+                                               weight=10.0, pred_is_inverse=True)
+        else:
+            total, _ = edge_loss(d.cuda(), e.cuda(), None, True, True, 4, normal.cuda(), weight=10.0)
+        assert torch.isnan(total).item(), what
+    # and the accumulators are clean again afterwards
+    l0, _ = edge_loss(depth.cuda(), edge.cuda(), None, True, True, 4, normal.cuda(), weight=10.0)
+    assert torch.isfinite(l0).item()
+
+
 def test_multiscale_matches_per_scale_loop():
     """One launch over 4 scales == the reference's per-scale loop + /4
     (models/SemiSupEdgeModel.py:164-198), inv2depth fused."""
@@ -229,7 +295,9 @@ def test_streaming_kernels_small_and_ragged_shapes(shape, inv):
         assert torch.equal(gm.cpu(), gmap_ref)
         _plane_close(got_grad, ref_grad)
     else:
-        _plane_close(gm.cpu().numpy(), gmap_ref.numpy(), rtol=1e-4)
-        # responses of 1/(1/d) carry rounding noise: pixels whose response is ~0 may flip sign(c); allow <1 % of them
+        _plane_close(gm.cpu().numpy(), gmap_ref.numpy())
+        # 1/(1/d) is off the 1/64 grid by an ulp, so a response that is exactly 0 on the grid comes out as +-1 ulp:
+        # sign(c) is then decided by the summation order.  Every pixel outside the tolerance must be one of those.
         bad = np.abs(got_grad - ref_grad) > RTOL * max(float(np.abs(ref_grad).max()), 1e-30)
-        assert bad.mean() <= 0.02, bad.mean()
+        amb = _sign_ambiguous(d_fused.numpy(), normal.numpy())
+        assert not (bad & ~amb).any(), (int(bad.sum()), int((bad & ~amb).sum()))

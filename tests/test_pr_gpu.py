@@ -160,20 +160,97 @@ def test_kitti_size_sweep_vs_oracle():
     assert ref[:, 0].min() > 1000  # the matcher has real work
 
 
-def test_ddad_size_uncropped_property():
-    """Config 5 shape (1216x1936, no crop, radius 4.57 px).  Size-independent properties: counts are
-    bounded by both sides, monotone in the threshold, and an identical pred/GT pair matches fully."""
+def test_bench_kitti_set_counts_vs_oracle():
+    """The workload bench.py times (BASELINE.json config 2): the reference's bundled KITTI-DE GT maps against
+    bench.kitti_like_set's synthetic predicted depth, shipped wiring (12 Canny settings, KITTI crop, max_dist 0.002).
+    26 of the 102 images incl. the two heaviest (#19, #29): counts bit-exact against the oracle."""
+    import bench
+    from mindtheedge_b200.eval_depth_edges import sweep_counts
+    from oracle import pr_counts as opr
+    depths, gts = bench.kitti_like_set(102, 7000)
+    idx = sorted(set([19, 29] + list(range(0, 102, 4))))
+    assert len(idx) >= 24
+    rng = list(range(20, 241, 20))
+    d = torch.from_numpy(depths[idx]).cuda()
+    g = torch.from_numpy(gts[idx]).cuda()
+    c = sweep_counts(d, g, rng, bench.KITTI_CROP, 0.0, 80.0, max_dist=0.002).cpu().numpy()
+    ref = opr.pr_sweep_counts([depths[i] for i in idx], [gts[i] * 255 for i in idx], rng, tuple(bench.KITTI_CROP))
+    assert np.array_equal(c, ref), (c.tolist(), ref.tolist())
+    assert ref[:, 0].min() > 5000
+
+
+def test_ddad_size_uncropped_vs_oracle():
+    """Config 5 shape (1216x1936, NO crop, matching radius 4.57 px = 69 offsets, ~26 k GT + ~27 k predicted pixels
+    per window -- more than one SM's shared memory holds): counts bit-exact against the C oracle for all 12
+    settings, plus the size-independent properties."""
     from mindtheedge_b200.eval_depth_edges import correspond_pixels_batch, sweep_counts
+    from oracle import pr_counts as opr
     gt, depth = scene_with_gt(1216, 1936, 5, n_rect=120)
     d = torch.from_numpy(depth)[None].cuda()
     g = torch.from_numpy((gt > 127).astype(np.uint8))[None].cuda()
     rng = list(range(20, 241, 20))
     c = sweep_counts(d, g, rng, None, 0.0, 80.0, max_dist=0.002).cpu().numpy()
+    ref = opr.pr_sweep_counts([depth], [gt], rng, gt_crop=None)
+    assert np.array_equal(c, ref), (c.tolist(), ref.tolist())
     assert (c[:, 0] == c[:, 2]).all() and (c[:, 0] <= c[:, 1]).all() and (c[:, 0] <= c[:, 3]).all()
     assert (np.diff(c[:, 3]) <= 0).all() and (np.diff(c[:, 0]) <= 0).all()  # higher threshold -> fewer edges
-    assert (c[:, 1] == int((gt > 127).sum())).all()
     _, _, cnt = correspond_pixels_batch(g, g, 0.002, want_maps=False)
     assert cnt.item() == int((gt > 127).sum())
+
+
+def _mask_fixture(tmp_path):
+    import cv2
+    z = np.load(os.path.join(GOLDEN, "pr_mask.npz"))
+    H, W = (int(v) for v in z["shape"])
+    mp = str(tmp_path / "mask.png")
+    cv2.imwrite(mp, z["mask"])
+    gts, preds = [], []
+    for i in range(2):
+        g = np.unpackbits(z[f"gt{i}"])[:H * W].reshape(H, W)
+        gp, dp = str(tmp_path / f"gt{i}.png"), str(tmp_path / f"pred{i}.npy")
+        cv2.imwrite(gp, g.astype(np.uint8) * 255)
+        np.save(dp, (z[f"depth_u16_{i}"] / 256).astype(np.float32))
+        gts.append(gp)
+        preds.append(dp)
+    return z, mp, gts, preds
+
+
+def test_pr_evaluation_mask_image_golden(tmp_path):
+    """The mask-image branch of _pred_eval (eval_depth_edges.py:182-186, 198-200, 209-210) through pr_evaluation:
+    precision / recall equal to the unmodified reference run (fractional sum_r, full-plane matching radius)."""
+    from mindtheedge_b200.eval_depth_edges import pr_evaluation
+    z, mp, gts, preds = _mask_fixture(tmp_path)
+    pv, rv = pr_evaluation(gts, preds, edge_thresh_range=[int(v) for v in z["range"]], gt_crop=mp)
+    assert np.array_equal(np.array(pv), z["precision"]), (pv, z["precision"])
+    assert np.array_equal(np.array(rv), z["recall"]), (rv, z["recall"])
+
+
+def test_pred_eval_golden(tmp_path):
+    """_pred_eval on one predicted edge image: mask image, list crop and empty crop -- EvalResult fields equal to the
+    reference's."""
+    import cv2
+    from mindtheedge_b200.eval_depth_edges import _pred_eval
+    z, mp, gts, _ = _mask_fixture(tmp_path)
+    pe = str(tmp_path / "pred_edge0.png")
+    cv2.imwrite(pe, z["pred_edge0"])   # lossless copy of the JPEG-decoded plane the reference read
+    for tag, crop in (("mask", mp), ("crop", str([10, 250, 8, 112])), ("nocrop", "[]")):
+        r = _pred_eval(pe, gts[0], crop)
+        got = np.array([r.count_r_overall[0], r.sum_r_overall[0], r.count_p_overall[0], r.sum_p_overall[0],
+                        r.recall[0], r.precision[0]])
+        assert np.array_equal(got, z[f"pe_{tag}"]), (tag, got, z[f"pe_{tag}"])
+        assert r.count_r_best == r.count_r_overall[0] and r.used_thresholds[0] == 0.5
+
+
+def test_sum_r_is_gt_sum_not_count():
+    """evaluate_boundaries: sum_r is gt.sum() (eval_depth_edges.py:138) on both code paths, also for GT maps that are
+    not 0/1 (255-valued PNG planes, soft maps)."""
+    from mindtheedge_b200.eval_depth_edges import evaluate_boundaries
+    pred, gt = random_boundary_maps(60, 90, 7)
+    g255 = gt.astype(np.float64) * 255
+    for thin_flag in (False, True):
+        c_r, s_r, c_p, s_p, _ = evaluate_boundaries(pred.astype(np.float64), [g255], thresholds=1,
+                                                    apply_thinning=thin_flag)
+        assert s_r[0] == g255.sum()
 
 
 def test_thin_vs_oracle():
