@@ -46,6 +46,9 @@ _SIGNATURES = {
     "mte_edge_loss_ctx_bytes": (_sz, [C.POINTER(LossScale), _i]),
     "mte_edge_loss_fwd": (_i, [C.POINTER(LossScale), _i, C.POINTER(LossAttrs), _vp, _vp, _vp, _sz, _vp]),
     "mte_edge_loss_bwd": (_i, [C.POINTER(LossScale), _i, C.POINTER(LossAttrs), _vp, _vp, _vp, _sz, _vp]),
+    "mte_edge_loss_fused_supported": (_i, [C.POINTER(LossScale), _i, C.POINTER(LossAttrs)]),
+    "mte_edge_loss_fwd_grad": (_i, [C.POINTER(LossScale), _i, C.POINTER(LossAttrs), _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mte_edge_loss_grad_rescale": (_i, [C.POINTER(LossScale), _i, _vp, _vp, _vp, _vp]),
     "mte_canny_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "mte_canny_from_depth": (_i, [_vp, _i, _i, _i, _i, _d, _d, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i,
                                   _vp, _vp, _vp, _sz, _vp]),

@@ -252,7 +252,9 @@ extern "C" size_t mte_edge_loss_ctx_bytes(const mte_loss_scale_t *sc, int n) {
     if (validate(sc, n)) return 0;
     size_t imgs = 0;
     for (int i = 0; i < n; i++) imgs += sc[i].B;
-    return align_up((imgs + 2 * MTE_MAX_SCALES) * sizeof(float), 16);
+    // alpha per image, {coef, maskBinary} per scale, then (one-pass variant) the factor grad_pred carries per scale and
+    // the rescale kernel's ticket
+    return align_up((imgs + 3 * MTE_MAX_SCALES + 4) * sizeof(float), 16);
 }
 
 extern "C" int mte_edge_loss_fwd(const mte_loss_scale_t *sc, int n, const mte_loss_attrs_t *at, float *loss_out,

@@ -1,0 +1,520 @@
+// Edge loss, ONE PASS: loss + grad map + d loss / d pred in a single launch (shipped configuration: directional
+// responses, no mask, prediction at the target size, rows of whole float4s).
+//
+// Why one pass is possible: the class balance alpha_b = Wn_b / (Wp_b + Wn_b) (grad_loss.py:169-178) depends only on
+// the TARGETS (Wp_b = sum of the soft edge labels of image b), not on the prediction.  So the kernel
+//   phase 1  sums the edge plane (every warp over the rows it will process: 4 B/px, and the lines stay in L2),
+//   -------- grid barrier (persistent cooperative grid, one CTA per SM) --------
+//   phase 2  streams depth / edge / normal rows once through the per-warp cp.async ring: 3x3 directional response ->
+//            |c| (grad map out) -> p = sigmoid(|c| - T) -> the two log terms (loss sums, order-independent fixed-point
+//            atomics as in edge_loss_fwd_kernel) AND d loss / d|c| with the now-known alpha -> the 3x3 adjoint scatter
+//            into three rolling output rows -> d loss / d pred out (inv2depth chain rule fused),
+// for the upstream gradient the caller EXPECTS (1 for loss.backward(); the value of the previous step otherwise).
+// The autograd backward is then mte_edge_loss_grad_rescale: a kernel that exits at once when the actual upstream
+// gradient equals the expected one and rescales in place otherwise.
+// HBM traffic: 12 B/px in + 8 B/px out = 20 B/px instead of 34 B/px over two launches with a stash round trip.
+//
+// Reference arithmetic preserved: packnet_code/packnet_sfm/losses/grad_loss.py:65-95 (responses, band pick),
+// :122-159 (sigmoid, weight), :161-219 (class-balanced BCE); backward = SURVEY.md A.1.
+#include <string.h>
+
+#include "edge_loss_kernels.cuh"
+
+namespace mte {
+namespace loss {
+
+#ifndef MTE_FUSED_D
+#define MTE_FUSED_D 3
+#endif
+constexpr int kFusedD = MTE_FUSED_D;
+constexpr int kSegCostFused = 6;  // a segment start costs the window prologue + two halo rows of full work
+__host__ __device__ constexpr int fused_smem_bytes() { return kRWarps * kFusedD * 3 * 512; }
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// All CTAs of the (cooperative, co-resident) grid meet here once per launch.  The counter is reset by the last CTA
+// of the launch (every CTA has left the barrier before it takes its final ticket).
+__device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned nCtas) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        while (ld_acquire_u32(ctr) < nCtas) __nanosleep(20);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+struct FusedP {
+    LossP L;
+    const float *expectG;   // device [1 + nScales] upstream gradient the caller expects, or nullptr = {1, 0, ...}
+    unsigned *barrier;      // grid barrier counter (workspace header, self-resetting)
+};
+
+// decode the unit range [u0, u1) into its next segment; returns false when the slice holds no rows
+struct Seg {
+    int si, img, strip, row0, nrows;
+};
+__device__ __forceinline__ bool next_segment(const LossP &P, int &u0, int u1, Seg &s) {
+    int si = 0;
+#pragma unroll
+    for (int k = 1; k < MTE_MAX_SCALES; k++)
+        if (k < P.nScales && u0 >= P.s[k].unitBase) si = k;
+    const ScaleP &S = P.s[si];
+    const int local = u0 - S.unitBase;
+    const int HV = S.H + kSegCostFused;
+    const int t = local / HV;  // (image, strip)
+    const int r = local - t * HV;
+    const int take = min(HV - r, u1 - u0);
+    s.row0 = max(r - kSegCostFused, 0);
+    s.nrows = max(r + take - kSegCostFused, 0) - s.row0;
+    u0 += take;
+    s.si = si;
+    s.img = t / S.strips;
+    s.strip = t - s.img * S.strips;
+    return s.nrows > 0;
+}
+
+template <bool INV, bool SIG>
+__device__ __forceinline__ void fused_segment(const LossP &P, const ScaleP &S, const Seg &sg, int lane,
+                                              unsigned char *ring, const float4 *sLut, float cp, float cn,
+                                              float (&la)[2], float &poison) {
+    constexpr int VEC = 4, D = kFusedD;
+    constexpr unsigned PLB = 512, SLB = 3 * PLB;
+    constexpr float kFill = INV ? 3.0e38f : 0.f;  // its reciprocal flushes to exactly 0 (the conv zero padding)
+    const int H = S.H, row0 = sg.row0, nrows = sg.nrows;
+    const unsigned W = (unsigned)S.W;
+    const int col0 = (sg.strip * kHaloLanes + lane - 1) * VEC;
+    const bool colOk = col0 >= 0 && col0 < (int)W;
+    const bool writer = colOk && lane >= 1 && lane <= kHaloLanes;
+    const size_t lo = (size_t)sg.img * H * W + (colOk ? col0 : 0);
+    const float *xP = S.x + lo, *eP = S.e + lo, *nP = S.n + lo;
+    float *gP = S.g + lo, *dP = S.dx + lo;
+    const bool writeG = writer && S.g != nullptr;
+    const float T = P.T;
+    unsigned char *slot0 = ring + lane * 16;
+    const unsigned ringS = (unsigned)__cvta_generic_to_shared(slot0);
+
+    // iteration j = 0 .. nrows + 1 handles RESPONSE row r = row0 - 1 + j (one halo row above and below the rows
+    // this segment owns): it needs depth row r + 1 (rows r - 1 and r are in the window) and the target rows r
+    auto issue = [&](unsigned so, int j) {
+        const int rx = row0 + j, r = row0 - 1 + j;
+        cp_async_vec<4>(ringS + so, elem_addr(xP, (unsigned)min(rx, H - 1) * W), colOk && rx < H);
+        const bool rOk = colOk && r >= 0 && r < H;
+        const unsigned ro = (unsigned)min(max(r, 0), H - 1) * W;
+        cp_async_vec<4>(ringS + so + PLB, elem_addr(eP, ro), rOk);
+        cp_async_vec<4>(ringS + so + 2 * PLB, elem_addr(nP, ro), rOk);
+    };
+    auto fix_row = [&](float (&x)[VEC], int row) {  // padding, inv2depth, non-finite tracking
+        if (INV) {
+            const bool ok = colOk && row >= 0 && row < H;
+#pragma unroll
+            for (int v = 0; v < VEC; v++) x[v] = inv_to_depth(ok ? x[v] : kFill);
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; v++) poison = fmaf(x[v], 0.f, poison);
+    };
+    auto load_plain = [&](float (&x)[VEC], int row) {
+#pragma unroll
+        for (int v = 0; v < VEC; v++) x[v] = 0.f;
+        if (colOk && row >= 0 && row < H) {
+            const float4 t = ld_cached4(elem_addr(xP, (unsigned)row * W));
+            x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+        }
+    };
+
+    const int niter = nrows + 2;
+    PRow<VEC> win[3];  // win[d % 3] holds depth row row0 - 2 + d
+    float xa[VEC], xc[VEC];
+    load_plain(xa, row0 - 2);
+    load_plain(xc, row0 - 1);
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        if (k < niter) issue(k * SLB, k);
+        cp_async_commit();
+    }
+    fix_row(xa, row0 - 2);
+    fix_row(xc, row0 - 1);
+    prep_row<VEC, MODE_DIR>(win[0], xa);
+    prep_row<VEC, MODE_DIR>(win[1], xc);
+    float oacc[3][VEC];
+#pragma unroll
+    for (int o = 0; o < 3; o++)
+#pragma unroll
+        for (int v = 0; v < VEC; v++) oacc[o][v] = 0.f;
+
+    unsigned so = 0;
+#pragma unroll 1
+    for (int jj = 0; jj < niter; jj += 3) {
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const int j = jj + u;
+            if (j < niter) {  // warp-uniform
+                cp_async_wait<D - 1>();
+                float xn[VEC], e[VEC], th[VEC];
+                lds_vec<VEC>(xn, slot0 + so);
+                lds_vec<VEC>(e, slot0 + so + PLB);
+                lds_vec<VEC>(th, slot0 + so + 2 * PLB);
+                if (j + D < niter) issue(so, j + D);  // refill the slot just read
+                cp_async_commit();
+                so = (so + SLB == D * SLB) ? 0u : so + SLB;
+                const int r = row0 - 1 + j;
+                PRow<VEC> &dn = win[(u + 2) % 3];
+                fix_row(xn, r + 1);
+                prep_row<VEC, MODE_DIR>(dn, xn);
+                const PRow<VEC> &up = win[u % 3];
+                const PRow<VEC> &mid = win[(u + 1) % 3];
+                const bool own = j >= 1 && j <= nrows;            // a row this segment owns (warp-uniform)
+                const bool live = colOk && r >= 0 && r < H;       // the response pixel exists
+                float g[VEC], A[VEC], C[VEC], A2[VEC], C2[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; v++) {
+                    // separable parts of the four zero-padded 3x3 cross-correlations of grad_loss.py:20-31:
+                    // c_v = Pv + dv, c_h = Rh + Dm, c_lr = Pv + Rh, c_rl = Rh - Pv
+                    const float Pv = dn.s3[v] - up.s3[v];
+                    const float Dm = mid.d[v];
+                    const float Rh = (up.d[v] + Dm) + dn.d[v];
+                    const float dv = dn.c[v] - up.c[v];
+                    float c;
+                    unsigned cd;
+                    pick_directional(th[v], Pv, Rh, Dm, dv, c, cd);
+                    g[v] = fabsf(c);
+                    // p the reference-faithful way (accurate expf, correctly rounded reciprocal): the gradient term
+                    // p(1-p)/(1-p+eps) amplifies the last bits of p where the sigmoid saturates
+                    const float p = SIG ? sigmoid_ref(g[v] - T) : g[v];
+                    const float q = 1.0f - p;
+                    const float pe = p + kEps, qe = q + kEps;
+                    const float ee = e[v], ne = 1.0f - ee;
+                    if (own) {
+                        la[0] = fmaf(ee, lg2_approx(pe), la[0]);
+                        la[1] = fmaf(ne, lg2_approx(qe), la[1]);
+                    }
+                    float d = cp * ee * rcp_approx(pe) + cn * ne * rcp_approx(qe);
+                    if (SIG) d = d * p * q;
+                    d = (live && g[v] != 0.f) ? d : 0.f;  // sign(0) = 0; pixels outside the image do not exist
+                    const float4 k = sLut[cd & 15u];
+                    A[v] = d * k.x; C[v] = d * k.y; A2[v] = d * k.z; C2[v] = d * k.w;
+                }
+                if (own && writeG)
+                    st_stream4(elem_addr(gP, (unsigned)r * W), make_float4(g[0], g[1], g[2], g[3]));
+                const float Al = __shfl_up_sync(MTE_FULL_MASK, A[VEC - 1], 1), Ar = __shfl_down_sync(MTE_FULL_MASK, A[0], 1);
+                const float Cl = __shfl_up_sync(MTE_FULL_MASK, C[VEC - 1], 1), Cr = __shfl_down_sync(MTE_FULL_MASK, C[0], 1);
+                const float C2l = __shfl_up_sync(MTE_FULL_MASK, C2[VEC - 1], 1), C2r = __shfl_down_sync(MTE_FULL_MASK, C2[0], 1);
+                // response row r acts as "up" for output row r + 1 (first contribution: overwrites the retired slot),
+                // as "mid" for output row r and as "down" for output row r - 1, which it completes
+#pragma unroll
+                for (int v = 0; v < VEC; v++) {
+                    const float a_l = v == 0 ? Al : A[(v + VEC - 1) % VEC], a_r = v == VEC - 1 ? Ar : A[(v + 1) % VEC];
+                    const float c_l = v == 0 ? Cl : C[(v + VEC - 1) % VEC], c_r = v == VEC - 1 ? Cr : C[(v + 1) % VEC];
+                    const float c2_l = v == 0 ? C2l : C2[(v + VEC - 1) % VEC], c2_r = v == VEC - 1 ? C2r : C2[(v + 1) % VEC];
+                    const float SA = (a_l + a_r) + A2[v], DC = c_l - c_r;
+                    oacc[u][v] = SA + DC;
+                    oacc[(u + 2) % 3][v] += c2_l - c2_r;
+                    oacc[(u + 1) % 3][v] -= SA - DC;
+                }
+                if (j >= 2) {
+                    float out[VEC];
+#pragma unroll
+                    for (int v = 0; v < VEC; v++) {
+                        float d = oacc[(u + 1) % 3][v];
+                        if (INV) {
+                            // pred was an inverse depth: chain through depth = 1 / clamp(inv, 1e-6)
+                            // (utils/depth.py:104-121); the depth of output row r - 1 is the window's upper row
+                            const float dep = up.c[v];
+                            d = (dep < 1e6f) ? -d * dep * dep : 0.f;
+                        }
+                        out[v] = d;
+                    }
+                    if (writer) st_stream4(elem_addr(dP, (unsigned)(r - 1) * W), make_float4(out[0], out[1], out[2], out[3]));
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    if (!writer) {  // halo / out-of-image lanes: their pixels belong to the neighbouring strips
+        la[0] = 0.f;
+        la[1] = 0.f;
+    }
+}
+
+template <bool INV, bool SIG>
+__global__ void __launch_bounds__(kRThreads, 1) edge_loss_fused_kernel(const __grid_constant__ FusedP F) {
+    extern __shared__ __align__(16) unsigned char fusedRing[];
+    __shared__ float4 sLut[16];  // per stash code (direction | 4 << sign): adjoint coefficients (A, C, A2, C2) for s = 1
+    __shared__ double sLoss[MTE_MAX_SCALES];
+    __shared__ int sLast;
+    const LossP &P = F.L;
+    if (threadIdx.x < 16) {
+        const int di = threadIdx.x & 3, sgn_ = threadIdx.x >> 2;
+        const float sgn = sgn_ == 1 ? 1.f : (sgn_ == 2 ? -1.f : 0.f);
+        const float a = (di == 2 || di == 3) ? 1.f : (di == 1 ? -1.f : 0.f);  // h:0 rl:-1 v:1 lr:1
+        const float c = (di == 2) ? 0.f : 1.f;                                // h:1 rl:1 v:0 lr:1
+        const float bb = (di & 1) ? 1.f : 2.f;                                // axis stencils weigh the centre twice
+        sLut[threadIdx.x] = make_float4(sgn * a, sgn * c, sgn * a * bb, sgn * c * bb);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nWarps = gridDim.x * kRWarps;
+    const int gw = blockIdx.x * kRWarps + warp;
+    unsigned char *ring = fusedRing + warp * (fused_smem_bytes() / kRWarps);
+    const int uBeg = (int)((long long)P.totalUnits * gw / nWarps);
+    const int uEnd = (int)((long long)P.totalUnits * (gw + 1) / nWarps);
+
+    // ---- phase 1: Wp_b = sum of the edge labels, every warp over the rows it owns (the lines stay in L2 for phase 2)
+    {
+        int u0 = uBeg;
+        while (u0 < uEnd) {
+            Seg sg;
+            if (!next_segment(P, u0, uEnd, sg)) continue;
+            const ScaleP &S = P.s[sg.si];
+            const unsigned W = (unsigned)S.W;
+            const int col0 = (sg.strip * kHaloLanes + lane - 1) * 4;
+            const bool writer = col0 >= 0 && col0 < (int)W && lane >= 1 && lane <= kHaloLanes;
+            const float *eP = S.e + (size_t)sg.img * S.H * W + (writer ? col0 : 0);
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll 1
+            for (int j0 = 0; j0 < sg.nrows; j0 += 8) {
+                float4 t[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    t[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (writer && j0 + k < sg.nrows)
+                        t[k] = *reinterpret_cast<const float4 *>(elem_addr(eP, (unsigned)(sg.row0 + j0 + k) * W));
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k += 2) {
+                    s0 += (t[k].x + t[k].y) + (t[k].z + t[k].w);
+                    s1 += (t[k + 1].x + t[k + 1].y) + (t[k + 1].z + t[k + 1].w);
+                }
+            }
+            const float v = warp_sum(s0 + s1);
+            unsigned long long *acc = P.accum + (size_t)(S.imgBase + sg.img) * kAcc;
+            if (lane == 0) {
+                atomicAdd(acc + A_WP, (unsigned long long)__double2ll_rn((double)v * kFix));
+                if (!isfinite(v)) atomicOr(acc + A_FLAGS, (unsigned long long)F_NONFINITE);
+            }
+        }
+    }
+    grid_barrier(F.barrier, gridDim.x);
+
+    // ---- phase 2
+    int u0 = uBeg;
+    while (u0 < uEnd) {
+        Seg sg;
+        if (!next_segment(P, u0, uEnd, sg)) continue;
+        const ScaleP &S = P.s[sg.si];
+        // class balance and normaliser of this image, exactly as finalize_loss / the two-kernel backward form them
+        const double npix = (double)S.H * (double)S.W;
+        float alpha;
+        {
+            const double wp = (double)(long long)__ldcg(P.accum + (size_t)(S.imgBase + sg.img) * kAcc + A_WP) / kFix;
+            const double wn = npix - wp;
+            alpha = (float)(wn / (wp + wn));
+            if (wn == 0.0) {  // rare: "no negatives anywhere in the batch" -> all alpha = 1 (grad_loss.py:175-176)
+                double wnSum = 0.0;
+                for (int b = 0; b < S.B; b++)
+                    wnSum += npix - (double)(long long)__ldcg(P.accum + (size_t)(S.imgBase + b) * kAcc + A_WP) / kFix;
+                if (wnSum == 0.0) alpha = 1.0f;
+            }
+        }
+        float G = F.expectG ? (__ldg(F.expectG) * S.scaleWeight + __ldg(F.expectG + 1 + sg.si)) : S.scaleWeight;
+        if (G == 0.f) G = 1.f;  // a zero expectation could not be rescaled later
+        const float coef = (float)((double)P.weight / (npix * (double)S.B)) * G;
+        const float cp = -coef * P.p2n * alpha, cn = coef * (1.0f - alpha);
+        float la[2] = {0.f, 0.f};
+        float poison = 0.f;
+        fused_segment<INV, SIG>(P, S, sg, lane, ring, sLut, cp, cn, la, poison);
+        bool bad = __any_sync(MTE_FULL_MASK, !(poison == 0.f));
+        unsigned long long *acc = P.accum + (size_t)(S.imgBase + sg.img) * kAcc;
+        const float vp = warp_sum(la[0]), vn = warp_sum(la[1]);
+        bad = bad || !isfinite(vp) || !isfinite(vn);
+        if (lane == 0) {
+            atomicAdd(acc + A_SPU, (unsigned long long)__double2ll_rn((double)vp * kFix));
+            atomicAdd(acc + A_SNU, (unsigned long long)__double2ll_rn((double)vn * kFix));
+            if (bad) atomicOr(acc + A_FLAGS, (unsigned long long)F_NONFINITE);
+        }
+    }
+    // ---- the last CTA to leave folds alpha, the normalisers and the loss (same code as the two-kernel forward)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        sLast = atomicAdd(P.ticket + 1, 1u) == gridDim.x - 1u;
+        __threadfence();
+    }
+    __syncthreads();
+    if (sLast) {
+        finalize_loss<false>(P, sLoss);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double total = 0.0;
+            for (int k = 0; k < P.nScales; k++) {
+                total += (double)P.s[k].scaleWeight * sLoss[k];
+                float G = F.expectG ? (F.expectG[0] * P.s[k].scaleWeight + F.expectG[1 + k]) : P.s[k].scaleWeight;
+                if (G == 0.f) G = 1.f;
+                P.ctx[P.totalImages + 2 * MTE_MAX_SCALES + k] = G;  // the factor grad_pred carries now
+            }
+            reinterpret_cast<unsigned *>(P.ctx + P.totalImages + 3 * MTE_MAX_SCALES)[0] = 0u;  // rescale ticket
+            P.lossOut[0] = (float)total;
+            P.ticket[0] = 0u;
+            P.ticket[1] = 0u;
+            *F.barrier = 0u;
+        }
+    }
+}
+
+// d loss / d pred was produced for the expected upstream gradient; bring it to the actual one.  Exits at once when
+// they agree (the common case: loss.backward() with the expectation 1, or a steady training loop).
+__global__ void __launch_bounds__(256) edge_loss_rescale_kernel(const __grid_constant__ LossP P, const float *gradLoss,
+                                                                float *ctx, float *expectedOut) {
+    float *cur = ctx + P.totalImages + 2 * MTE_MAX_SCALES;
+    unsigned *done = reinterpret_cast<unsigned *>(ctx + P.totalImages + 3 * MTE_MAX_SCALES);
+    for (int k = 0; k < P.nScales; k++) {
+        const ScaleP &S = P.s[k];
+        const float G = gradLoss[0] * S.scaleWeight + gradLoss[1 + k];
+        const float c = cur[k];
+        if (G == c) continue;
+        const float f = G / c;
+        const size_t n4 = (size_t)S.B * S.H * S.W / 4;
+        float4 *d = reinterpret_cast<float4 *>(S.dx);
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+            float4 v = d[i];
+            v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+            d[i] = v;
+        }
+    }
+    // the last CTA records what grad_pred carries now (every CTA has read `cur` before taking its ticket)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(done, 1u) == gridDim.x - 1u) {
+            for (int k = 0; k < P.nScales; k++) cur[k] = gradLoss[0] * P.s[k].scaleWeight + gradLoss[1 + k];
+            if (expectedOut)
+                for (int k = 0; k < 1 + P.nScales; k++) expectedOut[k] = gradLoss[k];
+            __threadfence();
+            *done = 0u;
+        }
+    }
+}
+
+template <bool INV, bool SIG>
+static int launch_fused_one(const FusedP &F, int grid, cudaStream_t st) {
+    constexpr int smem = fused_smem_bytes();
+    const void *fn = (const void *)edge_loss_fused_kernel<INV, SIG>;
+    if (opt_in_smem(fn, smem) != cudaSuccess) return (int)cudaGetLastError();
+    // the grid barrier needs every CTA resident at once: cap the grid at the co-resident maximum and launch
+    // cooperatively, so the driver never runs a partial grid next to another cooperative kernel
+    int perSm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, edge_loss_fused_kernel<INV, SIG>, kRThreads, smem);
+    if (perSm < 1) return MTE_ERR_ARG;
+    const int maxGrid = perSm * num_sms();
+    if (grid > maxGrid) grid = maxGrid;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)kRThreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, edge_loss_fused_kernel<INV, SIG>, F);
+    return e == cudaSuccess ? MTE_OK : (int)e;
+}
+
+int launch_fused(const FusedP &F, int grid, bool inv, bool sig, cudaStream_t st) {
+    if (inv) return sig ? launch_fused_one<true, true>(F, grid, st) : launch_fused_one<true, false>(F, grid, st);
+    return sig ? launch_fused_one<false, true>(F, grid, st) : launch_fused_one<false, false>(F, grid, st);
+}
+
+}  // namespace loss
+}  // namespace mte
+
+using namespace mte;
+using namespace mte::loss;
+
+static bool fused_supported(const mte_loss_scale_t *sc, int n, const mte_loss_attrs_t *at) {
+    if (!sc || !at || n < 1 || n > MTE_MAX_SCALES) return false;
+    if (!at->is_grad) return false;
+    for (int i = 0; i < n; i++) {
+        const mte_loss_scale_t &s = sc[i];
+        if (!s.pred || !s.edge || !s.normal || s.mask) return false;
+        if (s.h != s.H || s.w != s.W || s.B < 1 || s.H < 1 || s.W < 4 || (s.W % 4)) return false;
+        const void *ptrs[] = {s.pred, s.edge, s.normal, s.grad_map, s.grad_pred};
+        for (const void *p : ptrs)
+            if (!aligned16(p)) return false;
+    }
+    return true;
+}
+
+extern "C" int mte_edge_loss_fused_supported(const mte_loss_scale_t *sc, int n, const mte_loss_attrs_t *at) {
+    return fused_supported(sc, n, at) ? 1 : 0;
+}
+
+extern "C" int mte_edge_loss_fwd_grad(const mte_loss_scale_t *sc, int n, const mte_loss_attrs_t *at,
+                                      const float *expected_grad_loss, float *loss_out, void *ctx, void *ws,
+                                      size_t ws_bytes, mte_stream_t stream) {
+    if (!sc || !at || !loss_out || !ctx || !ws) return MTE_ERR_NULL;
+    if (!fused_supported(sc, n, at)) return MTE_ERR_ARG;
+    for (int i = 0; i < n; i++)
+        if (!sc[i].grad_pred) return MTE_ERR_NULL;
+    if (ws_bytes < MTE_WS_HEADER_BYTES) return MTE_ERR_WORKSPACE;
+    FusedP F;
+    memset(&F, 0, sizeof(F));
+    LossP &P = F.L;
+    int img = 0;
+    long long unitBase = 0;
+    for (int i = 0; i < n; i++) {
+        ScaleP &S = P.s[i];
+        S.B = sc[i].B; S.H = sc[i].H; S.W = sc[i].W;
+        S.x = sc[i].pred; S.e = sc[i].edge; S.n = sc[i].normal; S.m = nullptr;
+        S.g = sc[i].grad_map; S.dx = sc[i].grad_pred; S.stash = nullptr;
+        S.strips = ceil_div(S.W, kHaloLanes * 4);
+        S.imgBase = img;
+        S.unitBase = (int)unitBase;
+        unitBase += (long long)S.strips * (S.H + kSegCostFused) * S.B;
+        S.scaleWeight = sc[i].scale_weight;
+        img += S.B;
+    }
+    if (unitBase > 0x7fffffffLL || img > kWsMaxLossImages) return MTE_ERR_SHAPE;
+    P.nScales = n; P.totalImages = img; P.totalUnits = (int)unitBase;
+    P.T = at->sigmoid_thresh; P.weight = at->weight; P.p2n = at->pos_to_neg;
+    char *w = static_cast<char *>(ws);
+    WsHeader *hdr = reinterpret_cast<WsHeader *>(w);
+    P.accum = reinterpret_cast<unsigned long long *>(w + kWsAccumOffset);
+    P.ticket = hdr->ticket;
+    P.lossOut = loss_out;
+    P.ctx = static_cast<float *>(ctx);
+    F.expectG = expected_grad_loss;
+    F.barrier = hdr->ticket + 2;
+    int grid = num_sms();
+    const int minRows = 4;
+    if ((long long)grid * kRWarps * minRows > unitBase) grid = (int)((unitBase + kRWarps * minRows - 1) / (kRWarps * minRows));
+    if (grid < 1) grid = 1;
+    return launch_fused(F, grid, at->pred_is_inverse != 0, at->is_sigmoid != 0, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mte_edge_loss_grad_rescale(const mte_loss_scale_t *sc, int n, const float *grad_loss, void *ctx,
+                                          float *expected_out, mte_stream_t stream) {
+    if (!sc || !grad_loss || !ctx) return MTE_ERR_NULL;
+    if (n < 1 || n > MTE_MAX_SCALES) return MTE_ERR_ARG;
+    LossP P;
+    memset(&P, 0, sizeof(P));
+    int img = 0;
+    for (int i = 0; i < n; i++) {
+        if (!sc[i].grad_pred) return MTE_ERR_NULL;
+        if (!aligned16(sc[i].grad_pred) || (sc[i].W % 4)) return MTE_ERR_ALIGN;
+        P.s[i].B = sc[i].B; P.s[i].H = sc[i].H; P.s[i].W = sc[i].W;
+        P.s[i].dx = sc[i].grad_pred;
+        P.s[i].scaleWeight = sc[i].scale_weight;
+        img += sc[i].B;
+    }
+    P.nScales = n; P.totalImages = img;
+    edge_loss_rescale_kernel<<<num_sms() * 4, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        P, grad_loss, static_cast<float *>(ctx), expected_out);
+    MTE_RETURN_IF_CUDA_ERROR();
+    return MTE_OK;
+}

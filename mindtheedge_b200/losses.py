@@ -111,16 +111,85 @@ _LIBIMPL = runtime.LIBIMPL
 _LIBIMPL.impl("edge_loss_fwd", _edge_loss_fwd_cuda)
 _LIBIMPL.impl("edge_loss_bwd", _edge_loss_bwd_cuda)
 
+# ---- one-pass variant (mte_edge_loss_fwd_grad / mte_edge_loss_grad_rescale, include/mte.h) ------------------------
+# d loss / d pred is produced WITH the forward for the upstream gradient the call site expects (`expected_upstream`,
+# 1 for loss.backward()); the backward only compares the actual upstream gradient with it ON THE DEVICE and rescales
+# when they differ.  The expectation is an explicit argument, not learned state: the same inputs and the same upstream
+# gradient always give the same bits.
+_EXPECTED: dict = {}
+
+
+def _expected_upstream(dev, value: float):
+    key = (dev.index, float(value))
+    t = _EXPECTED.get(key)
+    if t is None:
+        t = torch.zeros(1 + _lib.MTE_MAX_SCALES, dtype=torch.float32, device=dev)
+        t[0] = float(value)
+        _EXPECTED[key] = t
+    return t
+
+
+def _fused_ok(pred, edge, normal, mask, scale_weights, is_grad):
+    if not is_grad or not normal or mask or any(float(w) == 0.0 for w in scale_weights):
+        return False
+    n = len(pred)
+    sc = _scales_struct(pred, edge, normal, None, edge, pred, scale_weights)   # pointers only matter for alignment
+    at = _attrs(True, True, False, 4.0, 1.0, 1.0)
+    return bool(_lib.lib.mte_edge_loss_fused_supported(sc, n, C.byref(at)))
+
+
+def _edge_loss_fwd_grad_cuda(pred, edge, normal, scale_weights, is_sigmoid, pred_is_inverse, sigmoid_thresh, weight,
+                             pos_to_neg, expected_upstream):
+    dev = runtime.same_device(pred, edge, normal)
+    n = len(pred)
+    grad_maps = [torch.empty_like(e) for e in edge]
+    grads = [torch.empty_like(p) for p in pred]
+    sc = _scales_struct(pred, edge, normal, None, grad_maps, grads, scale_weights)
+    at = _attrs(True, is_sigmoid, pred_is_inverse, sigmoid_thresh, weight, pos_to_neg)
+    losses = torch.empty(1 + n, dtype=torch.float32, device=dev)
+    ctx = torch.empty(_lib.lib.mte_edge_loss_ctx_bytes(sc, n) // 4, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = runtime.workspace(dev, _lib.lib.mte_edge_loss_workspace_bytes(sc, n))
+        runtime.call("mte_edge_loss_fwd_grad", dev, sc, n, C.byref(at),
+                     _expected_upstream(dev, expected_upstream).data_ptr(),
+                     losses.data_ptr(), ctx.data_ptr(), ws.data_ptr(), ws.numel(), runtime.current_stream_ptr(dev))
+    return losses, ctx, grad_maps, grads
+
+
+def _edge_loss_grad_rescale_cuda(grad_losses, ctx, grads, scale_weights):
+    dev = runtime.same_device(grad_losses, ctx, grads)
+    n = len(grads)
+    sc = _scales_struct(grads, grads, None, None, None, grads, scale_weights)
+    with torch.cuda.device(dev):
+        runtime.call("mte_edge_loss_grad_rescale", dev, sc, n, grad_losses.data_ptr(), ctx.data_ptr(), None,
+                     runtime.current_stream_ptr(dev))
+
+
+runtime.define_op("edge_loss_fwd_grad(Tensor[] pred, Tensor[] edge, Tensor[] normal, float[] scale_weights, "
+                  "bool is_sigmoid, bool pred_is_inverse, float sigmoid_thresh, float weight, float pos_to_neg, "
+                  "float expected_upstream) -> (Tensor, Tensor, Tensor[], Tensor[])", _edge_loss_fwd_grad_cuda)
+runtime.define_op("edge_loss_grad_rescale(Tensor grad_losses, Tensor(a!) ctx, Tensor(b!)[] grads, "
+                  "float[] scale_weights) -> ()", _edge_loss_grad_rescale_cuda)
+
 
 class _EdgeLossFn(torch.autograd.Function):
     """forward(*pred) -> losses[1+n]; backward is the hand-written kernel."""
 
     @staticmethod
     def forward(ctx, cfg, *pred):
-        edge, normal, mask, weights, flags = cfg
-        losses, saved, grad_maps, stash = torch.ops.mte.edge_loss_fwd(list(pred), edge, normal, mask, weights, *flags)
+        edge, normal, mask, weights, flags, expected = cfg
         ctx.cfg = cfg
         ctx.n = len(pred)
+        ctx.fused = any(ctx.needs_input_grad[1:]) and _fused_ok(pred, edge, normal, mask, weights, flags[0])
+        if ctx.fused:
+            # one launch: loss, grad maps and d loss / d pred (for the expected upstream gradient) together
+            losses, saved, grad_maps, grads = torch.ops.mte.edge_loss_fwd_grad(list(pred), edge, normal, weights,
+                                                                               *flags[1:], float(expected))
+            ctx.save_for_backward(saved, *grads)
+            ctx.used = False
+            ctx.mark_non_differentiable(*grad_maps)
+            return (losses, *grad_maps)
+        losses, saved, grad_maps, stash = torch.ops.mte.edge_loss_fwd(list(pred), edge, normal, mask, weights, *flags)
         ctx.has_stash = len(stash) > 0
         # the grad maps are outputs the caller may hold on to; the backward only reads them
         ctx.save_for_backward(saved, *pred, *(grad_maps if stash else []), *stash)
@@ -129,9 +198,17 @@ class _EdgeLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_losses, *_unused):
-        edge, normal, mask, weights, flags = ctx.cfg
+        edge, normal, mask, weights, flags, _expected = ctx.cfg
         saved, *rest = ctx.saved_tensors
         n = ctx.n
+        if ctx.fused:
+            g = grad_losses.contiguous().float()
+            torch.ops.mte.edge_loss_grad_rescale(g, saved, list(rest), weights)
+            # the first backward hands out the buffers themselves (autograd may keep or accumulate into them); a
+            # second backward through a retained graph works on copies
+            out = list(rest) if not ctx.used else [t.clone() for t in rest]
+            ctx.used = True
+            return (None, *out)
         pred = rest[:n]
         gmaps = rest[n:2 * n] if ctx.has_stash else []
         stash = rest[2 * n:3 * n] if ctx.has_stash else []
@@ -154,14 +231,18 @@ def multiscale_edge_loss(
     weight: float = 1.0,
     pos_to_neg: float = 1.0,
     pred_is_inverse: bool = False,
+    expected_upstream: float = 1.0,
 ):
-    """All pyramid scales in one launch per direction.
+    """All pyramid scales in one launch.
 
     Equivalent to the loop of ``compute_edge_loss_with_all_scales``
     (``models/SemiSupEdgeModel.py:164-198``): returns
     ``(sum_s scale_weights[s] * loss_s, per_scale_losses[n], grad_maps[n])``.
     With ``pred_is_inverse`` the ``inv2depth`` step (``utils/depth.py:104-121``)
-    is fused into the kernels.
+    is fused into the kernels.  In the shipped configuration (directional normals, no mask, prediction at the target
+    size) and when a prediction requires grad, ONE kernel produces the loss, the grad maps and ``d total / d pred``
+    for ``expected_upstream`` (the gradient the caller will send into ``total``: 1 for ``total.backward()``); the
+    backward then only checks the actual upstream gradient on the device and rescales if it differs.
     """
     n = len(preds)
     if not 1 <= n <= _lib.MTE_MAX_SCALES:
@@ -174,18 +255,18 @@ def multiscale_edge_loss(
     mask = [_prep(t, "gt_mask") for t in gt_masks] if gt_masks is not None else []
     flags = (bool(is_grad), bool(is_sigmoid), bool(pred_is_inverse), float(sigmoid_thresh), float(weight),
              float(pos_to_neg))
-    cfg = (edge, normal, mask, [float(w) for w in scale_weights], flags)
+    cfg = (edge, normal, mask, [float(w) for w in scale_weights], flags, float(expected_upstream))
     losses, *grad_maps = _EdgeLossFn.apply(cfg, *pred)
     return losses[0], losses[1:], list(grad_maps)
 
 
 def edge_loss(output, gt_edge, gt_mask=None, is_grad=True, is_sigmoid=True, sigmoid_thresh=4, gt_normals=None, *,
-              weight=1.0, pos_to_neg=1.0):
+              weight=1.0, pos_to_neg=1.0, expected_upstream=1.0):
     """Single-scale functional form -> (loss, grad_map)."""
     total, _, maps = multiscale_edge_loss(
         [output], [gt_edge], None if gt_mask is None else [gt_mask], None if gt_normals is None else [gt_normals],
         scale_weights=[1.0], is_grad=is_grad, is_sigmoid=is_sigmoid, sigmoid_thresh=sigmoid_thresh, weight=weight,
-        pos_to_neg=pos_to_neg)
+        pos_to_neg=pos_to_neg, expected_upstream=expected_upstream)
     return total, maps[0]
 
 
@@ -288,6 +369,10 @@ class GradLoss(nn.Module):
         self.use_external_edges_for_loss = use_external_edges_for_loss
         self.edge_loss_class_list_to_mask_out = edge_loss_class_list_to_mask_out
         self.device = "cuda"
+        # the gradient the training loop sends into the returned loss (performance hint only, any value is correct):
+        # SemiSupEdgeModel sums the 4 scales, divides by 4 and multiplies by model.loss.depth_edges_loss_weight
+        # (models/SemiSupEdgeModel.py:150, 187-197), so a head called once per scale sees 0.25 * that weight
+        self.expected_upstream = 1.0
 
     def forward(self, output, gt_edge, gt_mask=None, is_grad=True, is_sigmoid=True, sigmoid_thresh=4,
                 gt_normals=None):
@@ -295,4 +380,5 @@ class GradLoss(nn.Module):
             return _alt_edge_loss(self.loss_types, output, gt_edge, gt_mask, is_grad, is_sigmoid, sigmoid_thresh,
                                   gt_normals, self.weight, self.depth_edges_loss_pos_to_neg_weight)
         return edge_loss(output, gt_edge, gt_mask, is_grad, is_sigmoid, sigmoid_thresh, gt_normals,
-                         weight=self.weight, pos_to_neg=self.depth_edges_loss_pos_to_neg_weight)
+                         weight=self.weight, pos_to_neg=self.depth_edges_loss_pos_to_neg_weight,
+                         expected_upstream=self.expected_upstream)

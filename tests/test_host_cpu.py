@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert n in exported, f"{n} declared in include/mte.h but not exported by libmte.so"
         assert n in _lib.EXPORTED_SYMBOLS, f"{n} has no ctypes signature"
-    assert _lib.lib.mte_version() == 100
+    assert _lib.lib.mte_version() == 200
     assert _lib.lib.mte_error_string(0) == b"ok"
     assert b"workspace" in _lib.lib.mte_error_string(-3)
 
