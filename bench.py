@@ -50,7 +50,7 @@ DEE_BYTES_PER_PX = 9.0     # prob fp32 in, normal u8 + edge fp32 out
 KITTI_N, KITTI_T = 102, 12
 KITTI_CROP = [44, 1197, 153, 371]
 DDAD_H, DDAD_W, DDAD_N = 1216, 1936, 8
-DEE_FRAMES = 64
+DEE_FRAMES = 148   # one frame per SM for the one-CTA-per-frame hysteresis
 
 
 def measured_peak_gbs():

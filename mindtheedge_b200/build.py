@@ -18,7 +18,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.environ.get("MTE_LIB_OUT", os.path.join(HERE, "libmte.so"))  # alternate output for A/B experiments
-OBJ = OBJ if "MTE_LIB_OUT" not in os.environ else OBJ + "_alt"
+if "MTE_LIB_OUT" in os.environ:  # one object directory per alternate build (its defines differ)
+    OBJ = OBJ + "_" + os.path.splitext(os.path.basename(LIB))[0]
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

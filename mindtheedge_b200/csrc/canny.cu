@@ -517,6 +517,22 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
         __syncthreads();
     }
     tick(0);
+    if (T == 1) {
+        // a single pair: the flood result IS the edge set (every candidate connected to a strong pixel becomes an
+        // edge at level 0) -- no components to track over levels
+        for (int wi = threadIdx.x; wi < nW; wi += kUfThreads) {
+            unsigned bits = qbits[wi];
+            if (!bits) continue;
+            const int y = wi / WPR, pbase = y * W + (wi - y * WPR) * 32;
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                E[pbase + b] = 0;
+            }
+        }
+        if (threadIdx.x == 0) P.todo[img] = 0;
+        return;
+    }
     // ---- histogram of first-candidate levels over R (sparse: walk the set bits)
     for (int wi = threadIdx.x; wi < nW; wi += kUfThreads) {
         unsigned bits = qbits[wi];

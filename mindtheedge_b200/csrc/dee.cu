@@ -31,6 +31,11 @@ struct ImgStat {
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (n == 1) return 0;
+    // one reflection covers every halo index of a plane that is at least 3 wide (-n < i < 2n - 1): no division on
+    // the hot path (two integer modulos per loaded element were a third of the kernel's instructions)
+    int j = i < 0 ? -i : i;
+    j = j >= n ? 2 * (n - 1) - j : j;
+    if ((unsigned)j < (unsigned)n) return j;
     const int period = 2 * (n - 1);
     i %= period;
     if (i < 0) i += period;
@@ -52,9 +57,47 @@ __host__ __device__ inline double dkey_inv(unsigned long long k) {
 #endif
 }
 
+// ---- exact quantisation without atan2 ---------------------------------------------------------------------------
+// The u8 normal is trunc(U(atan2(-sy, sx))) with U(a) = ((a * (180/pi) + 180) / 360) * 255 evaluated op by op in
+// fp64 (infer_edge_estimation.py:247-249).  U is monotone, so level k starts at theta_k = the smallest double with
+// U(theta_k) >= k; dee_tables_kernel finds the 255 thresholds by bisection over the doubles with exactly the
+// operations of the slow path, and stores the DIRECTION (cos, sin) of each.  A pixel then takes a candidate level from
+// an fp32 atan2f and proves it with two fp64 cross products against the neighbouring threshold directions
+// (sin(A - theta) = (Y cos theta - X sin theta) / r); only when a cross product is within 2^-44 of zero relative to
+// |X| + |Y| -- i.e. the angle is within ~6e-14 rad of a threshold, where the last bits of atan2 decide -- the pixel
+// falls back to the exact double atan2.  The NMS bin (tools.py:24-38) is decided the same way by |sy| against
+// |sx| * tan(22.5 deg) / tan(67.5 deg) with a 2^-40 relative guard band.  ~100 fp64 operations per atan2 become ~12.
+struct DeeTab {
+    double2 dir[256];        // dir[k] = (cos, sin) of theta_k, k = 1..255
+    unsigned char zero4[4];  // level of a zero gradient, by the sign bits of (sy, sx)
+};
+
+__device__ __forceinline__ double normal_level_value(double ang) {
+    return __dmul_rn(__ddiv_rn(__dadd_rn(__dmul_rn(ang, 180.0 / M_PI), 180.0), 360.0), 255.0);
+}
+
+__global__ void dee_tables_kernel(DeeTab *tab) {
+    const int k = threadIdx.x;
+    if (k >= 1 && k < 256) {
+        unsigned long long lo = dkey(-M_PI), hi = dkey(M_PI);  // U(lo) < k <= U(hi)
+        while (hi - lo > 1ull) {
+            const unsigned long long mid = lo + (hi - lo) / 2ull;
+            if (normal_level_value(dkey_inv(mid)) >= (double)k) hi = mid; else lo = mid;
+        }
+        const double th = dkey_inv(hi);
+        tab->dir[k] = make_double2(cos(th), sin(th));
+    }
+    if (k == 0) tab->dir[0] = make_double2(-1.0, 0.0);
+    if (k < 4) {
+        const double sy = (k & 1) ? -0.0 : 0.0, sx = (k & 2) ? -0.0 : 0.0;
+        tab->zero4[k] = (unsigned char)(int)normal_level_value(atan2(-sy, sx));
+    }
+}
+
 // T = type of the input map (the reference passes float32 network outputs; float64 accepted)
 template <typename T>
-__global__ void __launch_bounds__(kThreads) dee_front_kernel(const T *__restrict__ img, int N, int H, int W, int doNms,
+__global__ void __launch_bounds__(kThreads) dee_front_kernel(const DeeTab *__restrict__ tab,
+                                                             const T *__restrict__ img, int N, int H, int W, int doNms,
                                                              int doHyst, double tLow, double tHigh,
                                                              unsigned char *__restrict__ normals,
                                                              T *__restrict__ nmsOut, unsigned char *__restrict__ cl,
@@ -62,16 +105,32 @@ __global__ void __launch_bounds__(kThreads) dee_front_kernel(const T *__restrict
     __shared__ double s[TH + 4][TW + 4];
     __shared__ double rowD[TH + 4][TW];  // row pass with the derivative taps  (-> sobel x)
     __shared__ double rowS[TH + 4][TW];  // row pass with the smoothing taps   (-> sobel y)
+    __shared__ double2 sDir[256];
+    __shared__ unsigned char sZero[4];
+    if (normals) {  // the table is only built (and only needed) for the normals
+        sDir[threadIdx.x & 255] = tab->dir[threadIdx.x & 255];
+        if (threadIdx.x < 4) sZero[threadIdx.x] = tab->zero4[threadIdx.x];
+    }
     const int tilesX = ceil_div(W, TW), tilesY = ceil_div(H, TH);
     const int tile = blockIdx.x % (tilesX * tilesY), im = blockIdx.x / (tilesX * tilesY);
     const int x0 = (tile % tilesX) * TW, y0 = (tile / tilesX) * TH;
     const T *src = img + (size_t)im * H * W;
     const bool needSobel = (normals != nullptr) || doNms;
 
-    for (int i = threadIdx.x; i < (TH + 4) * (TW + 4); i += kThreads) {
-        const int r = i / (TW + 4), c = i - r * (TW + 4);
-        const int y = reflect101(y0 + r - 2, H), x = reflect101(x0 + c - 2, W);
-        s[r][c] = (double)src[(size_t)y * W + x];
+    // halo tile: a thread keeps ONE column (its reflected x is computed once) and walks the rows; the four halo
+    // columns are a second, small step.  (A flat index costs a division and two reflections per element.)
+    {
+        const int c = threadIdx.x & (TW - 1), rg = threadIdx.x / TW;   // TW columns x (kThreads / TW) row groups
+        const int x = reflect101(x0 + c - 2, W);
+        for (int r = rg; r < TH + 4; r += kThreads / TW) {
+            const int y = reflect101(y0 + r - 2, H);
+            s[r][c] = (double)src[(size_t)y * W + x];
+        }
+        if (threadIdx.x < 4 * (TH + 4)) {
+            const int r = threadIdx.x >> 2, c2 = TW + (threadIdx.x & 3);
+            const int y = reflect101(y0 + r - 2, H), x2 = reflect101(x0 + c2 - 2, W);
+            s[r][c2] = (double)src[(size_t)y * W + x2];
+        }
     }
     __syncthreads();
     if (needSobel) {
@@ -98,7 +157,7 @@ __global__ void __launch_bounds__(kThreads) dee_front_kernel(const T *__restrict
         const int y = y0 + r, x = x0 + c;
         if (y >= H || x >= W) continue;
         const size_t o = (size_t)im * H * W + (size_t)y * W + x;
-        const T v = src[(size_t)y * W + x];
+        const T v = (T)s[r + 2][c + 2];   // the tile holds the exact input value
         double sx = 0.0, sy = 0.0;
         if (needSobel) {
             // symmetric column pass on the derivative rows, anti-symmetric on the smoothed rows
@@ -109,28 +168,53 @@ __global__ void __launch_bounds__(kThreads) dee_front_kernel(const T *__restrict
             sy = __dadd_rn(sy, __dmul_rn(1.0, __dsub_rn(rowS[r + 4][c], rowS[r][c])));
         }
         if (normals) {
-            const double ang = atan2(-sy, sx);
-            const double u = __dmul_rn(__ddiv_rn(__dadd_rn(__dmul_rn(ang, 180.0 / M_PI), 180.0), 360.0), 255.0);
-            normals[o] = (unsigned char)(int)u;
+            const double X = sx, Y = -sy;
+            int lvl = -1;
+            if (X == 0.0 && Y == 0.0) {
+                lvl = sZero[(int)(__double2hiint(sy) < 0) | ((int)(__double2hiint(sx) < 0) << 1)];
+            } else {
+                const float a32 = atan2f((float)Y, (float)X);
+                const int k0 = min(max((int)((a32 * 57.29577951f + 180.f) * (255.f / 360.f)), 0), 255);
+                const double m = (fabs(X) + fabs(Y)) * 0x1p-44;
+                bool ok = true;
+                if (k0 >= 1) { const double2 d = sDir[k0]; ok = (Y * d.x - X * d.y) > m; }                // theta_k0 < A
+                if (k0 <= 254) { const double2 d = sDir[k0 + 1]; ok = ok && (Y * d.x - X * d.y) < -m; }   // A < theta_k0+1
+                if (ok) lvl = k0;
+            }
+            if (lvl < 0) lvl = (int)normal_level_value(atan2(-sy, sx));  // within ~6e-14 rad of a threshold, NaN / Inf
+            normals[o] = (unsigned char)lvl;
         }
         const bool interior = y >= 1 && y < H - 1 && x >= 1 && x < W - 1;
         T keep = v;
         if (doNms) {
             keep = (T)0;
             if (interior) {
-                double a = __dmul_rn(atan2(sy, sx), 180.0 / M_PI);
-                if (a < 0.0) a = __dadd_rn(a, 180.0);
+                // bin: 0 = [0, 22.5) u [157.5, 180], 1 = [22.5, 67.5), 2 = [67.5, 112.5), 3 = [112.5, 157.5), 4 = none
+                int bin = -1;
+                {
+                    const double ax = fabs(sx), ay = fabs(sy);
+                    const double t1 = ax * 0.41421356237309503, t2 = ax * 2.4142135623730951;   // tan 22.5, tan 67.5
+                    constexpr double lo = 1.0 - 0x1p-40, hi = 1.0 + 0x1p-40;
+                    if (ax == 0.0 && ay == 0.0) bin = 0;            // atan2(+-0, +-0) is 0 or +-pi: bin 0 either way
+                    else if (ay < t1 * lo) bin = 0;
+                    else if (ay > t1 * hi && ay < t2 * lo) bin = ((sx < 0.0) != (sy < 0.0)) ? 3 : 1;
+                    else if (ay > t2 * hi) bin = 2;
+                }
+                if (bin < 0) {  // inside a guard band, NaN or Inf / Inf: the reference's own expression
+                    double a = __dmul_rn(atan2(sy, sx), 180.0 / M_PI);
+                    if (a < 0.0) a = __dadd_rn(a, 180.0);
+                    bin = 4;
+                    if ((0.0 <= a && a < 22.5) || (157.5 <= a && a <= 180.0)) bin = 0;
+                    else if (22.5 <= a && a < 67.5) bin = 1;
+                    else if (67.5 <= a && a < 112.5) bin = 2;
+                    else if (112.5 <= a && a < 157.5) bin = 3;
+                }
                 T q = (T)1, rr = (T)1;  // tools.py:22-23: no bin (NaN angle) compares against 1
                 const int cr = r + 2, cc = c + 2;
-                if ((0.0 <= a && a < 22.5) || (157.5 <= a && a <= 180.0)) {
-                    q = (T)s[cr][cc + 1]; rr = (T)s[cr][cc - 1];
-                } else if (22.5 <= a && a < 67.5) {
-                    q = (T)s[cr - 1][cc - 1]; rr = (T)s[cr + 1][cc + 1];
-                } else if (67.5 <= a && a < 112.5) {
-                    q = (T)s[cr + 1][cc]; rr = (T)s[cr - 1][cc];
-                } else if (112.5 <= a && a < 157.5) {
-                    q = (T)s[cr + 1][cc - 1]; rr = (T)s[cr - 1][cc + 1];
-                }
+                if (bin == 0) { q = (T)s[cr][cc + 1]; rr = (T)s[cr][cc - 1]; }
+                else if (bin == 1) { q = (T)s[cr - 1][cc - 1]; rr = (T)s[cr + 1][cc + 1]; }
+                else if (bin == 2) { q = (T)s[cr + 1][cc]; rr = (T)s[cr - 1][cc]; }
+                else if (bin == 3) { q = (T)s[cr + 1][cc - 1]; rr = (T)s[cr - 1][cc + 1]; }
                 if (v >= q && v >= rr) keep = v;
             }
         }
@@ -183,13 +267,14 @@ __global__ void dee_convert_kernel(const T *__restrict__ in, O *__restrict__ out
 }
 
 struct Layout {
-    size_t offStats, offVal, offCl, offE, offActive, total;
+    size_t offStats, offTab, offVal, offCl, offE, offActive, total;
 };
 
 static Layout layout(int N, int H, int W) {
     Layout L;
     size_t off = MTE_WS_HEADER_BYTES;
     L.offStats = off; off += align_up(sizeof(ImgStat) * (size_t)N, 256);
+    L.offTab = off; off += align_up(sizeof(DeeTab), 256);
     L.offVal = off; off += align_up((size_t)N * H * W * sizeof(double), 256);
     L.offCl = off; off += align_up((size_t)N * H * W, 256);
     L.offE = off; off += align_up((size_t)N * H * W, 256);
@@ -217,8 +302,10 @@ static int run(const T *prob, int N, int H, int W, int do_nms, int do_hyst, doub
     // NMS only, fp32 out of fp32 in (or fp64/fp64): write straight to the output
     if (wantVal && !do_hyst && ((out_dtype == MTE_F32 && sizeof(T) == 4) || (out_dtype == MTE_F64 && sizeof(T) == 8)))
         nmsDst = static_cast<T *>(out);
-    dee_front_kernel<T><<<tiles, kThreads, 0, st>>>(prob, N, H, W, do_nms, do_hyst && wantVal, lo, hi, normals, nmsDst,
-                                                    cl, E, stats);
+    DeeTab *tab = reinterpret_cast<DeeTab *>(ws + L.offTab);
+    if (normals) dee_tables_kernel<<<1, 256, 0, st>>>(tab);  // 255 bisections, a few microseconds, no host state
+    dee_front_kernel<T><<<tiles, kThreads, 0, st>>>(tab, prob, N, H, W, do_nms, do_hyst && wantVal, lo, hi, normals,
+                                                    nmsDst, cl, E, stats);
     MTE_RETURN_IF_CUDA_ERROR();
     if (!wantVal) return MTE_OK;
     const size_t n = (size_t)N * H * W;

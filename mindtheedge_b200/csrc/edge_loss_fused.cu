@@ -27,7 +27,14 @@ namespace loss {
 #define MTE_FUSED_D 3
 #endif
 constexpr int kFusedD = MTE_FUSED_D;
-constexpr int kSegCostFused = 6;  // a segment start costs the window prologue + two halo rows of full work
+#ifndef MTE_FUSED_SEGCOST
+#define MTE_FUSED_SEGCOST 6
+#endif
+constexpr int kSegCostFused = MTE_FUSED_SEGCOST;  // a segment start costs the window prologue + two halo rows of full work
+#ifndef MTE_FUSED_P1ROWS
+#define MTE_FUSED_P1ROWS 16
+#endif
+constexpr int kP1Rows = MTE_FUSED_P1ROWS;  // edge rows a lane keeps in flight in phase 1 (one DRAM round trip per batch)
 __host__ __device__ constexpr int fused_smem_bytes() { return kRWarps * kFusedD * 3 * 512; }
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
@@ -79,23 +86,58 @@ __device__ __forceinline__ bool next_segment(const LossP &P, int &u0, int u1, Se
     return s.nrows > 0;
 }
 
+// ---- packed fp32 (sm_100a FADD2 / FMUL2 / FFMA2): the row loop is issue-bound (ncu: warps mostly "not selected",
+// ALU + FMA + XU pipes at 30-45 %), and one packed instruction does the work of two for the same pipe time, so every
+// per-pixel float operation that has both pixels of a pair in an aligned register pair is issued once per TWO pixels.
+// A lane's four pixels are two pairs; the quantities of a pixel's adjoint (A, C) / (A2, C2) are paired per pixel.
+__device__ __forceinline__ float2 f2(float s) { return make_float2(s, s); }
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return __ffma2_rn(b, f2(-1.f), a); }  // a - b, exact
+// 1 / d correctly rounded for normal d (see rcp_rn_normal), two at a time
+__device__ __forceinline__ float2 rcp_rn_normal2(float2 d) {
+    float2 r = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+    const float2 nd = f2mul(d, f2(-1.f));
+    float2 e = f2fma(nd, r, f2(1.f));
+    r = f2fma(r, e, r);
+    e = f2fma(nd, r, f2(1.f));
+    return f2fma(r, e, r);
+}
+
+struct PRow2 {   // one depth row as the stencils consume it, pixel pairs (0,1) and (2,3)
+    float2 c[2], s3[2], d[2];
+};
+__device__ __forceinline__ void prep_row2(PRow2 &R, const float2 (&x)[2]) {
+    // horizontal neighbours across the lane boundary (lanes 0 / 31 are halo lanes: their outer values are unused)
+    const float l = __shfl_up_sync(MTE_FULL_MASK, x[1].y, 1);
+    const float r = __shfl_down_sync(MTE_FULL_MASK, x[0].x, 1);
+    R.c[0] = x[0];
+    R.c[1] = x[1];
+    // the shifted rows are not pair-aligned, so these stay scalar
+    R.s3[0] = make_float2((l + x[0].x) + x[0].y, (x[0].x + x[0].y) + x[1].x);
+    R.s3[1] = make_float2((x[0].y + x[1].x) + x[1].y, (x[1].x + x[1].y) + r);
+    R.d[0] = make_float2(x[0].y - l, x[1].x - x[0].x);
+    R.d[1] = make_float2(x[1].y - x[0].y, r - x[1].x);
+}
+
 template <bool INV, bool SIG>
 __device__ __forceinline__ void fused_segment(const LossP &P, const ScaleP &S, const Seg &sg, int lane,
                                               unsigned char *ring, const float4 *sLut, float cp, float cn,
-                                              float (&la)[2], float &poison) {
-    constexpr int VEC = 4, D = kFusedD;
+                                              float2 (&la)[2], float &poison) {
+    constexpr int D = kFusedD;
     constexpr unsigned PLB = 512, SLB = 3 * PLB;
     constexpr float kFill = INV ? 3.0e38f : 0.f;  // its reciprocal flushes to exactly 0 (the conv zero padding)
     const int H = S.H, row0 = sg.row0, nrows = sg.nrows;
     const unsigned W = (unsigned)S.W;
-    const int col0 = (sg.strip * kHaloLanes + lane - 1) * VEC;
+    const int col0 = (sg.strip * kHaloLanes + lane - 1) * 4;
     const bool colOk = col0 >= 0 && col0 < (int)W;
     const bool writer = colOk && lane >= 1 && lane <= kHaloLanes;
     const size_t lo = (size_t)sg.img * H * W + (colOk ? col0 : 0);
     const float *xP = S.x + lo, *eP = S.e + lo, *nP = S.n + lo;
     float *gP = S.g + lo, *dP = S.dx + lo;
     const bool writeG = writer && S.g != nullptr;
-    const float T = P.T;
+    const float2 mT = f2(-P.T), cp2 = f2(cp), cn2 = f2(cn), eps2 = f2(kEps), one2 = f2(1.f), m1 = f2(-1.f);
     unsigned char *slot0 = ring + lane * 16;
     const unsigned ringS = (unsigned)__cvta_generic_to_shared(slot0);
 
@@ -109,27 +151,38 @@ __device__ __forceinline__ void fused_segment(const LossP &P, const ScaleP &S, c
         cp_async_vec<4>(ringS + so + PLB, elem_addr(eP, ro), rOk);
         cp_async_vec<4>(ringS + so + 2 * PLB, elem_addr(nP, ro), rOk);
     };
-    auto fix_row = [&](float (&x)[VEC], int row) {  // padding, inv2depth, non-finite tracking
+    auto fix_row = [&](float2 (&x)[2], int row) {  // padding, inv2depth, non-finite tracking
         if (INV) {
             const bool ok = colOk && row >= 0 && row < H;
 #pragma unroll
-            for (int v = 0; v < VEC; v++) x[v] = inv_to_depth(ok ? x[v] : kFill);
+            for (int h = 0; h < 2; h++) {
+                // torch.clamp(min=1e-6) keeps a NaN (max.NaN), then the correctly rounded reciprocal
+                const float2 v = make_float2(fmax_nan(ok ? x[h].x : kFill, 1e-6f), fmax_nan(ok ? x[h].y : kFill, 1e-6f));
+                x[h] = rcp_rn_normal2(v);
+            }
         }
-#pragma unroll
-        for (int v = 0; v < VEC; v++) poison = fmaf(x[v], 0.f, poison);
+        // x * 0 is NaN exactly when x is NaN or +-Inf (the reference's conv2d turns such a pixel into a NaN loss)
+        const float2 t = f2fma(x[0], f2(0.f), f2mul(x[1], f2(0.f)));
+        poison += t.x + t.y;
     };
-    auto load_plain = [&](float (&x)[VEC], int row) {
-#pragma unroll
-        for (int v = 0; v < VEC; v++) x[v] = 0.f;
+    auto load_plain = [&](float2 (&x)[2], int row) {
+        x[0] = f2(0.f);
+        x[1] = f2(0.f);
         if (colOk && row >= 0 && row < H) {
             const float4 t = ld_cached4(elem_addr(xP, (unsigned)row * W));
-            x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+            x[0] = make_float2(t.x, t.y);
+            x[1] = make_float2(t.z, t.w);
         }
+    };
+    auto lds2 = [&](float2 (&x)[2], const unsigned char *p) {
+        const float4 t = *reinterpret_cast<const float4 *>(p);
+        x[0] = make_float2(t.x, t.y);
+        x[1] = make_float2(t.z, t.w);
     };
 
     const int niter = nrows + 2;
-    PRow<VEC> win[3];  // win[d % 3] holds depth row row0 - 2 + d
-    float xa[VEC], xc[VEC];
+    PRow2 win[3];  // win[d % 3] holds depth row row0 - 2 + d
+    float2 xa[2], xc[2];
     load_plain(xa, row0 - 2);
     load_plain(xc, row0 - 1);
 #pragma unroll
@@ -139,13 +192,13 @@ __device__ __forceinline__ void fused_segment(const LossP &P, const ScaleP &S, c
     }
     fix_row(xa, row0 - 2);
     fix_row(xc, row0 - 1);
-    prep_row<VEC, MODE_DIR>(win[0], xa);
-    prep_row<VEC, MODE_DIR>(win[1], xc);
-    float oacc[3][VEC];
+    prep_row2(win[0], xa);
+    prep_row2(win[1], xc);
+    float oacc[3][4];
 #pragma unroll
     for (int o = 0; o < 3; o++)
 #pragma unroll
-        for (int v = 0; v < VEC; v++) oacc[o][v] = 0.f;
+        for (int v = 0; v < 4; v++) oacc[o][v] = 0.f;
 
     unsigned so = 0;
 #pragma unroll 1
@@ -155,76 +208,91 @@ __device__ __forceinline__ void fused_segment(const LossP &P, const ScaleP &S, c
             const int j = jj + u;
             if (j < niter) {  // warp-uniform
                 cp_async_wait<D - 1>();
-                float xn[VEC], e[VEC], th[VEC];
-                lds_vec<VEC>(xn, slot0 + so);
-                lds_vec<VEC>(e, slot0 + so + PLB);
-                lds_vec<VEC>(th, slot0 + so + 2 * PLB);
+                float2 xn[2], e[2], th[2];
+                lds2(xn, slot0 + so);
+                lds2(e, slot0 + so + PLB);
+                lds2(th, slot0 + so + 2 * PLB);
                 if (j + D < niter) issue(so, j + D);  // refill the slot just read
                 cp_async_commit();
                 so = (so + SLB == D * SLB) ? 0u : so + SLB;
                 const int r = row0 - 1 + j;
-                PRow<VEC> &dn = win[(u + 2) % 3];
+                PRow2 &dn = win[(u + 2) % 3];
                 fix_row(xn, r + 1);
-                prep_row<VEC, MODE_DIR>(dn, xn);
-                const PRow<VEC> &up = win[u % 3];
-                const PRow<VEC> &mid = win[(u + 1) % 3];
+                prep_row2(dn, xn);
+                const PRow2 &up = win[u % 3];
+                const PRow2 &mid = win[(u + 1) % 3];
                 const bool own = j >= 1 && j <= nrows;            // a row this segment owns (warp-uniform)
                 const bool live = colOk && r >= 0 && r < H;       // the response pixel exists
-                float g[VEC], A[VEC], C[VEC], A2[VEC], C2[VEC];
+                float g[4];
+                float2 X[4], Z[4];   // per pixel: (A, C) and (A2, C2) of the adjoint
 #pragma unroll
-                for (int v = 0; v < VEC; v++) {
+                for (int h = 0; h < 2; h++) {
                     // separable parts of the four zero-padded 3x3 cross-correlations of grad_loss.py:20-31:
                     // c_v = Pv + dv, c_h = Rh + Dm, c_lr = Pv + Rh, c_rl = Rh - Pv
-                    const float Pv = dn.s3[v] - up.s3[v];
-                    const float Dm = mid.d[v];
-                    const float Rh = (up.d[v] + Dm) + dn.d[v];
-                    const float dv = dn.c[v] - up.c[v];
-                    float c;
-                    unsigned cd;
-                    pick_directional(th[v], Pv, Rh, Dm, dv, c, cd);
-                    g[v] = fabsf(c);
+                    const float2 Pv = f2sub(dn.s3[h], up.s3[h]);
+                    const float2 Dm = mid.d[h];
+                    const float2 Rh = f2add(f2add(up.d[h], Dm), dn.d[h]);
+                    const float2 dv = f2sub(dn.c[h], up.c[h]);
+                    float c0, c1;
+                    unsigned cd0, cd1;
+                    pick_directional(th[h].x, Pv.x, Rh.x, Dm.x, dv.x, c0, cd0);
+                    pick_directional(th[h].y, Pv.y, Rh.y, Dm.y, dv.y, c1, cd1);
+                    const float2 gg = make_float2(fabsf(c0), fabsf(c1));
+                    g[2 * h] = gg.x;
+                    g[2 * h + 1] = gg.y;
                     // p the reference-faithful way (accurate expf, correctly rounded reciprocal): the gradient term
                     // p(1-p)/(1-p+eps) amplifies the last bits of p where the sigmoid saturates
-                    const float p = SIG ? sigmoid_ref(g[v] - T) : g[v];
-                    const float q = 1.0f - p;
-                    const float pe = p + kEps, qe = q + kEps;
-                    const float ee = e[v], ne = 1.0f - ee;
-                    if (own) {
-                        la[0] = fmaf(ee, lg2_approx(pe), la[0]);
-                        la[1] = fmaf(ne, lg2_approx(qe), la[1]);
+                    float2 p = gg;
+                    if (SIG) {
+                        const float2 nz = f2sub(f2(P.T), gg);   // -(g - T), exactly as g - T negated
+                        p = rcp_rn_normal2(f2add(make_float2(expf(nz.x), expf(nz.y)), one2));
                     }
-                    float d = cp * ee * rcp_approx(pe) + cn * ne * rcp_approx(qe);
-                    if (SIG) d = d * p * q;
-                    d = (live && g[v] != 0.f) ? d : 0.f;  // sign(0) = 0; pixels outside the image do not exist
-                    const float4 k = sLut[cd & 15u];
-                    A[v] = d * k.x; C[v] = d * k.y; A2[v] = d * k.z; C2[v] = d * k.w;
+                    const float2 q = f2fma(p, m1, one2);       // 1 - p
+                    const float2 pe = f2add(p, eps2), qe = f2add(q, eps2);
+                    const float2 ee = e[h], ne = f2fma(ee, m1, one2);
+                    if (own) {
+                        la[0] = f2fma(ee, make_float2(lg2_approx(pe.x), lg2_approx(pe.y)), la[0]);
+                        la[1] = f2fma(ne, make_float2(lg2_approx(qe.x), lg2_approx(qe.y)), la[1]);
+                    }
+                    float2 d = f2mul(f2mul(cp2, ee), make_float2(rcp_approx(pe.x), rcp_approx(pe.y)));
+                    d = f2fma(f2mul(cn2, ne), make_float2(rcp_approx(qe.x), rcp_approx(qe.y)), d);
+                    if (SIG) d = f2mul(f2mul(d, p), q);
+                    // sign(0) = 0; pixels outside the image do not exist
+                    const float d0 = (live && gg.x != 0.f) ? d.x : 0.f, d1 = (live && gg.y != 0.f) ? d.y : 0.f;
+                    const float4 k0 = sLut[cd0 & 15u], k1 = sLut[cd1 & 15u];
+                    X[2 * h] = f2mul(f2(d0), make_float2(k0.x, k0.y));
+                    Z[2 * h] = f2mul(f2(d0), make_float2(k0.z, k0.w));
+                    X[2 * h + 1] = f2mul(f2(d1), make_float2(k1.x, k1.y));
+                    Z[2 * h + 1] = f2mul(f2(d1), make_float2(k1.z, k1.w));
                 }
                 if (own && writeG)
                     st_stream4(elem_addr(gP, (unsigned)r * W), make_float4(g[0], g[1], g[2], g[3]));
-                const float Al = __shfl_up_sync(MTE_FULL_MASK, A[VEC - 1], 1), Ar = __shfl_down_sync(MTE_FULL_MASK, A[0], 1);
-                const float Cl = __shfl_up_sync(MTE_FULL_MASK, C[VEC - 1], 1), Cr = __shfl_down_sync(MTE_FULL_MASK, C[0], 1);
-                const float C2l = __shfl_up_sync(MTE_FULL_MASK, C2[VEC - 1], 1), C2r = __shfl_down_sync(MTE_FULL_MASK, C2[0], 1);
+                // neighbours across the lane boundary: (A, C) and C2 of the adjacent pixel
+                const float2 Xl = make_float2(__shfl_up_sync(MTE_FULL_MASK, X[3].x, 1), __shfl_up_sync(MTE_FULL_MASK, X[3].y, 1));
+                const float2 Xr = make_float2(__shfl_down_sync(MTE_FULL_MASK, X[0].x, 1), __shfl_down_sync(MTE_FULL_MASK, X[0].y, 1));
+                const float C2l = __shfl_up_sync(MTE_FULL_MASK, Z[3].y, 1), C2r = __shfl_down_sync(MTE_FULL_MASK, Z[0].y, 1);
                 // response row r acts as "up" for output row r + 1 (first contribution: overwrites the retired slot),
                 // as "mid" for output row r and as "down" for output row r - 1, which it completes
 #pragma unroll
-                for (int v = 0; v < VEC; v++) {
-                    const float a_l = v == 0 ? Al : A[(v + VEC - 1) % VEC], a_r = v == VEC - 1 ? Ar : A[(v + 1) % VEC];
-                    const float c_l = v == 0 ? Cl : C[(v + VEC - 1) % VEC], c_r = v == VEC - 1 ? Cr : C[(v + 1) % VEC];
-                    const float c2_l = v == 0 ? C2l : C2[(v + VEC - 1) % VEC], c2_r = v == VEC - 1 ? C2r : C2[(v + 1) % VEC];
-                    const float SA = (a_l + a_r) + A2[v], DC = c_l - c_r;
+                for (int v = 0; v < 4; v++) {
+                    const float2 xl = v == 0 ? Xl : X[(v + 3) % 4], xr = v == 3 ? Xr : X[(v + 1) % 4];
+                    const float c2_l = v == 0 ? C2l : Z[(v + 3) % 4].y, c2_r = v == 3 ? C2r : Z[(v + 1) % 4].y;
+                    // (a_l + a_r, c_l - c_r) in one packed add: the right neighbour enters as (A, -C)
+                    const float2 U = f2add(xl, make_float2(xr.x, -xr.y));
+                    const float SA = U.x + Z[v].x, DC = U.y;
                     oacc[u][v] = SA + DC;
                     oacc[(u + 2) % 3][v] += c2_l - c2_r;
                     oacc[(u + 1) % 3][v] -= SA - DC;
                 }
                 if (j >= 2) {
-                    float out[VEC];
+                    float out[4];
 #pragma unroll
-                    for (int v = 0; v < VEC; v++) {
+                    for (int v = 0; v < 4; v++) {
                         float d = oacc[(u + 1) % 3][v];
                         if (INV) {
                             // pred was an inverse depth: chain through depth = 1 / clamp(inv, 1e-6)
                             // (utils/depth.py:104-121); the depth of output row r - 1 is the window's upper row
-                            const float dep = up.c[v];
+                            const float dep = (v & 1) ? up.c[v >> 1].y : up.c[v >> 1].x;
                             d = (dep < 1e6f) ? -d * dep * dep : 0.f;
                         }
                         out[v] = d;
@@ -236,8 +304,8 @@ __device__ __forceinline__ void fused_segment(const LossP &P, const ScaleP &S, c
     }
     cp_async_wait<0>();
     if (!writer) {  // halo / out-of-image lanes: their pixels belong to the neighbouring strips
-        la[0] = 0.f;
-        la[1] = 0.f;
+        la[0] = f2(0.f);
+        la[1] = f2(0.f);
     }
 }
 
@@ -264,6 +332,7 @@ __global__ void __launch_bounds__(kRThreads, 1) edge_loss_fused_kernel(const __g
     const int uEnd = (int)((long long)P.totalUnits * (gw + 1) / nWarps);
 
     // ---- phase 1: Wp_b = sum of the edge labels, every warp over the rows it owns (the lines stay in L2 for phase 2)
+#ifndef MTE_FUSED_TIMING_NO_PHASE1   // timing experiments only (results are wrong without it)
     {
         int u0 = uBeg;
         while (u0 < uEnd) {
@@ -276,16 +345,16 @@ __global__ void __launch_bounds__(kRThreads, 1) edge_loss_fused_kernel(const __g
             const float *eP = S.e + (size_t)sg.img * S.H * W + (writer ? col0 : 0);
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll 1
-            for (int j0 = 0; j0 < sg.nrows; j0 += 8) {
-                float4 t[8];
+            for (int j0 = 0; j0 < sg.nrows; j0 += kP1Rows) {
+                float4 t[kP1Rows];
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
+                for (int k = 0; k < kP1Rows; k++) {
                     t[k] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (writer && j0 + k < sg.nrows)
                         t[k] = *reinterpret_cast<const float4 *>(elem_addr(eP, (unsigned)(sg.row0 + j0 + k) * W));
                 }
 #pragma unroll
-                for (int k = 0; k < 8; k += 2) {
+                for (int k = 0; k < kP1Rows; k += 2) {
                     s0 += (t[k].x + t[k].y) + (t[k].z + t[k].w);
                     s1 += (t[k + 1].x + t[k + 1].y) + (t[k + 1].z + t[k + 1].w);
                 }
@@ -299,6 +368,9 @@ __global__ void __launch_bounds__(kRThreads, 1) edge_loss_fused_kernel(const __g
         }
     }
     grid_barrier(F.barrier, gridDim.x);
+#else
+    __syncthreads();
+#endif
 
     // ---- phase 2
     int u0 = uBeg;
@@ -324,12 +396,12 @@ __global__ void __launch_bounds__(kRThreads, 1) edge_loss_fused_kernel(const __g
         if (G == 0.f) G = 1.f;  // a zero expectation could not be rescaled later
         const float coef = (float)((double)P.weight / (npix * (double)S.B)) * G;
         const float cp = -coef * P.p2n * alpha, cn = coef * (1.0f - alpha);
-        float la[2] = {0.f, 0.f};
+        float2 la[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
         float poison = 0.f;
         fused_segment<INV, SIG>(P, S, sg, lane, ring, sLut, cp, cn, la, poison);
         bool bad = __any_sync(MTE_FULL_MASK, !(poison == 0.f));
         unsigned long long *acc = P.accum + (size_t)(S.imgBase + sg.img) * kAcc;
-        const float vp = warp_sum(la[0]), vn = warp_sum(la[1]);
+        const float vp = warp_sum(la[0].x + la[0].y), vn = warp_sum(la[1].x + la[1].y);
         bad = bad || !isfinite(vp) || !isfinite(vn);
         if (lane == 0) {
             atomicAdd(acc + A_SPU, (unsigned long long)__double2ll_rn((double)vp * kFix));
@@ -371,6 +443,12 @@ __global__ void __launch_bounds__(256) edge_loss_rescale_kernel(const __grid_con
                                                                 float *ctx, float *expectedOut) {
     float *cur = ctx + P.totalImages + 2 * MTE_MAX_SCALES;
     unsigned *done = reinterpret_cast<unsigned *>(ctx + P.totalImages + 3 * MTE_MAX_SCALES);
+    bool any = false;
+    for (int k = 0; k < P.nScales; k++) any = any || (gradLoss[0] * P.s[k].scaleWeight + gradLoss[1 + k] != cur[k]);
+    if (!any) {  // every CTA sees the same values: nothing to rescale, nothing to record
+        if (expectedOut && blockIdx.x == 0 && threadIdx.x <= P.nScales) expectedOut[threadIdx.x] = gradLoss[threadIdx.x];
+        return;
+    }
     for (int k = 0; k < P.nScales; k++) {
         const ScaleP &S = P.s[k];
         const float G = gradLoss[0] * S.scaleWeight + gradLoss[1 + k];
@@ -513,7 +591,7 @@ extern "C" int mte_edge_loss_grad_rescale(const mte_loss_scale_t *sc, int n, con
         img += sc[i].B;
     }
     P.nScales = n; P.totalImages = img;
-    edge_loss_rescale_kernel<<<num_sms() * 4, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    edge_loss_rescale_kernel<<<num_sms() * 2, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         P, grad_loss, static_cast<float *>(ctx), expected_out);
     MTE_RETURN_IF_CUDA_ERROR();
     return MTE_OK;

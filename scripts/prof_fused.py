@@ -1,0 +1,29 @@
+"""Tiny driver for ncu: the one-pass loss kernel at the config-3 loss shape (B=8, 4 scales), a few launches."""
+import ctypes as C, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+import bench
+from mindtheedge_b200 import _lib
+from mindtheedge_b200.losses import _attrs, _scales_struct
+dev = torch.device("cuda", 0)
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+sets = [bench.loss_inputs(8, 1000 + i, dev) for i in range(2)]
+at = _attrs(True, True, True, 4.0, 10.0, 1.0)
+w = [0.25] * 4
+keep = []
+for sc in sets:
+    pred = [t[0] for t in sc]; edge = [t[1] for t in sc]; normal = [t[2] for t in sc]
+    gmap = [torch.empty_like(e) for e in edge]; gpred = [torch.empty_like(p) for p in pred]
+    b = _scales_struct(pred, edge, normal, None, gmap, gpred, w)
+    losses = torch.zeros(5, device=dev); ctx = torch.zeros(_lib.lib.mte_edge_loss_ctx_bytes(b, 4) // 4, device=dev)
+    ws = torch.zeros(_lib.lib.mte_edge_loss_workspace_bytes(b, 4), dtype=torch.uint8, device=dev)
+    gl = torch.zeros(5, device=dev); gl[0] = 1
+    keep.append((b, gmap, gpred, losses, ctx, ws, gl))
+st = torch.cuda.current_stream().cuda_stream
+for i in range(n):
+    b, _, _, losses, ctx, ws, gl = keep[i % 2]
+    _lib.check(_lib.lib.mte_edge_loss_fwd_grad(b, 4, C.byref(at), None, losses.data_ptr(), ctx.data_ptr(), ws.data_ptr(), ws.numel(), st))
+    _lib.check(_lib.lib.mte_edge_loss_grad_rescale(b, 4, gl.data_ptr(), ctx.data_ptr(), None, st))
+torch.cuda.synchronize()
+print("loss", keep[0][3][0].item())

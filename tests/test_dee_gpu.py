@@ -45,3 +45,44 @@ def test_fused_batch_vs_oracle(shape):
         ref = odee.hysteresis(odee.non_max_suppression(probs[k]))
         assert _eq(out[k], ref), ("edges", k, int((out[k] != ref).sum()))
     assert (out[0] > 0).any()
+
+
+def test_exact_quantisation_on_adversarial_gradients():
+    """The atan2-free quantisation (candidate level from fp32, proved by fp64 cross products, exact double atan2 only
+    inside the guard bands) on inputs built to sit ON the decision boundaries: flat planes (zero gradient, every sign
+    of zero), exact ramps whose Sobel ratio is 0, 1, -1, inf, tan(22.5 deg) to the last bit, tiny and huge dynamic
+    range, NaN / Inf pixels -- u8 normals and NMS planes bit-exact against the oracle (cv2.Sobel + NumPy)."""
+    from mindtheedge_b200.tools import dee_postprocess
+    from oracle import dee as odee
+    H, W = 64, 96
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    r = np.random.default_rng(3)
+    planes = [
+        np.zeros((H, W)), np.full((H, W), 0.25), xx / W, yy / H, (xx + yy) / (H + W), (xx - yy) / (H + W) + 0.5,
+        -xx / W + 1, (yy * 0.41421356237309503 + xx) / (2 * W), (yy * 2.4142135623730951 + xx) / (4 * W),
+        (np.round(r.random((H, W)) * 8) / 8), r.random((H, W)) * 1e-30, r.random((H, W)) * 1e30,
+        np.where(r.random((H, W)) < 0.02, np.nan, r.random((H, W))), np.where(r.random((H, W)) < 0.02, np.inf, r.random((H, W))),
+        np.sin(xx / 7.0) * np.cos(yy / 5.0) * 0.5 + 0.5,
+    ]
+    for dt in (np.float32, np.float64):
+        probs = np.stack(planes).astype(dt)
+        with np.errstate(all="ignore"):
+            nrm, out = dee_postprocess(torch.from_numpy(probs).cuda(), hysteresis=False)
+            nrm, out = nrm.cpu().numpy(), out.cpu().numpy()
+            for k in range(len(planes)):
+                assert np.array_equal(nrm[k], odee.normals_u8(probs[k])), ("normals", dt, k)
+                ref = odee.non_max_suppression(probs[k])
+                assert _eq(out[k], ref), ("nms", dt, k, int((out[k] != ref).sum()))
+
+
+def test_many_random_frames_vs_oracle():
+    """Volume check of the fast quantisation paths: 24 KITTI-size frames (11.8 Mpx), normals + NMS + hysteresis."""
+    from mindtheedge_b200.tools import dee_postprocess
+    from oracle import dee as odee
+    probs = np.stack([prob_map(384, 1280, 900 + k) for k in range(24)])
+    nrm, out = dee_postprocess(torch.from_numpy(probs).cuda())
+    nrm, out = nrm.cpu().numpy(), out.cpu().numpy()
+    for k in range(24):
+        assert np.array_equal(nrm[k], odee.normals_u8(probs[k])), ("normals", k)
+        ref = odee.hysteresis(odee.non_max_suppression(probs[k]))
+        assert _eq(out[k], ref), ("edges", k)

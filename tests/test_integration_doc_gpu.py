@@ -37,5 +37,8 @@ def test_s1_raw_loss_binding_runs_and_matches_the_adapter():
     x2 = depth.cuda().requires_grad_(True)
     loss2, gmap2 = GradLoss("cross_entropy", True, [], 10.0, 1.0)(x2, edge.cuda(), None, True, True, 4, normal.cuda())
     loss2.backward()
-    assert loss1.item() == loss2.item()
-    assert torch.equal(gmap1, gmap2) and torch.equal(x1.grad, x2.grad)
+    # the doc's binding is the two-kernel C-ABI pair; the adapter takes the one-pass kernel for this configuration:
+    # same responses (bit-equal grad map), sigmoid evaluated once the reference-faithful way for loss and gradient
+    assert abs(loss1.item() - loss2.item()) <= 1e-6 * abs(loss2.item())
+    assert torch.equal(gmap1, gmap2)
+    assert float((x1.grad - x2.grad).abs().max()) <= 2e-6 * float(x2.grad.abs().max())
