@@ -187,6 +187,41 @@ __global__ void __launch_bounds__(kThreads) alt_scatter_kernel(const float *__re
     }
 }
 
+// The same adjoint without normals (GradLayer's magnitude path, grad_loss.py:70-73: g = sqrt(c_v^2 + c_h^2 + 1e-6)):
+// d g / d x = (c_v K_v + c_h K_h) / g, so every response pixel n contributes K_v[m-n] * dldg * c_v / g +
+// K_h[m-n] * dldg * c_h / g; c_v, c_h are recomputed from the prediction (zero padding).  Off the shipped path: a
+// plain gather (9 neighbours x two 3x3 stencils per pixel).
+__global__ void __launch_bounds__(kThreads) alt_scatter_mag_kernel(const float *__restrict__ dldg,
+                                                                   const float *__restrict__ gmap,
+                                                                   const float *__restrict__ pred, float *__restrict__ dx,
+                                                                   int B, int H, int W, int accumulate) {
+    const size_t n = (size_t)B * H * W;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+        const int x = (int)(i % W), y = (int)((i / W) % H);
+        const float *img = pred + (i - (size_t)y * W - x);
+        const size_t plane = i - (size_t)y * W - x;
+        float d = 0.f;
+        for (int a = -1; a <= 1; a++)
+            for (int b = -1; b <= 1; b++) {
+                const int yy = y - a, xx = x - b;  // response pixel n with n + (a, b) = m
+                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                float cv = 0.f, ch = 0.f;
+                for (int u = -1; u <= 1; u++)
+                    for (int v = -1; v <= 1; v++) {
+                        const int py = yy + u, px = xx + v;
+                        if (py < 0 || py >= H || px < 0 || px >= W) continue;
+                        const float val = img[(size_t)py * W + px];
+                        cv += kK[2][u + 1][v + 1] * val;
+                        ch += kK[0][u + 1][v + 1] * val;
+                    }
+                const size_t j = plane + (size_t)yy * W + xx;
+                const float r = dldg[j] / gmap[j];   // g >= 1e-3 by construction
+                d += (kK[2][a + 1][b + 1] * cv + kK[0][a + 1][b + 1] * ch) * r;
+            }
+        dx[i] = accumulate ? dx[i] + d : d;
+    }
+}
+
 static int grid_for(size_t n) {
     const size_t b = (n + kThreads - 1) / kThreads;
     return (int)(b < (size_t)num_sms() * 8 ? (b ? b : 1) : (size_t)num_sms() * 8);
@@ -245,7 +280,9 @@ extern "C" int mte_edge_loss_alt_bwd(const float *grad_map, const float *edge, c
                                      const float *ctx, float *grad_pred, int accumulate, void *workspace, size_t ws_bytes,
                                      mte_stream_t stream) {
     if (!grad_map || !edge || !grad_loss || !ctx || !grad_pred || !workspace) return MTE_ERR_NULL;
-    if ((is_grad && !stash) || (pred_is_inverse && !pred)) return MTE_ERR_NULL;
+    // is_grad without a stash = the magnitude path (no normals): the adjoint is recomputed from the prediction
+    if ((is_grad && !stash && !pred) || (pred_is_inverse && !pred)) return MTE_ERR_NULL;
+    if (is_grad && !stash && pred_is_inverse) return MTE_ERR_ARG;
     if (B < 1 || H < 1 || W < 1) return MTE_ERR_SHAPE;
     if (!types_ok(loss_types)) return MTE_ERR_ARG;
     if (ws_bytes < mte_edge_loss_alt_workspace_bytes(B, H, W)) return MTE_ERR_WORKSPACE;
@@ -265,8 +302,11 @@ extern "C" int mte_edge_loss_alt_bwd(const float *grad_map, const float *edge, c
         P.alphaMap = am;
     }
     alt_dldg_kernel<<<grid_for(P.n), kThreads, 0, st>>>(P);
-    alt_scatter_kernel<<<grid_for(P.n), kThreads, 0, st>>>(P.dldg, grad_map, stash, pred, grad_pred, B, H, W, is_grad,
-                                                          pred_is_inverse, accumulate);
+    if (is_grad && !stash)
+        alt_scatter_mag_kernel<<<grid_for(P.n), kThreads, 0, st>>>(P.dldg, grad_map, pred, grad_pred, B, H, W, accumulate);
+    else
+        alt_scatter_kernel<<<grid_for(P.n), kThreads, 0, st>>>(P.dldg, grad_map, stash, pred, grad_pred, B, H, W, is_grad,
+                                                              pred_is_inverse, accumulate);
     MTE_RETURN_IF_CUDA_ERROR();
     return MTE_OK;
 }

@@ -342,10 +342,10 @@ class _AltEdgeLossFn(torch.autograd.Function):
 def _alt_edge_loss(types, output, gt_edge, gt_mask, is_grad, is_sigmoid, sigmoid_thresh, gt_normals, weight, pos_to_neg):
     pred = _prep(output, "prediction")
     edge = _prep(gt_edge, "gt_edge")
-    if pred.shape != edge.shape:
-        raise NotImplementedError("the attention / dice loss types need the prediction at the target size")
-    if is_grad and gt_normals is None:
-        raise NotImplementedError("the attention / dice loss types need gt_normals when is_grad (directional path)")
+    if pred.shape[-2:] != edge.shape[-2:]:
+        # grad_loss.py:127 resizes with F.interpolate(mode='bilinear') before anything else; off the shipped path
+        # (every scale has targets of its own size), so the same stock op is used and autograd carries its adjoint
+        pred = torch.nn.functional.interpolate(pred, size=edge.shape[-2:], mode="bilinear").contiguous()
     normal = [_prep(gt_normals, "gt_normals")] if (gt_normals is not None and is_grad) else []
     mask = [_prep(gt_mask, "gt_mask")] if gt_mask is not None else []
     flags = (bool(is_grad), bool(is_sigmoid), False, float(sigmoid_thresh), float(weight), float(pos_to_neg))

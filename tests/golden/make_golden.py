@@ -147,6 +147,44 @@ def gen_edge_loss_alt():
     print("edge_loss_alt:", {k: float(c["loss"]) for k, c in cases.items()})
 
 
+def gen_edge_loss_alt2():
+    """More of GradLoss.forward's alternative types through the UNMODIFIED reference: without normals (GradLayer's
+    magnitude path, grad_loss.py:70-73) and with a prediction smaller / larger than the targets (F.interpolate, :127)."""
+    GradLoss = load_gradloss()
+    cases = {}
+
+    def run(name, ltype, depth, edge, mask, normal, weight=10.0, thresh=4):
+        head = GradLoss(ltype, True, [], weight, 1.0)
+        x = depth.clone().requires_grad_(True)
+        loss, gmap = head(x, edge, mask, True, True, thresh, normal)
+        loss.backward()
+        cases[name] = dict(
+            depth=depth.numpy(), edge=edge.numpy(), ltype=np.array(ltype),
+            mask=np.zeros(0, np.float32) if mask is None else mask.numpy(),
+            normal=np.zeros(0, np.float32) if normal is None else normal.numpy(),
+            attrs=np.array([1, 1, thresh, weight], np.float64),
+            loss=np.float32(loss.item()), grad_map=gmap.numpy(), dgrad=x.grad.numpy())
+
+    g = torch.Generator().manual_seed(654)
+    d, e, n = loss_inputs(2, 48, 64, 21)
+    e = torch.where(torch.rand(e.shape, generator=g) < 0.3, (e > 0).float(), e)
+    m = (torch.rand(2, 1, 48, 64, generator=g) < 0.6).float()
+    run("attention_mag", "attention_loss", d, e, None, None)
+    run("spatial_mag_mask", "spatially_adaptive", d, e, m, None, weight=2.5, thresh=2)
+    run("ce_dice_mag", "cross_entropy_dice", d, e, None, None)
+    dsmall, _, _ = loss_inputs(2, 24, 32, 22)
+    dbig, _, _ = loss_inputs(2, 60, 100, 23)
+    run("attention_up", "attention_loss", dsmall, e, None, n)
+    run("spatial_dice_down", "spatially_adaptive_dice", dbig, e, None, n, weight=3.0)
+    run("attention_mag_up", "attention_loss", dsmall, e, None, None)
+    flat = {}
+    for k, c in cases.items():
+        for f, v in c.items():
+            flat[f"{k}/{f}"] = v
+    np.savez_compressed(os.path.join(HERE, "edge_loss_alt2.npz"), **flat)
+    print("edge_loss_alt2:", {k: float(c["loss"]) for k, c in cases.items()})
+
+
 def gen_canny():
     ref_edge = load_edge()
     out = {}
@@ -413,6 +451,10 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "targets":
         gen_targets()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "edge_loss_alt2":
+        torch.manual_seed(0)
+        gen_edge_loss_alt2()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "edge_loss_alt":
         torch.manual_seed(0)
         gen_edge_loss_alt()
@@ -420,6 +462,7 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     gen_edge_loss()
     gen_edge_loss_alt()
+    gen_edge_loss_alt2()
     gen_canny()
     gen_dee()
     gen_pr()

@@ -286,6 +286,9 @@ def test_no_cpu_fallback():
 ALT_CASES = load_cases("edge_loss_alt.npz")
 
 
+ALT_CASES.update(load_cases("edge_loss_alt2.npz"))   # without normals (magnitude path), prediction != target size
+
+
 @pytest.mark.parametrize("name", sorted(ALT_CASES))
 def test_alt_loss_types_golden(name):
     """attention_loss / spatially_adaptive / +dice (grad_loss.py:143-156) against the unmodified reference:
