@@ -200,25 +200,26 @@ __global__ void __launch_bounds__(kThreads) alt_scatter_mag_kernel(const float *
         const int x = (int)(i % W), y = (int)((i / W) % H);
         const float *img = pred + (i - (size_t)y * W - x);
         const size_t plane = i - (size_t)y * W - x;
-        float d = 0.f;
+        // fp64 accumulation: the stencil sums are then exact, so the only rounding left is the reference's own
+        double d = 0.0;
         for (int a = -1; a <= 1; a++)
             for (int b = -1; b <= 1; b++) {
                 const int yy = y - a, xx = x - b;  // response pixel n with n + (a, b) = m
                 if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-                float cv = 0.f, ch = 0.f;
+                double cv = 0.0, ch = 0.0;
                 for (int u = -1; u <= 1; u++)
                     for (int v = -1; v <= 1; v++) {
                         const int py = yy + u, px = xx + v;
                         if (py < 0 || py >= H || px < 0 || px >= W) continue;
-                        const float val = img[(size_t)py * W + px];
-                        cv += kK[2][u + 1][v + 1] * val;
-                        ch += kK[0][u + 1][v + 1] * val;
+                        const double val = (double)img[(size_t)py * W + px];
+                        cv += (double)kK[2][u + 1][v + 1] * val;
+                        ch += (double)kK[0][u + 1][v + 1] * val;
                     }
                 const size_t j = plane + (size_t)yy * W + xx;
-                const float r = dldg[j] / gmap[j];   // g >= 1e-3 by construction
-                d += (kK[2][a + 1][b + 1] * cv + kK[0][a + 1][b + 1] * ch) * r;
+                const double r = (double)dldg[j] / (double)gmap[j];   // g >= 1e-3 by construction
+                d += ((double)kK[2][a + 1][b + 1] * (double)(float)cv + (double)kK[0][a + 1][b + 1] * (double)(float)ch) * r;
             }
-        dx[i] = accumulate ? dx[i] + d : d;
+        dx[i] = accumulate ? dx[i] + (float)d : (float)d;
     }
 }
 

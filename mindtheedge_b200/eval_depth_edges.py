@@ -292,15 +292,52 @@ def _reorder_index(inv, device):
     return idx
 
 
+_SIDE_STREAMS: dict = {}
+
+
+def _side_streams(device, n):
+    key = (torch.device(device).index, n)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = [torch.cuda.Stream(device) for _ in range(n)]
+    return _SIDE_STREAMS[key]
+
+
+def _sweep_chunk(depth, gt, pairs, gt_crop, min_depth, max_depth, max_dist):
+    levels = canny_from_depth(depth, pairs, min_depth, max_depth, want_edges=False, want_levels=True)
+    return pr_counts(levels, gt, n_levels=len(pairs), max_dist=max_dist, crop=gt_crop)
+
+
 def sweep_counts(depth: torch.Tensor, gt: torch.Tensor, edge_thresh_range, gt_crop, min_depth, max_depth,
-                 max_dist=0.002, out=None) -> torch.Tensor:
+                 max_dist=0.002, out=None, pipeline_chunks: Optional[int] = None) -> torch.Tensor:
     """Device part of ``pr_evaluation`` for a batch: depth [N,H,W] (already at GT size), gt [N,H,W]
     uint8 -> int64[len(range),4].  Thresholds are swept strictest first internally (the level plane
-    needs nested pairs) and returned in the caller's order."""
+    needs nested pairs) and returned in the caller's order.
+
+    ``pipeline_chunks`` > 1 cuts the batch into chunks on side streams (a chunk's NMS + hysteresis next to another
+    chunk's matcher; counts are integer sums, the result does not depend on the chunking).  Measured on the bench set:
+    no gain (1.686 / 1.684 / 1.690 / 1.671 ms for 1-4 chunks) -- the step is the chain NMS -> hysteresis -> matcher of
+    its SLOWEST image, which no reordering of other images shortens -- so the default is one chunk."""
     order = np.argsort(-np.asarray(edge_thresh_range), kind="stable")
     pairs = [(int(edge_thresh_range[i] / 2), int(edge_thresh_range[i])) for i in order]
-    levels = canny_from_depth(depth, pairs, min_depth, max_depth, want_edges=False, want_levels=True)
-    c = pr_counts(levels, gt, n_levels=len(pairs), max_dist=max_dist, crop=gt_crop)
+    N = depth.shape[0] if depth.dim() == 3 else 1
+    chunks = pipeline_chunks if pipeline_chunks is not None else 1
+    if chunks <= 1 or depth.dim() != 3:
+        c = _sweep_chunk(depth, gt, pairs, gt_crop, min_depth, max_depth, max_dist)
+    else:
+        main = torch.cuda.current_stream(depth.device)
+        bounds = [round(k * N / chunks) for k in range(chunks + 1)]
+        parts = []
+        for k, st in enumerate(_side_streams(depth.device, chunks)):
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                parts.append(_sweep_chunk(depth[bounds[k]:bounds[k + 1]], gt[bounds[k]:bounds[k + 1]], pairs, gt_crop,
+                                          min_depth, max_depth, max_dist))
+        for p, st in zip(parts, _side_streams(depth.device, chunks)):
+            main.wait_stream(st)
+            p.record_stream(main)
+        c = parts[0]
+        for p in parts[1:]:
+            c = c + p
     c = c[_reorder_index(tuple(int(v) for v in np.argsort(order)), c.device)]
     if out is not None:
         out += c
