@@ -31,6 +31,9 @@ constexpr int kFusedD = MTE_FUSED_D;
 #define MTE_FUSED_SEGCOST 6
 #endif
 constexpr int kSegCostFused = MTE_FUSED_SEGCOST;  // a segment start costs the window prologue + two halo rows of full work
+#ifndef MTE_FUSED_REGS
+#define MTE_FUSED_REGS 120
+#endif
 #ifndef MTE_FUSED_P1ROWS
 #define MTE_FUSED_P1ROWS 16
 #endif
@@ -121,10 +124,49 @@ __device__ __forceinline__ void prep_row2(PRow2 &R, const float2 (&x)[2]) {
     R.d[1] = make_float2(x[1].y - x[0].y, r - x[1].x);
 }
 
+// The loads that open a segment (first D ring rows + the two depth rows above the first response row), as a function
+// of their own: the FIRST segment of every warp issues them BEFORE the grid barrier, so the DRAM round trip that
+// refills the pipeline after phase 1 overlaps the barrier instead of following it.
+__device__ __forceinline__ void fused_prologue(const ScaleP &S, const Seg &sg, int lane, unsigned char *ring,
+                                               float2 (&xa)[2], float2 (&xc)[2]) {
+    constexpr int D = kFusedD;
+    constexpr unsigned PLB = 512, SLB = 3 * PLB;
+    const int H = S.H, row0 = sg.row0, niter = sg.nrows + 2;
+    const unsigned W = (unsigned)S.W;
+    const int col0 = (sg.strip * kHaloLanes + lane - 1) * 4;
+    const bool colOk = col0 >= 0 && col0 < (int)W;
+    const size_t lo = (size_t)sg.img * H * W + (colOk ? col0 : 0);
+    const float *xP = S.x + lo, *eP = S.e + lo, *nP = S.n + lo;
+    const unsigned ringS = (unsigned)__cvta_generic_to_shared(ring + lane * 16);
+    auto load_plain = [&](float2 (&x)[2], int row) {
+        x[0] = make_float2(0.f, 0.f);
+        x[1] = make_float2(0.f, 0.f);
+        if (colOk && row >= 0 && row < H) {
+            const float4 t = ld_cached4(elem_addr(xP, (unsigned)row * W));
+            x[0] = make_float2(t.x, t.y);
+            x[1] = make_float2(t.z, t.w);
+        }
+    };
+    load_plain(xa, row0 - 2);
+    load_plain(xc, row0 - 1);
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        if (k < niter) {
+            const int rx = row0 + k, r = row0 - 1 + k;
+            cp_async_vec<4>(ringS + k * SLB, elem_addr(xP, (unsigned)min(rx, H - 1) * W), colOk && rx < H);
+            const bool rOk = colOk && r >= 0 && r < H;
+            const unsigned ro = (unsigned)min(max(r, 0), H - 1) * W;
+            cp_async_vec<4>(ringS + k * SLB + PLB, elem_addr(eP, ro), rOk);
+            cp_async_vec<4>(ringS + k * SLB + 2 * PLB, elem_addr(nP, ro), rOk);
+        }
+        cp_async_commit();
+    }
+}
+
 template <bool INV, bool SIG>
 __device__ __forceinline__ void fused_segment(const LossP &P, const ScaleP &S, const Seg &sg, int lane,
                                               unsigned char *ring, const float4 *sLut, float cp, float cn,
-                                              float2 (&la)[2], float &poison) {
+                                              float2 (&la)[2], float &poison, float2 (&xa)[2], float2 (&xc)[2]) {
     constexpr int D = kFusedD;
     constexpr unsigned PLB = 512, SLB = 3 * PLB;
     constexpr float kFill = INV ? 3.0e38f : 0.f;  // its reciprocal flushes to exactly 0 (the conv zero padding)
@@ -165,15 +207,6 @@ __device__ __forceinline__ void fused_segment(const LossP &P, const ScaleP &S, c
         const float2 t = f2fma(x[0], f2(0.f), f2mul(x[1], f2(0.f)));
         poison += t.x + t.y;
     };
-    auto load_plain = [&](float2 (&x)[2], int row) {
-        x[0] = f2(0.f);
-        x[1] = f2(0.f);
-        if (colOk && row >= 0 && row < H) {
-            const float4 t = ld_cached4(elem_addr(xP, (unsigned)row * W));
-            x[0] = make_float2(t.x, t.y);
-            x[1] = make_float2(t.z, t.w);
-        }
-    };
     auto lds2 = [&](float2 (&x)[2], const unsigned char *p) {
         const float4 t = *reinterpret_cast<const float4 *>(p);
         x[0] = make_float2(t.x, t.y);
@@ -181,15 +214,7 @@ __device__ __forceinline__ void fused_segment(const LossP &P, const ScaleP &S, c
     };
 
     const int niter = nrows + 2;
-    PRow2 win[3];  // win[d % 3] holds depth row row0 - 2 + d
-    float2 xa[2], xc[2];
-    load_plain(xa, row0 - 2);
-    load_plain(xc, row0 - 1);
-#pragma unroll
-    for (int k = 0; k < D; k++) {
-        if (k < niter) issue(k * SLB, k);
-        cp_async_commit();
-    }
+    PRow2 win[3];  // win[d % 3] holds depth row row0 - 2 + d; xa / xc and the first D ring rows come from fused_prologue
     fix_row(xa, row0 - 2);
     fix_row(xc, row0 - 1);
     prep_row2(win[0], xa);
@@ -309,8 +334,10 @@ __device__ __forceinline__ void fused_segment(const LossP &P, const ScaleP &S, c
     }
 }
 
+// 120 registers x 512 threads leave 4 K registers of the SM free: room for one 128-thread CTA of the (tiny) rescale
+// kernel that follows, so its programmatic dependent launch can become resident while this grid is still running.
 template <bool INV, bool SIG>
-__global__ void __launch_bounds__(kRThreads, 1) edge_loss_fused_kernel(const __grid_constant__ FusedP F) {
+__global__ void __maxnreg__(MTE_FUSED_REGS) edge_loss_fused_kernel(const __grid_constant__ FusedP F) {
     extern __shared__ __align__(16) unsigned char fusedRing[];
     __shared__ float4 sLut[16];  // per stash code (direction | 4 << sign): adjoint coefficients (A, C, A2, C2) for s = 1
     __shared__ double sLoss[MTE_MAX_SCALES];
@@ -330,6 +357,7 @@ __global__ void __launch_bounds__(kRThreads, 1) edge_loss_fused_kernel(const __g
     unsigned char *ring = fusedRing + warp * (fused_smem_bytes() / kRWarps);
     const int uBeg = (int)((long long)P.totalUnits * gw / nWarps);
     const int uEnd = (int)((long long)P.totalUnits * (gw + 1) / nWarps);
+    pdl_launch_dependents();   // the rescale kernel behind us may take its place on the SMs now (it waits for our end)
 
     // ---- phase 1: Wp_b = sum of the edge labels, every warp over the rows it owns (the lines stay in L2 for phase 2)
 #ifndef MTE_FUSED_TIMING_NO_PHASE1   // timing experiments only (results are wrong without it)
@@ -367,16 +395,26 @@ __global__ void __launch_bounds__(kRThreads, 1) edge_loss_fused_kernel(const __g
             }
         }
     }
+    // the first segment's opening loads go out before the barrier
+    int u0 = uBeg;
+    Seg sg;
+    bool have = false;
+    while (u0 < uEnd && !have) have = next_segment(P, u0, uEnd, sg);
+    float2 xa[2], xc[2];
+    if (have) fused_prologue(P.s[sg.si], sg, lane, ring, xa, xc);
     grid_barrier(F.barrier, gridDim.x);
 #else
     __syncthreads();
+    int u0 = uBeg;
+    Seg sg;
+    bool have = false;
+    while (u0 < uEnd && !have) have = next_segment(P, u0, uEnd, sg);
+    float2 xa[2], xc[2];
+    if (have) fused_prologue(P.s[sg.si], sg, lane, ring, xa, xc);
 #endif
 
     // ---- phase 2
-    int u0 = uBeg;
-    while (u0 < uEnd) {
-        Seg sg;
-        if (!next_segment(P, u0, uEnd, sg)) continue;
+    while (have) {
         const ScaleP &S = P.s[sg.si];
         // class balance and normaliser of this image, exactly as finalize_loss / the two-kernel backward form them
         const double npix = (double)S.H * (double)S.W;
@@ -398,7 +436,7 @@ __global__ void __launch_bounds__(kRThreads, 1) edge_loss_fused_kernel(const __g
         const float cp = -coef * P.p2n * alpha, cn = coef * (1.0f - alpha);
         float2 la[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
         float poison = 0.f;
-        fused_segment<INV, SIG>(P, S, sg, lane, ring, sLut, cp, cn, la, poison);
+        fused_segment<INV, SIG>(P, S, sg, lane, ring, sLut, cp, cn, la, poison, xa, xc);
         bool bad = __any_sync(MTE_FULL_MASK, !(poison == 0.f));
         unsigned long long *acc = P.accum + (size_t)(S.imgBase + sg.img) * kAcc;
         const float vp = warp_sum(la[0].x + la[0].y), vn = warp_sum(la[1].x + la[1].y);
@@ -408,6 +446,9 @@ __global__ void __launch_bounds__(kRThreads, 1) edge_loss_fused_kernel(const __g
             atomicAdd(acc + A_SNU, (unsigned long long)__double2ll_rn((double)vn * kFix));
             if (bad) atomicOr(acc + A_FLAGS, (unsigned long long)F_NONFINITE);
         }
+        have = false;
+        while (u0 < uEnd && !have) have = next_segment(P, u0, uEnd, sg);
+        if (have) fused_prologue(P.s[sg.si], sg, lane, ring, xa, xc);
     }
     // ---- the last CTA to leave folds alpha, the normalisers and the loss (same code as the two-kernel forward)
     __syncthreads();
@@ -439,8 +480,9 @@ __global__ void __launch_bounds__(kRThreads, 1) edge_loss_fused_kernel(const __g
 
 // d loss / d pred was produced for the expected upstream gradient; bring it to the actual one.  Exits at once when
 // they agree (the common case: loss.backward() with the expectation 1, or a steady training loop).
-__global__ void __launch_bounds__(256) edge_loss_rescale_kernel(const __grid_constant__ LossP P, const float *gradLoss,
+__global__ void __launch_bounds__(128) edge_loss_rescale_kernel(const __grid_constant__ LossP P, const float *gradLoss,
                                                                 float *ctx, float *expectedOut) {
+    pdl_wait();   // launched as a programmatic dependent of the kernel that produces ctx and grad_pred
     float *cur = ctx + P.totalImages + 2 * MTE_MAX_SCALES;
     unsigned *done = reinterpret_cast<unsigned *>(ctx + P.totalImages + 3 * MTE_MAX_SCALES);
     bool any = false;
@@ -591,8 +633,15 @@ extern "C" int mte_edge_loss_grad_rescale(const mte_loss_scale_t *sc, int n, con
         img += sc[i].B;
     }
     P.nScales = n; P.totalImages = img;
-    edge_loss_rescale_kernel<<<num_sms() * 2, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        P, grad_loss, static_cast<float *>(ctx), expected_out);
-    MTE_RETURN_IF_CUDA_ERROR();
-    return MTE_OK;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)num_sms() * 2u);
+    cfg.blockDim = dim3(128u);
+    cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, edge_loss_rescale_kernel, P, grad_loss, static_cast<float *>(ctx), expected_out);
+    return e == cudaSuccess ? MTE_OK : (int)e;
 }
