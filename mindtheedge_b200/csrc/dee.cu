@@ -13,6 +13,7 @@
 // Kernels:  dee_front_kernel  (Sobel5 + normals + NMS + hysteresis labels, shared-memory halo tile)
 //           canny::run_level_hysteresis (shared 8-connected union-find hysteresis)
 //           dee_finish_kernel (img * labels / max(labels), the reference's normalisation quirk included)
+#include <cuda.h>
 #include <math.h>
 #include <string.h>
 
@@ -237,6 +238,187 @@ __global__ void __launch_bounds__(kThreads) dee_front_kernel(const DeeTab *__res
     }
 }
 
+// ---------------------------------------------------------------------------
+// Front kernel, B200 form (fp32 input, W % 4 == 0, H, W >= 4): the halo tile arrives by ONE bulk-tensor copy (TMA,
+// cp.async.bulk.tensor.3d + mbarrier; out-of-image cells zero-filled by the copy engine and, on border tiles only,
+// patched with the REFLECT_101 values from inside the tile), and the separable Sobel runs out of a REGISTER window:
+// a thread owns one column, walks down the tile rows, computes the two fp64 row filters of a row from five shared
+// floats and keeps the last five results in registers for the column filter -- no fp64 round trip through shared
+// memory, no per-element index arithmetic.  Arithmetic (operation order of cv2.Sobel, quantisation, NMS, labels) is
+// the same as dee_front_kernel's; that kernel stays for fp64 inputs and odd shapes.
+// ---------------------------------------------------------------------------
+// The innermost box coordinate of a bulk-tensor copy must be 16-byte aligned (x0 - 2 traps with "illegal
+// instruction"; probed with scripts/ubench/tma_test.cu), so the box starts at x0 - 4 and is 8 columns wider than the tile.
+constexpr int XW = 128, XH = 31, XROWS = XH + 4, XPAD = 4, XCOLS = XW + 2 * XPAD, kXThreads = XW;   // 35 tile rows = 7 groups of 5
+static_assert(XROWS % 5 == 0, "the register window rotates with period 5");
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(kXThreads) dee_front_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                  const DeeTab *__restrict__ tab, int N, int H, int W,
+                                                                  int doNms, int doHyst, double tLow, double tHigh,
+                                                                  unsigned char *__restrict__ normals,
+                                                                  float *__restrict__ nmsOut, unsigned char *__restrict__ cl,
+                                                                  unsigned char *__restrict__ E, ImgStat *stats) {
+    __shared__ __align__(128) float tile[XROWS][XCOLS];
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ double2 sDir[256];
+    __shared__ unsigned char sZero[4];
+    const int tilesX = ceil_div(W, XW), tilesY = ceil_div(H, XH);
+    const int t = blockIdx.x % (tilesX * tilesY), im = blockIdx.x / (tilesX * tilesY);
+    const int x0 = (t % tilesX) * XW, y0 = (t / tilesX) * XH;
+    const unsigned bar = smem_u32(&mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)sizeof(tile)) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(smem_u32(&tile[0][0])), "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"(x0 - XPAD), "r"(y0 - 2), "r"(im),
+              "r"(bar)
+            : "memory");
+    }
+    if (normals) {  // overlaps the copy
+        sDir[threadIdx.x] = tab->dir[threadIdx.x];
+        sDir[threadIdx.x + 128] = tab->dir[threadIdx.x + 128];
+        if (threadIdx.x < 4) sZero[threadIdx.x] = tab->zero4[threadIdx.x];
+    }
+    {  // wait for the tile (phase 0)
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar) : "memory");
+    }
+    // border tiles: the zero-filled cells within two pixels of the image get their REFLECT_101 value, which lies
+    // inside this tile (in-image cells are never written, so one pass suffices)
+    if (x0 == 0 || y0 == 0 || x0 + XW + 2 > W || y0 + XH + 2 > H) {
+        for (int i = threadIdx.x; i < XROWS * XCOLS; i += kXThreads) {
+            const int r = i / XCOLS, c = i - r * XCOLS;
+            const int y = y0 - 2 + r, x = x0 - XPAD + c;
+            const bool out = y < 0 || y >= H || x < 0 || x >= W;
+            if (out && y >= -2 && y <= H + 1 && x >= -2 && x <= W + 1) {
+                const int yy = reflect101(y, H), xx = reflect101(x, W);
+                tile[r][c] = tile[yy - (y0 - 2)][xx - (x0 - XPAD)];
+            }
+        }
+    }
+    __syncthreads();
+
+    const int c = threadIdx.x, x = x0 + c;
+    const bool needSobel = (normals != nullptr) || doNms;
+    const bool colIn = x < W;
+    double wD[5], wS[5];   // row-filter results of the last five tile rows, slot = tile row % 5
+    bool anyStrong = false;
+#pragma unroll 1
+    for (int g = 0; g < XROWS / 5; g++) {
+#pragma unroll
+        for (int u = 0; u < 5; u++) {
+            const int k = g * 5 + u;   // tile row k = image row y0 - 2 + k
+            if (needSobel) {
+                const float *tr = &tile[k][c + XPAD - 2];   // columns x - 2 .. x + 2
+                const double a0 = (double)tr[0], a1 = (double)tr[1], a2 = (double)tr[2], a3 = (double)tr[3], a4 = (double)tr[4];
+                double d = __dmul_rn(-1.0, a0);
+                d = __dadd_rn(d, __dmul_rn(-2.0, a1));
+                d = __dadd_rn(d, __dmul_rn(0.0, a2));
+                d = __dadd_rn(d, __dmul_rn(2.0, a3));
+                d = __dadd_rn(d, __dmul_rn(1.0, a4));
+                double m = __dmul_rn(1.0, a0);
+                m = __dadd_rn(m, __dmul_rn(4.0, a1));
+                m = __dadd_rn(m, __dmul_rn(6.0, a2));
+                m = __dadd_rn(m, __dmul_rn(4.0, a3));
+                m = __dadd_rn(m, __dmul_rn(1.0, a4));
+                wD[u] = d;
+                wS[u] = m;
+            }
+            const int j = k - 4;           // output row of the tile, image row y0 + j
+            const int y = y0 + j;
+            if (j < 0 || y >= H || !colIn) continue;
+            const size_t o = (size_t)im * H * W + (size_t)y * W + x;
+            const int cr = j + 2, cc = c + XPAD;   // centre cell in the tile
+            const float v = tile[cr][cc];
+            double sx = 0.0, sy = 0.0;
+            if (needSobel) {
+                // rows j .. j+4 of the row filters sit in slots (u+1)%5 .. (u+5)%5
+                const double d0 = wD[(u + 1) % 5], d1 = wD[(u + 2) % 5], d2 = wD[(u + 3) % 5], d3 = wD[(u + 4) % 5], d4 = wD[u];
+                const double s0 = wS[(u + 1) % 5], s1 = wS[(u + 2) % 5], s3 = wS[(u + 4) % 5], s4 = wS[u];
+                sx = __dmul_rn(6.0, d2);
+                sx = __dadd_rn(sx, __dmul_rn(4.0, __dadd_rn(d3, d1)));
+                sx = __dadd_rn(sx, __dmul_rn(1.0, __dadd_rn(d4, d0)));
+                sy = __dmul_rn(2.0, __dsub_rn(s3, s1));
+                sy = __dadd_rn(sy, __dmul_rn(1.0, __dsub_rn(s4, s0)));
+            }
+            if (normals) {
+                const double X = sx, Y = -sy;
+                int lvl = -1;
+                if (X == 0.0 && Y == 0.0) {
+                    lvl = sZero[(int)(__double2hiint(sy) < 0) | ((int)(__double2hiint(sx) < 0) << 1)];
+                } else {
+                    const float a32 = atan2f((float)Y, (float)X);
+                    const int k0 = min(max((int)((a32 * 57.29577951f + 180.f) * (255.f / 360.f)), 0), 255);
+                    const double m = (fabs(X) + fabs(Y)) * 0x1p-44;
+                    bool ok = true;
+                    if (k0 >= 1) { const double2 d = sDir[k0]; ok = (Y * d.x - X * d.y) > m; }
+                    if (k0 <= 254) { const double2 d = sDir[k0 + 1]; ok = ok && (Y * d.x - X * d.y) < -m; }
+                    if (ok) lvl = k0;
+                }
+                if (lvl < 0) lvl = (int)normal_level_value(atan2(-sy, sx));
+                normals[o] = (unsigned char)lvl;
+            }
+            const bool interior = y >= 1 && y < H - 1 && x >= 1 && x < W - 1;
+            float keep = v;
+            if (doNms) {
+                keep = 0.f;
+                if (interior) {
+                    int bin = -1;
+                    {
+                        const double ax = fabs(sx), ay = fabs(sy);
+                        const double t1 = ax * 0.41421356237309503, t2 = ax * 2.4142135623730951;
+                        constexpr double lo = 1.0 - 0x1p-40, hi = 1.0 + 0x1p-40;
+                        if (ax == 0.0 && ay == 0.0) bin = 0;
+                        else if (ay < t1 * lo) bin = 0;
+                        else if (ay > t1 * hi && ay < t2 * lo) bin = ((sx < 0.0) != (sy < 0.0)) ? 3 : 1;
+                        else if (ay > t2 * hi) bin = 2;
+                    }
+                    if (bin < 0) {
+                        double a = __dmul_rn(atan2(sy, sx), 180.0 / M_PI);
+                        if (a < 0.0) a = __dadd_rn(a, 180.0);
+                        bin = 4;
+                        if ((0.0 <= a && a < 22.5) || (157.5 <= a && a <= 180.0)) bin = 0;
+                        else if (22.5 <= a && a < 67.5) bin = 1;
+                        else if (67.5 <= a && a < 112.5) bin = 2;
+                        else if (112.5 <= a && a < 157.5) bin = 3;
+                    }
+                    float q = 1.f, rr = 1.f;
+                    if (bin == 0) { q = tile[cr][cc + 1]; rr = tile[cr][cc - 1]; }
+                    else if (bin == 1) { q = tile[cr - 1][cc - 1]; rr = tile[cr + 1][cc + 1]; }
+                    else if (bin == 2) { q = tile[cr + 1][cc]; rr = tile[cr - 1][cc]; }
+                    else if (bin == 3) { q = tile[cr + 1][cc - 1]; rr = tile[cr - 1][cc + 1]; }
+                    if (v >= q && v >= rr) keep = v;
+                }
+            }
+            if (nmsOut) nmsOut[o] = keep;
+            if (doHyst) {
+                unsigned char c_l = 255, e_l = 255;
+                const double kv = (double)keep;
+                if (interior) {
+                    if (kv > tHigh) { c_l = 0; e_l = 0; }
+                    else if (!(kv < tLow)) c_l = 0;
+                    anyStrong = anyStrong || e_l == 0;
+                } else {
+                    if (kv != kv) atomicOr(&stats[im].borderNaN, 1u);
+                    else atomicMax(&stats[im].borderMaxKey, dkey(kv));
+                }
+                cl[o] = c_l;
+                E[o] = e_l;
+            }
+        }
+    }
+    if (doHyst && __syncthreads_or(anyStrong ? 1 : 0) && threadIdx.x == 0) atomicOr(&stats[im].anyStrong, 1u);
+}
+
 // out = img * (labels / max(labels))  in the dtype the reference computes in (C = float or double)
 template <typename T, typename C, typename O>
 __global__ void dee_finish_kernel(const T *__restrict__ val, const unsigned char *__restrict__ E, int N, int H, int W,
@@ -269,6 +451,36 @@ __global__ void dee_convert_kernel(const T *__restrict__ in, O *__restrict__ out
 struct Layout {
     size_t offStats, offTab, offVal, offCl, offE, offActive, total;
 };
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libmte.so does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        cudaGetLastError();
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// [N, H, W] fp32 planes as a 3-D tensor map with a (XCOLS, XROWS, 1) box; out-of-bounds cells read as zero
+static bool make_plane_map(CUtensorMap &m, const float *base, int N, int H, int W) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || (W % 4) || H < 4 || W < 4 || (reinterpret_cast<uintptr_t>(base) & 15u)) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)XCOLS, (cuuint32_t)XROWS, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 static Layout layout(int N, int H, int W) {
     Layout L;
@@ -304,8 +516,19 @@ static int run(const T *prob, int N, int H, int W, int do_nms, int do_hyst, doub
         nmsDst = static_cast<T *>(out);
     DeeTab *tab = reinterpret_cast<DeeTab *>(ws + L.offTab);
     if (normals) dee_tables_kernel<<<1, 256, 0, st>>>(tab);  // 255 bisections, a few microseconds, no host state
-    dee_front_kernel<T><<<tiles, kThreads, 0, st>>>(tab, prob, N, H, W, do_nms, do_hyst && wantVal, lo, hi, normals,
-                                                    nmsDst, cl, E, stats);
+    bool tma = false;
+    if constexpr (sizeof(T) == 4) {
+        CUtensorMap map;
+        if (!debug_knob("MTE_DEE_NO_TMA") && make_plane_map(map, reinterpret_cast<const float *>(prob), N, H, W)) {
+            const int xt = ceil_div(W, XW) * ceil_div(H, XH) * N;
+            dee_front_tma_kernel<<<xt, kXThreads, 0, st>>>(map, tab, N, H, W, do_nms, do_hyst && wantVal, lo, hi, normals,
+                                                          reinterpret_cast<float *>(nmsDst), cl, E, stats);
+            tma = true;
+        }
+    }
+    if (!tma)
+        dee_front_kernel<T><<<tiles, kThreads, 0, st>>>(tab, prob, N, H, W, do_nms, do_hyst && wantVal, lo, hi, normals,
+                                                        nmsDst, cl, E, stats);
     MTE_RETURN_IF_CUDA_ERROR();
     if (!wantVal) return MTE_OK;
     const size_t n = (size_t)N * H * W;
