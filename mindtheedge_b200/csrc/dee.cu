@@ -254,9 +254,30 @@ static_assert(XROWS % 5 == 0, "the register window rotates with period 5");
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+// Branch-free fp32 atan2 (octant reduction + odd minimax polynomial, |error| < ~1e-5 rad): only a CANDIDATE for the
+// exact fp64 decisions below, which fall back to the double atan2 when the candidate cannot be proved.
+__device__ __forceinline__ float atan2_candidate(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float t = __fdividef(mn, mx);
+    const float t2 = t * t;
+    float p = fmaf(t2, -0.0117212f, 0.05265332f);
+    p = fmaf(p, t2, -0.11643287f);
+    p = fmaf(p, t2, 0.19354346f);
+    p = fmaf(p, t2, -0.33262347f);
+    p = fmaf(p, t2, 0.99997726f);
+    // fmaxf / fminf drop a NaN operand: x * 0 + y * 0 carries a NaN (or an Inf, as NaN) into the result, so that
+    // the exact decisions see a candidate they cannot prove and take the reference's own expression
+    p = fmaf(p, t, fmaf(x, 0.f, y * 0.f));
+    p = ay > ax ? 1.57079637f - p : p;
+    p = x < 0.f ? 3.14159274f - p : p;
+    return y < 0.f ? -p : p;
+}
+
+template <bool NRM, bool NMS, bool HYST>
 __global__ void __launch_bounds__(kXThreads) dee_front_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                   const DeeTab *__restrict__ tab, int N, int H, int W,
-                                                                  int doNms, int doHyst, double tLow, double tHigh,
+                                                                  double tLow, double tHigh,
                                                                   unsigned char *__restrict__ normals,
                                                                   float *__restrict__ nmsOut, unsigned char *__restrict__ cl,
                                                                   unsigned char *__restrict__ E, ImgStat *stats) {
@@ -281,7 +302,7 @@ __global__ void __launch_bounds__(kXThreads) dee_front_tma_kernel(const __grid_c
               "r"(bar)
             : "memory");
     }
-    if (normals) {  // overlaps the copy
+    if (NRM) {  // overlaps the copy
         sDir[threadIdx.x] = tab->dir[threadIdx.x];
         sDir[threadIdx.x + 128] = tab->dir[threadIdx.x + 128];
         if (threadIdx.x < 4) sZero[threadIdx.x] = tab->zero4[threadIdx.x];
@@ -308,115 +329,130 @@ __global__ void __launch_bounds__(kXThreads) dee_front_tma_kernel(const __grid_c
     __syncthreads();
 
     const int c = threadIdx.x, x = x0 + c;
-    const bool needSobel = (normals != nullptr) || doNms;
+    constexpr bool SOBEL = NRM || NMS;
     const bool colIn = x < W;
+    const bool xInterior = x >= 1 && x < W - 1;
+    const int jEnd = min(XH, H - y0);   // output rows of this tile
     double wD[5], wS[5];   // row-filter results of the last five tile rows, slot = tile row % 5
     bool anyStrong = false;
+    size_t o = (size_t)im * H * W + (size_t)y0 * W + x;   // advances by W per output row
 #pragma unroll 1
     for (int g = 0; g < XROWS / 5; g++) {
 #pragma unroll
         for (int u = 0; u < 5; u++) {
             const int k = g * 5 + u;   // tile row k = image row y0 - 2 + k
-            if (needSobel) {
+            if (SOBEL) {
                 const float *tr = &tile[k][c + XPAD - 2];   // columns x - 2 .. x + 2
                 const double a0 = (double)tr[0], a1 = (double)tr[1], a2 = (double)tr[2], a3 = (double)tr[3], a4 = (double)tr[4];
-                double d = __dmul_rn(-1.0, a0);
+                // cv2.Sobel's row pass, tap by tap (x * 1.0 and x * -1.0 are exact: written as x and -x)
+                double d = -a0;
                 d = __dadd_rn(d, __dmul_rn(-2.0, a1));
                 d = __dadd_rn(d, __dmul_rn(0.0, a2));
                 d = __dadd_rn(d, __dmul_rn(2.0, a3));
-                d = __dadd_rn(d, __dmul_rn(1.0, a4));
-                double m = __dmul_rn(1.0, a0);
+                d = __dadd_rn(d, a4);
+                double m = a0;
                 m = __dadd_rn(m, __dmul_rn(4.0, a1));
                 m = __dadd_rn(m, __dmul_rn(6.0, a2));
                 m = __dadd_rn(m, __dmul_rn(4.0, a3));
-                m = __dadd_rn(m, __dmul_rn(1.0, a4));
+                m = __dadd_rn(m, a4);
                 wD[u] = d;
                 wS[u] = m;
             }
             const int j = k - 4;           // output row of the tile, image row y0 + j
-            const int y = y0 + j;
-            if (j < 0 || y >= H || !colIn) continue;
-            const size_t o = (size_t)im * H * W + (size_t)y * W + x;
-            const int cr = j + 2, cc = c + XPAD;   // centre cell in the tile
-            const float v = tile[cr][cc];
-            double sx = 0.0, sy = 0.0;
-            if (needSobel) {
-                // rows j .. j+4 of the row filters sit in slots (u+1)%5 .. (u+5)%5
-                const double d0 = wD[(u + 1) % 5], d1 = wD[(u + 2) % 5], d2 = wD[(u + 3) % 5], d3 = wD[(u + 4) % 5], d4 = wD[u];
-                const double s0 = wS[(u + 1) % 5], s1 = wS[(u + 2) % 5], s3 = wS[(u + 4) % 5], s4 = wS[u];
-                sx = __dmul_rn(6.0, d2);
-                sx = __dadd_rn(sx, __dmul_rn(4.0, __dadd_rn(d3, d1)));
-                sx = __dadd_rn(sx, __dmul_rn(1.0, __dadd_rn(d4, d0)));
-                sy = __dmul_rn(2.0, __dsub_rn(s3, s1));
-                sy = __dadd_rn(sy, __dmul_rn(1.0, __dsub_rn(s4, s0)));
-            }
-            if (normals) {
-                const double X = sx, Y = -sy;
-                int lvl = -1;
-                if (X == 0.0 && Y == 0.0) {
-                    lvl = sZero[(int)(__double2hiint(sy) < 0) | ((int)(__double2hiint(sx) < 0) << 1)];
-                } else {
-                    const float a32 = atan2f((float)Y, (float)X);
+            if (j >= 0 && j < jEnd && colIn) {
+                const int y = y0 + j;
+                const int cr = j + 2, cc = c + XPAD;   // centre cell in the tile
+                const float v = tile[cr][cc];
+                double sx = 0.0, sy = 0.0;
+                float a32 = 0.f;
+                if (SOBEL) {
+                    // rows j .. j+4 of the row filters sit in slots (u+1)%5 .. (u+5)%5
+                    const double d0 = wD[(u + 1) % 5], d1 = wD[(u + 2) % 5], d2 = wD[(u + 3) % 5], d3 = wD[(u + 4) % 5], d4 = wD[u];
+                    const double s0 = wS[(u + 1) % 5], s1 = wS[(u + 2) % 5], s3 = wS[(u + 4) % 5], s4 = wS[u];
+                    sx = __dmul_rn(6.0, d2);
+                    sx = __dadd_rn(sx, __dmul_rn(4.0, __dadd_rn(d3, d1)));
+                    sx = __dadd_rn(sx, __dadd_rn(d4, d0));
+                    sy = __dmul_rn(2.0, __dsub_rn(s3, s1));
+                    sy = __dadd_rn(sy, __dsub_rn(s4, s0));
+                    a32 = atan2_candidate((float)-sy, (float)sx);   // angle of the normal, atan2(-sy, sx)
+                }
+                const bool zero = sx == 0.0 && sy == 0.0;
+                if (NRM) {
+                    const double X = sx, Y = -sy;
                     const int k0 = min(max((int)((a32 * 57.29577951f + 180.f) * (255.f / 360.f)), 0), 255);
                     const double m = (fabs(X) + fabs(Y)) * 0x1p-44;
-                    bool ok = true;
-                    if (k0 >= 1) { const double2 d = sDir[k0]; ok = (Y * d.x - X * d.y) > m; }
-                    if (k0 <= 254) { const double2 d = sDir[k0 + 1]; ok = ok && (Y * d.x - X * d.y) < -m; }
-                    if (ok) lvl = k0;
+                    const double2 dl = sDir[max(k0, 1)], dh = sDir[min(k0 + 1, 255)];
+                    const bool okLo = k0 < 1 || (Y * dl.x - X * dl.y) > m;       // theta_k0 < A
+                    const bool okHi = k0 > 254 || (Y * dh.x - X * dh.y) < -m;    // A < theta_k0+1
+                    int lvl = k0;
+                    if (zero) lvl = sZero[(int)(__double2hiint(sy) < 0) | ((int)(__double2hiint(sx) < 0) << 1)];
+                    else if (!(okLo && okHi)) lvl = (int)normal_level_value(atan2(-sy, sx));  // guard band, NaN / Inf
+                    normals[o] = (unsigned char)lvl;
                 }
-                if (lvl < 0) lvl = (int)normal_level_value(atan2(-sy, sx));
-                normals[o] = (unsigned char)lvl;
-            }
-            const bool interior = y >= 1 && y < H - 1 && x >= 1 && x < W - 1;
-            float keep = v;
-            if (doNms) {
-                keep = 0.f;
-                if (interior) {
-                    int bin = -1;
-                    {
-                        const double ax = fabs(sx), ay = fabs(sy);
-                        const double t1 = ax * 0.41421356237309503, t2 = ax * 2.4142135623730951;
-                        constexpr double lo = 1.0 - 0x1p-40, hi = 1.0 + 0x1p-40;
-                        if (ax == 0.0 && ay == 0.0) bin = 0;
-                        else if (ay < t1 * lo) bin = 0;
-                        else if (ay > t1 * hi && ay < t2 * lo) bin = ((sx < 0.0) != (sy < 0.0)) ? 3 : 1;
-                        else if (ay > t2 * hi) bin = 2;
+                const bool interior = xInterior && y >= 1 && y < H - 1;
+                float keep = v;
+                if (NMS) {
+                    keep = 0.f;
+                    if (interior) {
+                        // bin of atan2(sy, sx) = -a32 folded to [0, pi): 0 = [0, 22.5) u [157.5, 180], 1 = [22.5, 67.5),
+                        // 2 = [67.5, 112.5), 3 = [112.5, 157.5), 4 = none.  The fp32 candidate decides when it is at least
+                        // 1e-4 of an octant (4e-5 rad, four times its error) away from every boundary.
+                        const float an = -a32;
+                        const float am = (an < 0.f ? an + 3.14159274f : an) * 2.54647899f;   // in units of pi / 8
+                        const int idx = (int)am;
+                        const float fr = am - (float)idx;
+                        int bin = ((idx + 1) >> 1) & 3;
+                        if (zero) bin = 0;   // atan2(+-0, +-0) is 0 or +-pi: bin 0 either way
+                        // bin boundaries are the ODD multiples of pi / 8 only (0, 45, 90, 135 deg -- axis-aligned and
+                        // diagonal gradients, which are common -- lie in the middle of a bin)
+                        else if (!((idx & 1) ? fr >= 1e-4f : fr <= 1.f - 1e-4f) || idx < 0 || idx > 8) {
+                            // near a boundary (or NaN / Inf): |sy| against |sx| tan(22.5 / 67.5 deg) in fp64 with a 2^-40
+                            // guard band, and inside that band the reference's own expression
+                            const double ax = fabs(sx), ay = fabs(sy);
+                            const double t1 = ax * 0.41421356237309503, t2 = ax * 2.4142135623730951;
+                            constexpr double lo = 1.0 - 0x1p-40, hi = 1.0 + 0x1p-40;
+                            bin = -1;
+                            if (ay < t1 * lo) bin = 0;
+                            else if (ay > t1 * hi && ay < t2 * lo) bin = ((sx < 0.0) != (sy < 0.0)) ? 3 : 1;
+                            else if (ay > t2 * hi) bin = 2;
+                            if (bin < 0) {
+                                double a = __dmul_rn(atan2(sy, sx), 180.0 / M_PI);
+                                if (a < 0.0) a = __dadd_rn(a, 180.0);
+                                bin = 4;
+                                if ((0.0 <= a && a < 22.5) || (157.5 <= a && a <= 180.0)) bin = 0;
+                                else if (22.5 <= a && a < 67.5) bin = 1;
+                                else if (67.5 <= a && a < 112.5) bin = 2;
+                                else if (112.5 <= a && a < 157.5) bin = 3;
+                            }
+                        }
+                        // neighbours (q, r): bin 0 (E, W), 1 (NW, SE), 2 (S, N), 3 (SW, NE); no bin -> 1 (tools.py:22-23)
+                        const int dy = bin == 0 ? 0 : (bin == 1 ? -1 : 1);
+                        const int dx = bin == 0 ? 1 : (bin == 2 ? 0 : -1);
+                        float q = tile[cr + dy][cc + dx], rr = tile[cr - dy][cc - dx];
+                        if (bin == 4) { q = 1.f; rr = 1.f; }
+                        if (v >= q && v >= rr) keep = v;
                     }
-                    if (bin < 0) {
-                        double a = __dmul_rn(atan2(sy, sx), 180.0 / M_PI);
-                        if (a < 0.0) a = __dadd_rn(a, 180.0);
-                        bin = 4;
-                        if ((0.0 <= a && a < 22.5) || (157.5 <= a && a <= 180.0)) bin = 0;
-                        else if (22.5 <= a && a < 67.5) bin = 1;
-                        else if (67.5 <= a && a < 112.5) bin = 2;
-                        else if (112.5 <= a && a < 157.5) bin = 3;
+                }
+                if (nmsOut) nmsOut[o] = keep;
+                if (HYST) {
+                    unsigned char c_l = 255, e_l = 255;
+                    const double kv = (double)keep;
+                    if (interior) {
+                        if (kv > tHigh) { c_l = 0; e_l = 0; }
+                        else if (!(kv < tLow)) c_l = 0;
+                        anyStrong = anyStrong || e_l == 0;
+                    } else {
+                        if (kv != kv) atomicOr(&stats[im].borderNaN, 1u);
+                        else atomicMax(&stats[im].borderMaxKey, dkey(kv));
                     }
-                    float q = 1.f, rr = 1.f;
-                    if (bin == 0) { q = tile[cr][cc + 1]; rr = tile[cr][cc - 1]; }
-                    else if (bin == 1) { q = tile[cr - 1][cc - 1]; rr = tile[cr + 1][cc + 1]; }
-                    else if (bin == 2) { q = tile[cr + 1][cc]; rr = tile[cr - 1][cc]; }
-                    else if (bin == 3) { q = tile[cr + 1][cc - 1]; rr = tile[cr - 1][cc + 1]; }
-                    if (v >= q && v >= rr) keep = v;
+                    cl[o] = c_l;
+                    E[o] = e_l;
                 }
-            }
-            if (nmsOut) nmsOut[o] = keep;
-            if (doHyst) {
-                unsigned char c_l = 255, e_l = 255;
-                const double kv = (double)keep;
-                if (interior) {
-                    if (kv > tHigh) { c_l = 0; e_l = 0; }
-                    else if (!(kv < tLow)) c_l = 0;
-                    anyStrong = anyStrong || e_l == 0;
-                } else {
-                    if (kv != kv) atomicOr(&stats[im].borderNaN, 1u);
-                    else atomicMax(&stats[im].borderMaxKey, dkey(kv));
-                }
-                cl[o] = c_l;
-                E[o] = e_l;
+                o += (size_t)W;
             }
         }
     }
-    if (doHyst && __syncthreads_or(anyStrong ? 1 : 0) && threadIdx.x == 0) atomicOr(&stats[im].anyStrong, 1u);
+    if (HYST && __syncthreads_or(anyStrong ? 1 : 0) && threadIdx.x == 0) atomicOr(&stats[im].anyStrong, 1u);
 }
 
 // out = img * (labels / max(labels))  in the dtype the reference computes in (C = float or double)
@@ -521,8 +557,18 @@ static int run(const T *prob, int N, int H, int W, int do_nms, int do_hyst, doub
         CUtensorMap map;
         if (!debug_knob("MTE_DEE_NO_TMA") && make_plane_map(map, reinterpret_cast<const float *>(prob), N, H, W)) {
             const int xt = ceil_div(W, XW) * ceil_div(H, XH) * N;
-            dee_front_tma_kernel<<<xt, kXThreads, 0, st>>>(map, tab, N, H, W, do_nms, do_hyst && wantVal, lo, hi, normals,
-                                                          reinterpret_cast<float *>(nmsDst), cl, E, stats);
+            const bool nr = normals != nullptr, nm = do_nms != 0, hy = do_hyst && wantVal;
+            float *dst = reinterpret_cast<float *>(nmsDst);
+#define MTE_DEE_LAUNCH(A, B, C) dee_front_tma_kernel<A, B, C><<<xt, kXThreads, 0, st>>>(map, tab, N, H, W, lo, hi, normals, dst, cl, E, stats)
+            if (nr && nm && hy) MTE_DEE_LAUNCH(true, true, true);
+            else if (nr && nm) MTE_DEE_LAUNCH(true, true, false);
+            else if (nr && hy) MTE_DEE_LAUNCH(true, false, true);
+            else if (nr) MTE_DEE_LAUNCH(true, false, false);
+            else if (nm && hy) MTE_DEE_LAUNCH(false, true, true);
+            else if (nm) MTE_DEE_LAUNCH(false, true, false);
+            else if (hy) MTE_DEE_LAUNCH(false, false, true);
+            else MTE_DEE_LAUNCH(false, false, false);
+#undef MTE_DEE_LAUNCH
             tma = true;
         }
     }
