@@ -455,27 +455,53 @@ __global__ void __launch_bounds__(kXThreads) dee_front_tma_kernel(const __grid_c
     if (HYST && __syncthreads_or(anyStrong ? 1 : 0) && threadIdx.x == 0) atomicOr(&stats[im].anyStrong, 1u);
 }
 
-// out = img * (labels / max(labels))  in the dtype the reference computes in (C = float or double)
+// out = img * (labels / max(labels))  in the dtype the reference computes in (C = float or double).  One image per
+// blockIdx.y, four consecutive pixels per thread; labels / max takes only two values inside the image (2 / max at kept
+// pixels, 0 / max elsewhere), computed once per thread with the same division the reference does per pixel -- only the
+// one-pixel border (label = the raw value) divides per pixel.
 template <typename T, typename C, typename O>
-__global__ void dee_finish_kernel(const T *__restrict__ val, const unsigned char *__restrict__ E, int N, int H, int W,
-                                  const ImgStat *__restrict__ stats, O *__restrict__ out) {
-    const size_t plane = (size_t)H * W, n = plane * N;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const int im = (int)(i / plane);
-        const size_t j = i - (size_t)im * plane;
-        const int y = (int)(j / W), x = (int)(j - (size_t)y * W);
-        const ImgStat st = stats[im];
-        // np.max over {0, 2 at kept pixels, raw border values}; NaN wins
-        double mx = (H > 2 && W > 2) ? 0.0 : -INFINITY;
-        if (st.anyStrong) mx = 2.0;
-        if (st.borderMaxKey != 0ull) { const double b = dkey_inv(st.borderMaxKey); mx = b > mx ? b : mx; }
-        if (st.borderNaN) mx = NAN;
-        const bool interior = y >= 1 && y < H - 1 && x >= 1 && x < W - 1;
-        const C v = (C)val[i];
-        const C label = interior ? (E[i] == 0 ? (C)2 : (C)0) : v;
-        const C norm = label / (C)mx;
-        out[i] = (O)(v * norm);
+__global__ void __launch_bounds__(256) dee_finish_kernel(const T *__restrict__ val, const unsigned char *__restrict__ E,
+                                                         int N, int H, int W, const ImgStat *__restrict__ stats,
+                                                         O *__restrict__ out) {
+    const int im = blockIdx.y;
+    const int plane = H * W;
+    const ImgStat st = stats[im];
+    // np.max over {0, 2 at kept pixels, raw border values}; NaN wins
+    double mx = (H > 2 && W > 2) ? 0.0 : -INFINITY;
+    if (st.anyStrong) mx = 2.0;
+    if (st.borderMaxKey != 0ull) { const double b = dkey_inv(st.borderMaxKey); mx = b > mx ? b : mx; }
+    if (st.borderNaN) mx = NAN;
+    const C cm = (C)mx;
+    const C n2 = (C)2 / cm, n0 = (C)0 / cm;
+    const size_t base = (size_t)im * plane;
+    const int j0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (j0 >= plane) return;
+    int y = j0 / W, x = j0 - y * W;
+    const int cnt = min(4, plane - j0);
+    T v[4];
+    unsigned char e[4];
+    const bool vec = cnt == 4 && ((base + j0) & 3) == 0 && (reinterpret_cast<uintptr_t>(val) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(E) & 3) == 0 && sizeof(T) == 4;
+    if (vec) {
+        const float4 t = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(val) + base + j0);
+        v[0] = (T)t.x; v[1] = (T)t.y; v[2] = (T)t.z; v[3] = (T)t.w;
+        const uchar4 u = *reinterpret_cast<const uchar4 *>(E + base + j0);
+        e[0] = u.x; e[1] = u.y; e[2] = u.z; e[3] = u.w;
+    } else {
+        for (int k = 0; k < cnt; k++) { v[k] = val[base + j0 + k]; e[k] = E[base + j0 + k]; }
     }
+    O r[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (k < cnt) {
+            const bool interior = y >= 1 && y < H - 1 && x >= 1 && x < W - 1;
+            const C cv = (C)v[k];
+            const C norm = interior ? (e[k] == 0 ? n2 : n0) : cv / cm;
+            r[k] = (O)(cv * norm);
+            if (++x == W) { x = 0; y++; }
+        }
+    }
+    for (int k = 0; k < cnt; k++) out[base + j0 + k] = r[k];
 }
 
 template <typename T, typename O>
@@ -584,12 +610,13 @@ static int run(const T *prob, int N, int H, int W, int do_nms, int do_hyst, doub
         if (rc) return rc;
         // the reference computes in float64 once NMS has run (its output array is float64), else in the input type
         const bool c64 = do_nms || sizeof(T) == 8;
+        const dim3 fg((unsigned)ceil_div(H * W, 1024), (unsigned)N);
         if (out_dtype == MTE_F64) {
-            if (c64) dee_finish_kernel<T, double, double><<<grid, 256, 0, st>>>(val, E, N, H, W, stats, (double *)out);
-            else dee_finish_kernel<T, float, double><<<grid, 256, 0, st>>>(val, E, N, H, W, stats, (double *)out);
+            if (c64) dee_finish_kernel<T, double, double><<<fg, 256, 0, st>>>(val, E, N, H, W, stats, (double *)out);
+            else dee_finish_kernel<T, float, double><<<fg, 256, 0, st>>>(val, E, N, H, W, stats, (double *)out);
         } else {
-            if (c64) dee_finish_kernel<T, double, float><<<grid, 256, 0, st>>>(val, E, N, H, W, stats, (float *)out);
-            else dee_finish_kernel<T, float, float><<<grid, 256, 0, st>>>(val, E, N, H, W, stats, (float *)out);
+            if (c64) dee_finish_kernel<T, double, float><<<fg, 256, 0, st>>>(val, E, N, H, W, stats, (float *)out);
+            else dee_finish_kernel<T, float, float><<<fg, 256, 0, st>>>(val, E, N, H, W, stats, (float *)out);
         }
         MTE_RETURN_IF_CUDA_ERROR();
     } else if (nmsDst == val) {
