@@ -254,12 +254,15 @@ static_assert(XROWS % 5 == 0, "the register window rotates with period 5");
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-// Branch-free fp32 atan2 (octant reduction + odd minimax polynomial, |error| < ~1e-5 rad): only a CANDIDATE for the
-// exact fp64 decisions below, which fall back to the double atan2 when the candidate cannot be proved.
+// Branch-free fp32 atan2 (octant reduction + odd minimax polynomial; |error| < 3e-6 rad for components in [1e-30, 1e30],
+// tests/test_host_cpu.py::test_atan2_candidate_error_bound): only a CANDIDATE; the exact fp64 decisions take over
+// whenever it lies too close to a boundary to decide.
 __device__ __forceinline__ float atan2_candidate(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    const float t = __fdividef(mn, mx);
+    float rc;   // the caller discards candidates whose larger component is outside [1e-30, 1e30]: no denormal handling
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(mx));
+    const float t = mn * rc;
     const float t2 = t * t;
     float p = fmaf(t2, -0.0117212f, 0.05265332f);
     p = fmaf(p, t2, -0.11643287f);
@@ -274,8 +277,53 @@ __device__ __forceinline__ float atan2_candidate(float y, float x) {
     return y < 0.f ? -p : p;
 }
 
+// The exact decisions of the pixels whose fp32 candidate is too close to a boundary (or is NaN: zero gradient, NaN /
+// Inf, values outside the fast division's range).  Rare, so they are real calls: ten inlined copies of the double
+// atan2 made the row loop 60 KB of code.
+__device__ __noinline__ int dee_level_exact(double sx, double sy, int k0, const double2 *sDir, const unsigned char *sZero) {
+    if (sx == 0.0 && sy == 0.0) return sZero[(int)(__double2hiint(sy) < 0) | ((int)(__double2hiint(sx) < 0) << 1)];
+    const double X = sx, Y = -sy;
+    const int kc = min(max(k0, 0), 255);
+    const double m = (fabs(X) + fabs(Y)) * 0x1p-44;
+    // k0 >= 0: a valid candidate (within 1.2e-4 levels of the truth), possibly one level off next to a threshold:
+    // try kc, kc - 1, kc + 1.  Two fp64 cross products against the neighbouring threshold DIRECTIONS prove a level
+    // (sin(A - theta) = (Y cos theta - X sin theta) / r) -- ONLY for an angle known to lie near theta: the sign of a
+    // sine says nothing half a turn away, so without a candidate (k0 < 0) the reference's expression decides.
+    for (int t = 0; t < 3 && k0 >= 0; t++) {
+        const int kk = kc + (t == 0 ? 0 : (t == 1 ? -1 : 1));
+        if (kk < 0 || kk > 255) continue;
+        const double2 dl = sDir[max(kk, 1)], dh = sDir[min(kk + 1, 255)];
+        const bool okLo = kk < 1 || (Y * dl.x - X * dl.y) > m;       // theta_kk < A
+        const bool okHi = kk > 254 || (Y * dh.x - X * dh.y) < -m;    // A < theta_kk+1
+        if (okLo && okHi) return kk;
+    }
+    return (int)normal_level_value(atan2(-sy, sx));  // inside a 2^-44 guard band, NaN / Inf: the reference's expression
+}
+
+__device__ __noinline__ int dee_bin_exact(double sx, double sy) {
+    // |sy| against |sx| tan(22.5 / 67.5 deg) in fp64 with a 2^-40 guard band, and inside that band the reference's own
+    // expression (tools.py:12-17, 24-38)
+    const double ax = fabs(sx), ay = fabs(sy);
+    const double t1 = ax * 0.41421356237309503, t2 = ax * 2.4142135623730951;
+    constexpr double lo = 1.0 - 0x1p-40, hi = 1.0 + 0x1p-40;
+    if (ax == 0.0 && ay == 0.0) return 0;   // atan2(+-0, +-0) is 0 or +-pi: bin 0 either way
+    if (ay < t1 * lo) return 0;
+    if (ay > t1 * hi && ay < t2 * lo) return ((sx < 0.0) != (sy < 0.0)) ? 3 : 1;
+    if (ay > t2 * hi) return 2;
+    double a = __dmul_rn(atan2(sy, sx), 180.0 / M_PI);
+    if (a < 0.0) a = __dadd_rn(a, 180.0);
+    if ((0.0 <= a && a < 22.5) || (157.5 <= a && a <= 180.0)) return 0;
+    if (22.5 <= a && a < 67.5) return 1;
+    if (67.5 <= a && a < 112.5) return 2;
+    if (112.5 <= a && a < 157.5) return 3;
+    return 4;
+}
+
+#ifndef MTE_DEE_MINB
+#define MTE_DEE_MINB 5
+#endif
 template <bool NRM, bool NMS, bool HYST>
-__global__ void __launch_bounds__(kXThreads) dee_front_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(kXThreads, MTE_DEE_MINB) dee_front_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                   const DeeTab *__restrict__ tab, int N, int H, int W,
                                                                   double tLow, double tHigh,
                                                                   unsigned char *__restrict__ normals,
@@ -333,122 +381,129 @@ __global__ void __launch_bounds__(kXThreads) dee_front_tma_kernel(const __grid_c
     const bool colIn = x < W;
     const bool xInterior = x >= 1 && x < W - 1;
     const int jEnd = min(XH, H - y0);   // output rows of this tile
+    // the hysteresis labels compare an fp32 value with fp64 thresholds: keep > tHigh <=> keep > (largest float <=
+    // tHigh), keep < tLow <=> keep < (smallest float >= tLow) -- exact for every threshold incl. +-Inf / NaN
+    const float thF = __double2float_rd(tHigh), tlF = __double2float_ru(tLow);
     double wD[5], wS[5];   // row-filter results of the last five tile rows, slot = tile row % 5
+    float f[5][3];         // the fp32 values at columns x - 1, x, x + 1 of the same rows (NMS neighbours, centre value)
     bool anyStrong = false;
-    size_t o = (size_t)im * H * W + (size_t)y0 * W + x;   // advances by W per output row
+    const size_t o0 = (size_t)im * H * W + (size_t)y0 * W + x;
+    unsigned char *nrmP = NRM ? normals + o0 : nullptr;     // running pointers: advance by W per output row
+    float *nmsP = nmsOut ? nmsOut + o0 : nullptr;
+    unsigned char *clP = HYST ? cl + o0 : nullptr, *eP = HYST ? E + o0 : nullptr;
+    const float *tr = &tile[0][c + XPAD - 2];               // columns x - 2 .. x + 2 of the current tile row
 #pragma unroll 1
     for (int g = 0; g < XROWS / 5; g++) {
 #pragma unroll
-        for (int u = 0; u < 5; u++) {
+        for (int u = 0; u < 5; u++, tr += XCOLS) {
             const int k = g * 5 + u;   // tile row k = image row y0 - 2 + k
-            if (SOBEL) {
-                const float *tr = &tile[k][c + XPAD - 2];   // columns x - 2 .. x + 2
-                const double a0 = (double)tr[0], a1 = (double)tr[1], a2 = (double)tr[2], a3 = (double)tr[3], a4 = (double)tr[4];
-                // cv2.Sobel's row pass, tap by tap (x * 1.0 and x * -1.0 are exact: written as x and -x)
-                double d = -a0;
-                d = __dadd_rn(d, __dmul_rn(-2.0, a1));
-                d = __dadd_rn(d, __dmul_rn(0.0, a2));
-                d = __dadd_rn(d, __dmul_rn(2.0, a3));
-                d = __dadd_rn(d, a4);
-                double m = a0;
-                m = __dadd_rn(m, __dmul_rn(4.0, a1));
-                m = __dadd_rn(m, __dmul_rn(6.0, a2));
-                m = __dadd_rn(m, __dmul_rn(4.0, a3));
-                m = __dadd_rn(m, a4);
-                wD[u] = d;
-                wS[u] = m;
+            {
+                const float t0 = tr[0], t1 = tr[1], t2 = tr[2], t3 = tr[3], t4 = tr[4];
+                f[u][0] = t1; f[u][1] = t2; f[u][2] = t3;
+                if (SOBEL) {
+                    const double a0 = (double)t0, a1 = (double)t1, a2 = (double)t2, a3 = (double)t3, a4 = (double)t4;
+                    // cv2.Sobel's row pass, tap by tap.  The inputs are fp32 values, so every product with a tap (0,
+                    // +-1, +-2, 4, 6) is EXACT in fp64 and a fused multiply-add rounds exactly once, like the separate
+                    // add of the exact product: bit-identical to the mul + add sequence (signs of zero and NaN / Inf
+                    // included; tests/test_oracle_cpu.py::test_sobel5_fused_taps), half the instructions.
+                    double d = __fma_rn(-2.0, a1, -a0);
+                    d = __fma_rn(0.0, a2, d);
+                    d = __fma_rn(2.0, a3, d);
+                    d = __dadd_rn(d, a4);
+                    double m = __fma_rn(4.0, a1, a0);
+                    m = __fma_rn(6.0, a2, m);
+                    m = __fma_rn(4.0, a3, m);
+                    m = __dadd_rn(m, a4);
+                    wD[u] = d;
+                    wS[u] = m;
+                }
             }
-            const int j = k - 4;           // output row of the tile, image row y0 + j
+            const int j = k - 4;           // output row of the tile, image row y0 + j; its centre is tile row k - 2
             if (j >= 0 && j < jEnd && colIn) {
                 const int y = y0 + j;
-                const int cr = j + 2, cc = c + XPAD;   // centre cell in the tile
-                const float v = tile[cr][cc];
+                const float v = f[(u + 3) % 5][1];
                 double sx = 0.0, sy = 0.0;
                 float a32 = 0.f;
                 if (SOBEL) {
                     // rows j .. j+4 of the row filters sit in slots (u+1)%5 .. (u+5)%5
                     const double d0 = wD[(u + 1) % 5], d1 = wD[(u + 2) % 5], d2 = wD[(u + 3) % 5], d3 = wD[(u + 4) % 5], d4 = wD[u];
                     const double s0 = wS[(u + 1) % 5], s1 = wS[(u + 2) % 5], s3 = wS[(u + 4) % 5], s4 = wS[u];
-                    sx = __dmul_rn(6.0, d2);
-                    sx = __dadd_rn(sx, __dmul_rn(4.0, __dadd_rn(d3, d1)));
+                    // column pass: products with a power of two are exact for any double, so they fuse as well
+                    // (6 * d2 is rounded on its own, as in OpenCV)
+                    sx = __fma_rn(4.0, __dadd_rn(d3, d1), __dmul_rn(6.0, d2));
                     sx = __dadd_rn(sx, __dadd_rn(d4, d0));
-                    sy = __dmul_rn(2.0, __dsub_rn(s3, s1));
-                    sy = __dadd_rn(sy, __dsub_rn(s4, s0));
-                    a32 = atan2_candidate((float)-sy, (float)sx);   // angle of the normal, atan2(-sy, sx)
+                    sy = __fma_rn(2.0, __dsub_rn(s3, s1), __dsub_rn(s4, s0));
+                    // angle of the normal, atan2(-sy, sx), as an fp32 CANDIDATE (|error| < 3e-6 rad on [1e-30, 1e30]:
+                    // tests/test_host_cpu.py::test_atan2_candidate_error_bound).  Outside that range the fast division
+                    // flushes or overflows: the candidate becomes NaN and every decision takes its exact path.
+                    const float fx = (float)sx, fy = (float)-sy;
+                    const float big = fmaxf(fabsf(fx), fabsf(fy));
+                    a32 = atan2_candidate(fy, fx);
+                    a32 = (big > 1e-30f && big < 1e30f) ? a32 : __int_as_float(0x7fc00000);
                 }
-                const bool zero = sx == 0.0 && sy == 0.0;
                 if (NRM) {
-                    const double X = sx, Y = -sy;
-                    const int k0 = min(max((int)((a32 * 57.29577951f + 180.f) * (255.f / 360.f)), 0), 255);
-                    const double m = (fabs(X) + fabs(Y)) * 0x1p-44;
-                    const double2 dl = sDir[max(k0, 1)], dh = sDir[min(k0 + 1, 255)];
-                    const bool okLo = k0 < 1 || (Y * dl.x - X * dl.y) > m;       // theta_k0 < A
-                    const bool okHi = k0 > 254 || (Y * dh.x - X * dh.y) < -m;    // A < theta_k0+1
+                    // level = trunc(lv(A)), lv(A) = A * 255 / (2 pi) + 127.5.  The candidate decides alone when its
+                    // fractional part is at least 1e-3 away from an integer (8x the candidate's 1.2e-4 levels of
+                    // error + the fp32 rounding of lv); the rest (0.2 % of the pixels, zero gradients, NaN / Inf) is
+                    // proved with two fp64 cross products against the neighbouring threshold DIRECTIONS, and inside
+                    // their 2^-44 guard band by the reference's own double atan2 expression.
+                    const float lv = fmaf(a32, 40.5845105f, 127.5f);
+                    const int k0 = (int)lv;
+                    const float fl = lv - (float)k0;
                     int lvl = k0;
-                    if (zero) lvl = sZero[(int)(__double2hiint(sy) < 0) | ((int)(__double2hiint(sx) < 0) << 1)];
-                    else if (!(okLo && okHi)) lvl = (int)normal_level_value(atan2(-sy, sx));  // guard band, NaN / Inf
-                    normals[o] = (unsigned char)lvl;
+                    if (!(fl >= 1e-3f && fl <= 1.f - 1e-3f && (unsigned)k0 <= 254u)) {
+                        // flat regions (zero gradient) are common in real maps: decided here, without the call
+                        if (sx == 0.0 && sy == 0.0) lvl = sZero[(int)(__double2hiint(sy) < 0) | ((int)(__double2hiint(sx) < 0) << 1)];
+                        else lvl = dee_level_exact(sx, sy, (fl == fl) ? k0 : -1, sDir, sZero);   // NaN candidate: none
+                    }
+                    *nrmP = (unsigned char)lvl;
                 }
                 const bool interior = xInterior && y >= 1 && y < H - 1;
                 float keep = v;
                 if (NMS) {
                     keep = 0.f;
                     if (interior) {
-                        // bin of atan2(sy, sx) = -a32 folded to [0, pi): 0 = [0, 22.5) u [157.5, 180], 1 = [22.5, 67.5),
-                        // 2 = [67.5, 112.5), 3 = [112.5, 157.5), 4 = none.  The fp32 candidate decides when it is at least
-                        // 1e-4 of an octant (4e-5 rad, four times its error) away from every boundary.
-                        const float an = -a32;
-                        const float am = (an < 0.f ? an + 3.14159274f : an) * 2.54647899f;   // in units of pi / 8
-                        const int idx = (int)am;
-                        const float fr = am - (float)idx;
-                        int bin = ((idx + 1) >> 1) & 3;
-                        if (zero) bin = 0;   // atan2(+-0, +-0) is 0 or +-pi: bin 0 either way
-                        // bin boundaries are the ODD multiples of pi / 8 only (0, 45, 90, 135 deg -- axis-aligned and
-                        // diagonal gradients, which are common -- lie in the middle of a bin)
-                        else if (!((idx & 1) ? fr >= 1e-4f : fr <= 1.f - 1e-4f) || idx < 0 || idx > 8) {
-                            // near a boundary (or NaN / Inf): |sy| against |sx| tan(22.5 / 67.5 deg) in fp64 with a 2^-40
-                            // guard band, and inside that band the reference's own expression
-                            const double ax = fabs(sx), ay = fabs(sy);
-                            const double t1 = ax * 0.41421356237309503, t2 = ax * 2.4142135623730951;
-                            constexpr double lo = 1.0 - 0x1p-40, hi = 1.0 + 0x1p-40;
-                            bin = -1;
-                            if (ay < t1 * lo) bin = 0;
-                            else if (ay > t1 * hi && ay < t2 * lo) bin = ((sx < 0.0) != (sy < 0.0)) ? 3 : 1;
-                            else if (ay > t2 * hi) bin = 2;
-                            if (bin < 0) {
-                                double a = __dmul_rn(atan2(sy, sx), 180.0 / M_PI);
-                                if (a < 0.0) a = __dadd_rn(a, 180.0);
-                                bin = 4;
-                                if ((0.0 <= a && a < 22.5) || (157.5 <= a && a <= 180.0)) bin = 0;
-                                else if (22.5 <= a && a < 67.5) bin = 1;
-                                else if (67.5 <= a && a < 112.5) bin = 2;
-                                else if (112.5 <= a && a < 157.5) bin = 3;
-                            }
-                        }
-                        // neighbours (q, r): bin 0 (E, W), 1 (NW, SE), 2 (S, N), 3 (SW, NE); no bin -> 1 (tools.py:22-23)
-                        const int dy = bin == 0 ? 0 : (bin == 1 ? -1 : 1);
-                        const int dx = bin == 0 ? 1 : (bin == 2 ? 0 : -1);
-                        float q = tile[cr + dy][cc + dx], rr = tile[cr - dy][cc - dx];
+                        // bin of atan2(sy, sx) = -a32 (mod pi): 0 = [0, 22.5) u [157.5, 180], 1 = [22.5, 67.5),
+                        // 2 = [67.5, 112.5), 3 = [112.5, 157.5), 4 = none.  In units of pi / 4 shifted by half a bin the
+                        // boundaries are the integers and the bins repeat with period 4: the fp32 candidate decides
+                        // when it is at least 5e-5 (4e-5 rad, > 10x its error) away from every boundary.
+                        const float uu = fmaf(-a32, 1.27323954f, 4.5f);   // in (0.5, 8.5)
+                        const int iu = (int)uu;
+                        const float fu = uu - (float)iu;
+                        int bin = iu & 3;
+                        if (!(fu >= 5e-5f && fu <= 1.f - 5e-5f))   // near a boundary, zero gradient (flat: no call), NaN / Inf
+                            bin = (sx == 0.0 && sy == 0.0) ? 0 : dee_bin_exact(sx, sy);
+                        // neighbours (q, r): bin 0 (E, W), 1 (NW, SE), 2 (S, N), 3 (SW, NE); no bin -> 1 (tools.py:22-23),
+                        // out of the register window: rows above / at / below the centre are slots u+2, u+3, u+4
+                        const float(&up)[3] = f[(u + 2) % 5];
+                        const float(&md)[3] = f[(u + 3) % 5];
+                        const float(&dn)[3] = f[(u + 4) % 5];
+                        float q = bin == 0 ? md[2] : (bin == 1 ? up[0] : (bin == 2 ? dn[1] : dn[0]));
+                        float rr = bin == 0 ? md[0] : (bin == 1 ? dn[2] : (bin == 2 ? up[1] : up[2]));
                         if (bin == 4) { q = 1.f; rr = 1.f; }
                         if (v >= q && v >= rr) keep = v;
                     }
                 }
-                if (nmsOut) nmsOut[o] = keep;
+                if (nmsOut) *nmsP = keep;
                 if (HYST) {
-                    unsigned char c_l = 255, e_l = 255;
-                    const double kv = (double)keep;
                     if (interior) {
-                        if (kv > tHigh) { c_l = 0; e_l = 0; }
-                        else if (!(kv < tLow)) c_l = 0;
-                        anyStrong = anyStrong || e_l == 0;
+                        const bool strong = keep > thF;
+                        const bool cand = !(keep < tlF);
+                        anyStrong = anyStrong || strong;
+                        *clP = (strong || cand) ? 0 : 255;
+                        *eP = strong ? 0 : 255;
                     } else {
+                        // border pixels keep their raw value as "label" (tools.py:54-55 never touches them)
+                        const double kv = (double)keep;
                         if (kv != kv) atomicOr(&stats[im].borderNaN, 1u);
                         else atomicMax(&stats[im].borderMaxKey, dkey(kv));
+                        *clP = 255;
+                        *eP = 255;
                     }
-                    cl[o] = c_l;
-                    E[o] = e_l;
                 }
-                o += (size_t)W;
+                if (NRM) nrmP += W;
+                if (nmsOut) nmsP += W;
+                if (HYST) { clP += W; eP += W; }
             }
         }
     }

@@ -14,6 +14,14 @@
 // gradient equals the expected one and rescales in place otherwise.
 // HBM traffic: 12 B/px in + 8 B/px out = 20 B/px instead of 34 B/px over two launches with a stash round trip.
 //
+// No halo ROWS: a segment (a warp's run of rows in one strip) computes only the response rows it owns.  The 3x3
+// adjoint of its first / last response row also reaches the output rows just outside, and its own first / last output
+// rows lack the contribution of the neighbouring segment's response row: those four rows per segment are written by
+// BOTH segments with a vector red.add onto rows that phase 1 zeroed (the grid barrier orders zero < add).  Segments
+// start on even rows, so every such output row has exactly two contributors and 0 + a + b = 0 + b + a bit for bit:
+// the result does not depend on the order of arrival.  (Recomputing one halo row above and below, as the two-kernel
+// path does, cost 2 of ~20 rows per segment.)
+//
 // Reference arithmetic preserved: packnet_code/packnet_sfm/losses/grad_loss.py:65-95 (responses, band pick),
 // :122-159 (sigmoid, weight), :161-219 (class-balanced BCE); backward = SURVEY.md A.1.
 #include <string.h>
@@ -28,9 +36,9 @@ namespace loss {
 #endif
 constexpr int kFusedD = MTE_FUSED_D;
 #ifndef MTE_FUSED_SEGCOST
-#define MTE_FUSED_SEGCOST 6
+#define MTE_FUSED_SEGCOST 2
 #endif
-constexpr int kSegCostFused = MTE_FUSED_SEGCOST;  // a segment start costs the window prologue + two halo rows of full work
+constexpr int kSegCostFused = MTE_FUSED_SEGCOST;  // units are ROW PAIRS; a segment start costs the window prologue + the boundary adds
 #ifndef MTE_FUSED_REGS
 #define MTE_FUSED_REGS 120
 #endif
@@ -76,17 +84,21 @@ __device__ __forceinline__ bool next_segment(const LossP &P, int &u0, int u1, Se
         if (k < P.nScales && u0 >= P.s[k].unitBase) si = k;
     const ScaleP &S = P.s[si];
     const int local = u0 - S.unitBase;
-    const int HV = S.H + kSegCostFused;
+    const int HV = ((S.H + 1) >> 1) + kSegCostFused;  // row pairs of a strip + the virtual units of opening a segment
     const int t = local / HV;  // (image, strip)
     const int r = local - t * HV;
     const int take = min(HV - r, u1 - u0);
-    s.row0 = max(r - kSegCostFused, 0);
-    s.nrows = max(r + take - kSegCostFused, 0) - s.row0;
+    s.row0 = 2 * max(r - kSegCostFused, 0);   // segments start on even rows (see the header: two contributors per row)
+    s.nrows = min(2 * max(r + take - kSegCostFused, 0), S.H) - s.row0;
     u0 += take;
     s.si = si;
     s.img = t / S.strips;
     s.strip = t - s.img * S.strips;
     return s.nrows > 0;
+}
+
+__device__ __forceinline__ void red_add4(float *p, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 // ---- packed fp32 (sm_100a FADD2 / FMUL2 / FFMA2): the row loop is issue-bound (ncu: warps mostly "not selected",
@@ -124,14 +136,14 @@ __device__ __forceinline__ void prep_row2(PRow2 &R, const float2 (&x)[2]) {
     R.d[1] = make_float2(x[1].y - x[0].y, r - x[1].x);
 }
 
-// The loads that open a segment (first D ring rows + the two depth rows above the first response row), as a function
+// The loads that open a segment (first D ring rows + the depth rows above / at the first response row), as a function
 // of their own: the FIRST segment of every warp issues them BEFORE the grid barrier, so the DRAM round trip that
 // refills the pipeline after phase 1 overlaps the barrier instead of following it.
 __device__ __forceinline__ void fused_prologue(const ScaleP &S, const Seg &sg, int lane, unsigned char *ring,
                                                float2 (&xa)[2], float2 (&xc)[2]) {
     constexpr int D = kFusedD;
     constexpr unsigned PLB = 512, SLB = 3 * PLB;
-    const int H = S.H, row0 = sg.row0, niter = sg.nrows + 2;
+    const int H = S.H, row0 = sg.row0, niter = sg.nrows;
     const unsigned W = (unsigned)S.W;
     const int col0 = (sg.strip * kHaloLanes + lane - 1) * 4;
     const bool colOk = col0 >= 0 && col0 < (int)W;
@@ -147,17 +159,16 @@ __device__ __forceinline__ void fused_prologue(const ScaleP &S, const Seg &sg, i
             x[1] = make_float2(t.z, t.w);
         }
     };
-    load_plain(xa, row0 - 2);
-    load_plain(xc, row0 - 1);
+    load_plain(xa, row0 - 1);
+    load_plain(xc, row0);
 #pragma unroll
     for (int k = 0; k < D; k++) {
-        if (k < niter) {
-            const int rx = row0 + k, r = row0 - 1 + k;
+        if (k < niter) {   // response row row0 + k (inside the image): depth row below it, its own target rows
+            const int rx = row0 + 1 + k;
             cp_async_vec<4>(ringS + k * SLB, elem_addr(xP, (unsigned)min(rx, H - 1) * W), colOk && rx < H);
-            const bool rOk = colOk && r >= 0 && r < H;
-            const unsigned ro = (unsigned)min(max(r, 0), H - 1) * W;
-            cp_async_vec<4>(ringS + k * SLB + PLB, elem_addr(eP, ro), rOk);
-            cp_async_vec<4>(ringS + k * SLB + 2 * PLB, elem_addr(nP, ro), rOk);
+            const unsigned ro = (unsigned)(row0 + k) * W;
+            cp_async_vec<4>(ringS + k * SLB + PLB, elem_addr(eP, ro), colOk);
+            cp_async_vec<4>(ringS + k * SLB + 2 * PLB, elem_addr(nP, ro), colOk);
         }
         cp_async_commit();
     }
@@ -183,15 +194,14 @@ __device__ __forceinline__ void fused_segment(const LossP &P, const ScaleP &S, c
     unsigned char *slot0 = ring + lane * 16;
     const unsigned ringS = (unsigned)__cvta_generic_to_shared(slot0);
 
-    // iteration j = 0 .. nrows + 1 handles RESPONSE row r = row0 - 1 + j (one halo row above and below the rows
-    // this segment owns): it needs depth row r + 1 (rows r - 1 and r are in the window) and the target rows r
+    // iteration j = 0 .. nrows - 1 handles RESPONSE row r = row0 + j, a row this segment owns: it needs depth row
+    // r + 1 (rows r - 1 and r are in the window) and the target rows r
     auto issue = [&](unsigned so, int j) {
-        const int rx = row0 + j, r = row0 - 1 + j;
+        const int rx = row0 + 1 + j;
         cp_async_vec<4>(ringS + so, elem_addr(xP, (unsigned)min(rx, H - 1) * W), colOk && rx < H);
-        const bool rOk = colOk && r >= 0 && r < H;
-        const unsigned ro = (unsigned)min(max(r, 0), H - 1) * W;
-        cp_async_vec<4>(ringS + so + PLB, elem_addr(eP, ro), rOk);
-        cp_async_vec<4>(ringS + so + 2 * PLB, elem_addr(nP, ro), rOk);
+        const unsigned ro = (unsigned)(row0 + j) * W;
+        cp_async_vec<4>(ringS + so + PLB, elem_addr(eP, ro), colOk);
+        cp_async_vec<4>(ringS + so + 2 * PLB, elem_addr(nP, ro), colOk);
     };
     auto fix_row = [&](float2 (&x)[2], int row) {  // padding, inv2depth, non-finite tracking
         if (INV) {
@@ -213,10 +223,10 @@ __device__ __forceinline__ void fused_segment(const LossP &P, const ScaleP &S, c
         x[1] = make_float2(t.z, t.w);
     };
 
-    const int niter = nrows + 2;
-    PRow2 win[3];  // win[d % 3] holds depth row row0 - 2 + d; xa / xc and the first D ring rows come from fused_prologue
-    fix_row(xa, row0 - 2);
-    fix_row(xc, row0 - 1);
+    const int niter = nrows;
+    PRow2 win[3];  // win[d % 3] holds depth row row0 - 1 + d; xa / xc and the first D ring rows come from fused_prologue
+    fix_row(xa, row0 - 1);
+    fix_row(xc, row0);
     prep_row2(win[0], xa);
     prep_row2(win[1], xc);
     float oacc[3][4];
@@ -224,6 +234,26 @@ __device__ __forceinline__ void fused_segment(const LossP &P, const ScaleP &S, c
     for (int o = 0; o < 3; o++)
 #pragma unroll
         for (int v = 0; v < 4; v++) oacc[o][v] = 0.f;
+    // one output row (accumulator slot `slot`, depth row `dep` for the inv2depth chain rule) to memory: complete rows are
+    // stored, rows shared with the neighbouring segment are added onto the zeroed row (see the header)
+    auto emit = [&](const float (&acc)[4], const PRow2 &dep, int row, bool shared) {
+        float out[4];
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            float d = acc[v];
+            if (INV) {
+                // pred was an inverse depth: chain through depth = 1 / clamp(inv, 1e-6) (utils/depth.py:104-121)
+                const float dp = (v & 1) ? dep.c[v >> 1].y : dep.c[v >> 1].x;
+                d = (dp < 1e6f) ? -d * dp * dp : 0.f;
+            }
+            out[v] = d;
+        }
+        if (writer) {
+            float *o = elem_addr(dP, (unsigned)row * W);
+            if (shared) red_add4(o, make_float4(out[0], out[1], out[2], out[3]));
+            else st_stream4(o, make_float4(out[0], out[1], out[2], out[3]));
+        }
+    };
 
     unsigned so = 0;
 #pragma unroll 1
@@ -240,14 +270,12 @@ __device__ __forceinline__ void fused_segment(const LossP &P, const ScaleP &S, c
                 if (j + D < niter) issue(so, j + D);  // refill the slot just read
                 cp_async_commit();
                 so = (so + SLB == D * SLB) ? 0u : so + SLB;
-                const int r = row0 - 1 + j;
+                const int r = row0 + j;
                 PRow2 &dn = win[(u + 2) % 3];
                 fix_row(xn, r + 1);
                 prep_row2(dn, xn);
                 const PRow2 &up = win[u % 3];
                 const PRow2 &mid = win[(u + 1) % 3];
-                const bool own = j >= 1 && j <= nrows;            // a row this segment owns (warp-uniform)
-                const bool live = colOk && r >= 0 && r < H;       // the response pixel exists
                 float g[4];
                 float2 X[4], Z[4];   // per pixel: (A, C) and (A2, C2) of the adjoint
 #pragma unroll
@@ -275,23 +303,20 @@ __device__ __forceinline__ void fused_segment(const LossP &P, const ScaleP &S, c
                     const float2 q = f2fma(p, m1, one2);       // 1 - p
                     const float2 pe = f2add(p, eps2), qe = f2add(q, eps2);
                     const float2 ee = e[h], ne = f2fma(ee, m1, one2);
-                    if (own) {
-                        la[0] = f2fma(ee, make_float2(lg2_approx(pe.x), lg2_approx(pe.y)), la[0]);
-                        la[1] = f2fma(ne, make_float2(lg2_approx(qe.x), lg2_approx(qe.y)), la[1]);
-                    }
+                    la[0] = f2fma(ee, make_float2(lg2_approx(pe.x), lg2_approx(pe.y)), la[0]);
+                    la[1] = f2fma(ne, make_float2(lg2_approx(qe.x), lg2_approx(qe.y)), la[1]);
                     float2 d = f2mul(f2mul(cp2, ee), make_float2(rcp_approx(pe.x), rcp_approx(pe.y)));
                     d = f2fma(f2mul(cn2, ne), make_float2(rcp_approx(qe.x), rcp_approx(qe.y)), d);
                     if (SIG) d = f2mul(f2mul(d, p), q);
                     // sign(0) = 0; pixels outside the image do not exist
-                    const float d0 = (live && gg.x != 0.f) ? d.x : 0.f, d1 = (live && gg.y != 0.f) ? d.y : 0.f;
+                    const float d0 = (colOk && gg.x != 0.f) ? d.x : 0.f, d1 = (colOk && gg.y != 0.f) ? d.y : 0.f;
                     const float4 k0 = sLut[cd0 & 15u], k1 = sLut[cd1 & 15u];
                     X[2 * h] = f2mul(f2(d0), make_float2(k0.x, k0.y));
                     Z[2 * h] = f2mul(f2(d0), make_float2(k0.z, k0.w));
                     X[2 * h + 1] = f2mul(f2(d1), make_float2(k1.x, k1.y));
                     Z[2 * h + 1] = f2mul(f2(d1), make_float2(k1.z, k1.w));
                 }
-                if (own && writeG)
-                    st_stream4(elem_addr(gP, (unsigned)r * W), make_float4(g[0], g[1], g[2], g[3]));
+                if (writeG) st_stream4(elem_addr(gP, (unsigned)r * W), make_float4(g[0], g[1], g[2], g[3]));
                 // neighbours across the lane boundary: (A, C) and C2 of the adjacent pixel
                 const float2 Xl = make_float2(__shfl_up_sync(MTE_FULL_MASK, X[3].x, 1), __shfl_up_sync(MTE_FULL_MASK, X[3].y, 1));
                 const float2 Xr = make_float2(__shfl_down_sync(MTE_FULL_MASK, X[0].x, 1), __shfl_down_sync(MTE_FULL_MASK, X[0].y, 1));
@@ -309,20 +334,12 @@ __device__ __forceinline__ void fused_segment(const LossP &P, const ScaleP &S, c
                     oacc[(u + 2) % 3][v] += c2_l - c2_r;
                     oacc[(u + 1) % 3][v] -= SA - DC;
                 }
-                if (j >= 2) {
-                    float out[4];
-#pragma unroll
-                    for (int v = 0; v < 4; v++) {
-                        float d = oacc[(u + 1) % 3][v];
-                        if (INV) {
-                            // pred was an inverse depth: chain through depth = 1 / clamp(inv, 1e-6)
-                            // (utils/depth.py:104-121); the depth of output row r - 1 is the window's upper row
-                            const float dep = (v & 1) ? up.c[v >> 1].y : up.c[v >> 1].x;
-                            d = (dep < 1e6f) ? -d * dep * dep : 0.f;
-                        }
-                        out[v] = d;
-                    }
-                    if (writer) st_stream4(elem_addr(dP, (unsigned)(r - 1) * W), make_float4(out[0], out[1], out[2], out[3]));
+                // output row r - 1 has all it gets from this segment: rows row0 - 1 (the neighbour's) and row0 (missing
+                // the neighbour's response row) are shared, the rest is complete
+                if (r >= 1) emit(oacc[(u + 1) % 3], up, r - 1, j < 2);
+                if (j == niter - 1) {   // the last response row: rows r and r + 1 are shared with the segment below
+                    emit(oacc[(u + 2) % 3], mid, r, true);
+                    if (r + 1 < H) emit(oacc[u], dn, r + 1, true);
                 }
             }
         }
@@ -371,6 +388,12 @@ __global__ void __maxnreg__(MTE_FUSED_REGS) edge_loss_fused_kernel(const __grid_
             const int col0 = (sg.strip * kHaloLanes + lane - 1) * 4;
             const bool writer = col0 >= 0 && col0 < (int)W && lane >= 1 && lane <= kHaloLanes;
             const float *eP = S.e + (size_t)sg.img * S.H * W + (writer ? col0 : 0);
+            if (writer) {   // the two output rows this segment shares with its neighbours start at zero (see the header)
+                float *dP = S.dx + (size_t)sg.img * S.H * W + col0;
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4 *>(elem_addr(dP, (unsigned)sg.row0 * W)) = z;
+                *reinterpret_cast<float4 *>(elem_addr(dP, (unsigned)(sg.row0 + sg.nrows - 1) * W)) = z;
+            }
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll 1
             for (int j0 = 0; j0 < sg.nrows; j0 += kP1Rows) {
@@ -595,7 +618,7 @@ extern "C" int mte_edge_loss_fwd_grad(const mte_loss_scale_t *sc, int n, const m
         S.strips = ceil_div(S.W, kHaloLanes * 4);
         S.imgBase = img;
         S.unitBase = (int)unitBase;
-        unitBase += (long long)S.strips * (S.H + kSegCostFused) * S.B;
+        unitBase += (long long)S.strips * (((S.H + 1) >> 1) + kSegCostFused) * S.B;   // units are row pairs
         S.scaleWeight = sc[i].scale_weight;
         img += S.B;
     }
@@ -611,8 +634,8 @@ extern "C" int mte_edge_loss_fwd_grad(const mte_loss_scale_t *sc, int n, const m
     F.expectG = expected_grad_loss;
     F.barrier = hdr->ticket + 2;
     int grid = num_sms();
-    const int minRows = 4;
-    if ((long long)grid * kRWarps * minRows > unitBase) grid = (int)((unitBase + kRWarps * minRows - 1) / (kRWarps * minRows));
+    const int minUnits = 2;   // row pairs per warp below which a smaller grid is better
+    if ((long long)grid * kRWarps * minUnits > unitBase) grid = (int)((unitBase + kRWarps * minUnits - 1) / (kRWarps * minUnits));
     if (grid < 1) grid = 1;
     return launch_fused(F, grid, at->pred_is_inverse != 0, at->is_sigmoid != 0, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -175,3 +175,41 @@ def test_reference_arm_prints_one_contract_line():
     assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_atan2_candidate_error_bound():
+    """dee_front_tma_kernel (csrc/dee.cu: atan2_candidate) lets an fp32 angle candidate decide the u8 normal level and
+    the NMS bin ALONE when it is >= 1e-3 levels / 5e-5 bin units away from every boundary.  That needs a hard bound
+    on the candidate's error: the same polynomial, emulated here in fp32 (with a deliberately sloppy division: the
+    kernel's rcp.approx is good to 1 ulp), must stay within 3e-6 rad of atan2 -- 1.2e-4 levels, 3.8e-6 bin units."""
+    f = np.float32
+
+    def fma(a, b, c):
+        return (a.astype(np.float64) * b.astype(np.float64) + np.float64(c)).astype(f)
+
+    def cand(y, x, sloppy):
+        ax, ay = np.abs(x), np.abs(y)
+        mx, mn = np.maximum(ax, ay), np.minimum(ax, ay)
+        t = (mn * ((f(1) / mx) * f(sloppy)).astype(f)).astype(f)
+        t2 = (t * t).astype(f)
+        p = fma(t2, np.full_like(t2, f(-0.0117212)), f(0.05265332))
+        for c in (-0.11643287, 0.19354346, -0.33262347, 0.99997726):
+            p = fma(p, t2, f(c))
+        p = (p.astype(np.float64) * t.astype(np.float64)).astype(f)
+        p = np.where(ay > ax, f(1.57079637) - p, p).astype(f)
+        p = np.where(x < 0, f(3.14159274) - p, p).astype(f)
+        return np.where(y < 0, -p, p).astype(f)
+
+    rng = np.random.default_rng(0)
+    n = 2_000_000
+    ang = rng.uniform(-np.pi, np.pi, n)
+    r = np.exp(rng.uniform(np.log(1e-30), np.log(1e30), n))
+    X, Y = r * np.cos(ang), r * np.sin(ang)
+    for sloppy in (1.0, 1.0 + 3e-7, 1.0 - 3e-7):
+        a = cand(Y.astype(f), X.astype(f), sloppy).astype(np.float64)
+        err = np.abs(a - np.arctan2(Y, X))
+        err = np.minimum(err, 2 * np.pi - err)
+        assert err.max() < 3e-6, err.max()
+    t = np.linspace(0, 1, 1_000_001).astype(f)
+    a = cand(t, np.ones_like(t), 1.0).astype(np.float64)
+    assert np.abs(a - np.arctan(t.astype(np.float64))).max() < 3e-6

@@ -88,6 +88,28 @@ def test_dee_oracle_vs_golden_and_cv2_sobel():
         assert np.array_equal(dee.normals_u8(p), z[f"normals{i}"])
 
 
+def test_sobel5_fused_taps():
+    """Premise of the fused multiply-adds in dee_front_tma_kernel (csrc/dee.cu): a Sobel5 tap times an fp32 value is
+    EXACT in fp64, and so is a power of two times any double that comes out of the row pass, so fma(tap, a, acc)
+    rounds once, exactly like acc + (tap * a) with the exact product: the kernel stays bit-identical to cv2.Sobel."""
+    from fractions import Fraction
+    rng = np.random.default_rng(11)
+    mant = rng.integers(1 << 23, 1 << 24, 4000).astype(np.float64)
+    expo = rng.integers(-140, 120, 4000)
+    vals = np.ldexp(mant, expo - 23).astype(np.float32)            # normals, subnormals, huge values
+    vals = np.concatenate([vals, -vals, np.array([0.0, -0.0, 1.0, 3.0, np.finfo(np.float32).max], np.float32)])
+    for tap in (-2.0, -1.0, 0.0, 1.0, 2.0, 4.0, 6.0):
+        prod = np.float64(tap) * vals.astype(np.float64)
+        for a, p in zip(vals[::7], prod[::7]):
+            assert Fraction(float(p)) == Fraction(tap) * Fraction(float(a))
+        assert np.array_equal(np.signbit(prod), np.signbit(np.float64(tap)) ^ np.signbit(vals))   # signed zeros too
+    # column pass: doubles that are sums of such products, times 2 / 4
+    acc = (vals[:-1].astype(np.float64) * 6.0 + vals[1:].astype(np.float64) * 4.0)
+    for tap in (2.0, 4.0):
+        for a in acc[::11]:
+            assert Fraction(float(np.float64(tap) * a)) == Fraction(tap) * Fraction(float(a))
+
+
 def test_matcher_oracle_vs_scipy():
     from oracle import pr_counts as opr
     for k, (shape, md) in enumerate([((60, 90), 0.0075), ((218, 1153), 0.002), ((40, 40), 0.05), ((100, 300), 0.01)]):
