@@ -253,6 +253,17 @@ constexpr int XW = 128, XH = 31, XROWS = XH + 4, XPAD = 4, XCOLS = XW + 2 * XPAD
 static_assert(XROWS % 5 == 0, "the register window rotates with period 5");
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+// cond ? a : b as a real SELP (keeps ptxas from turning value selections into divergent branches)
+__device__ __forceinline__ float selp(bool cond, float a, float b) {
+    float r;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f32 %0, %1, %2, p;\n\t}" : "=f"(r) : "f"(a), "f"(b), "r"((int)cond));
+    return r;
+}
+__device__ __forceinline__ unsigned selp(bool cond, unsigned a, unsigned b) {
+    unsigned r;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.u32 %0, %1, %2, p;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"((int)cond));
+    return r;
+}
 
 // Branch-free fp32 atan2 (octant reduction + odd minimax polynomial; |error| < 3e-6 rad for components in [1e-30, 1e30],
 // tests/test_host_cpu.py::test_atan2_candidate_error_bound): only a CANDIDATE; the exact fp64 decisions take over
@@ -387,10 +398,19 @@ __global__ void __launch_bounds__(kXThreads, MTE_DEE_MINB) dee_front_tma_kernel(
     double wD[5], wS[5];   // row-filter results of the last five tile rows, slot = tile row % 5
     float f[5][3];         // the fp32 values at columns x - 1, x, x + 1 of the same rows (NMS neighbours, centre value)
     bool anyStrong = false;
-    const size_t o0 = (size_t)im * H * W + (size_t)y0 * W + x;
-    unsigned char *nrmP = NRM ? normals + o0 : nullptr;     // running pointers: advance by W per output row
-    float *nmsP = nmsOut ? nmsOut + o0 : nullptr;
-    unsigned char *clP = HYST ? cl + o0 : nullptr, *eP = HYST ? E + o0 : nullptr;
+    // output addresses = a CTA-uniform base + ONE 32-bit running offset (x + row * W), formed by a single wide
+    // multiply-add per store (four running 64-bit pointers cost 16 instructions per pixel in adds and pair moves)
+    const size_t o0 = (size_t)im * H * W + (size_t)y0 * W;
+    unsigned char *const nrmB = NRM ? normals + o0 : nullptr;
+    float *const nmsB = nmsOut ? nmsOut + o0 : nullptr;
+    unsigned char *const clB = HYST ? cl + o0 : nullptr, *const eB = HYST ? E + o0 : nullptr;
+    unsigned oi = (unsigned)x;
+    auto st8 = [](unsigned char *base, unsigned off, unsigned v) {
+        asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %0, 1, %1;\n\tst.global.u8 [a], %2;\n\t}" ::"r"(off), "l"(base), "r"(v) : "memory");
+    };
+    auto st32 = [](float *base, unsigned off, float v) {
+        asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %0, 4, %1;\n\tst.global.f32 [a], %2;\n\t}" ::"r"(off), "l"(base), "f"(v) : "memory");
+    };
     const float *tr = &tile[0][c + XPAD - 2];               // columns x - 2 .. x + 2 of the current tile row
 #pragma unroll 1
     for (int g = 0; g < XROWS / 5; g++) {
@@ -456,7 +476,7 @@ __global__ void __launch_bounds__(kXThreads, MTE_DEE_MINB) dee_front_tma_kernel(
                         if (sx == 0.0 && sy == 0.0) lvl = sZero[(int)(__double2hiint(sy) < 0) | ((int)(__double2hiint(sx) < 0) << 1)];
                         else lvl = dee_level_exact(sx, sy, (fl == fl) ? k0 : -1, sDir, sZero);   // NaN candidate: none
                     }
-                    *nrmP = (unsigned char)lvl;
+                    st8(nrmB, oi, (unsigned)lvl);
                 }
                 const bool interior = xInterior && y >= 1 && y < H - 1;
                 float keep = v;
@@ -478,32 +498,34 @@ __global__ void __launch_bounds__(kXThreads, MTE_DEE_MINB) dee_front_tma_kernel(
                         const float(&up)[3] = f[(u + 2) % 5];
                         const float(&md)[3] = f[(u + 3) % 5];
                         const float(&dn)[3] = f[(u + 4) % 5];
-                        float q = bin == 0 ? md[2] : (bin == 1 ? up[0] : (bin == 2 ? dn[1] : dn[0]));
-                        float rr = bin == 0 ? md[0] : (bin == 1 ? dn[2] : (bin == 2 ? up[1] : up[2]));
-                        if (bin == 4) { q = 1.f; rr = 1.f; }
-                        if (v >= q && v >= rr) keep = v;
+                        // (real selects: as ternaries the compiler builds a branch tree with register moves, 25
+                        // instructions per pixel)
+                        const bool b0 = bin == 0, b1 = bin == 1, b2 = bin == 2, b4 = bin == 4;
+                        float q = selp(b2, dn[1], dn[0]), rr = selp(b2, up[1], up[2]);
+                        q = selp(b1, up[0], q); rr = selp(b1, dn[2], rr);
+                        q = selp(b0, md[2], q); rr = selp(b0, md[0], rr);
+                        q = selp(b4, 1.f, q); rr = selp(b4, 1.f, rr);
+                        keep = selp(v >= q && v >= rr, v, 0.f);
                     }
                 }
-                if (nmsOut) *nmsP = keep;
+                if (nmsOut) st32(nmsB, oi, keep);
                 if (HYST) {
                     if (interior) {
                         const bool strong = keep > thF;
-                        const bool cand = !(keep < tlF);
+                        const bool weak = keep < tlF && !strong;   // label 0; everything else (NaN too) is a candidate
                         anyStrong = anyStrong || strong;
-                        *clP = (strong || cand) ? 0 : 255;
-                        *eP = strong ? 0 : 255;
+                        st8(clB, oi, selp(weak, 255u, 0u));
+                        st8(eB, oi, selp(strong, 0u, 255u));
                     } else {
                         // border pixels keep their raw value as "label" (tools.py:54-55 never touches them)
                         const double kv = (double)keep;
                         if (kv != kv) atomicOr(&stats[im].borderNaN, 1u);
                         else atomicMax(&stats[im].borderMaxKey, dkey(kv));
-                        *clP = 255;
-                        *eP = 255;
+                        st8(clB, oi, 255u);
+                        st8(eB, oi, 255u);
                     }
                 }
-                if (NRM) nrmP += W;
-                if (nmsOut) nmsP += W;
-                if (HYST) { clP += W; eP += W; }
+                oi += (unsigned)W;
             }
         }
     }
