@@ -249,7 +249,10 @@ __global__ void __launch_bounds__(kThreads) dee_front_kernel(const DeeTab *__res
 // ---------------------------------------------------------------------------
 // The innermost box coordinate of a bulk-tensor copy must be 16-byte aligned (x0 - 2 traps with "illegal
 // instruction"; probed with scripts/ubench/tma_test.cu), so the box starts at x0 - 4 and is 8 columns wider than the tile.
-constexpr int XW = 128, XH = 31, XROWS = XH + 4, XPAD = 4, XCOLS = XW + 2 * XPAD, kXThreads = XW;   // 35 tile rows = 7 groups of 5
+#ifndef MTE_DEE_XH
+#define MTE_DEE_XH 31
+#endif
+constexpr int XW = 128, XH = MTE_DEE_XH, XROWS = XH + 4, XPAD = 4, XCOLS = XW + 2 * XPAD, kXThreads = XW;   // 35 tile rows = 7 groups of 5
 static_assert(XROWS % 5 == 0, "the register window rotates with period 5");
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -533,52 +536,85 @@ __global__ void __launch_bounds__(kXThreads, MTE_DEE_MINB) dee_front_tma_kernel(
 }
 
 // out = img * (labels / max(labels))  in the dtype the reference computes in (C = float or double).  One image per
-// blockIdx.y, four consecutive pixels per thread; labels / max takes only two values inside the image (2 / max at kept
-// pixels, 0 / max elsewhere), computed once per thread with the same division the reference does per pixel -- only the
-// one-pixel border (label = the raw value) divides per pixel.
+// blockIdx.y; a thread handles kFinG groups of four consecutive pixels, all loads issued before the first use.  labels /
+// max takes only two values inside the image (2 / max at kept pixels, 0 / max elsewhere): computed ONCE per CTA with the
+// same division the reference does per pixel -- only the one-pixel border (label = the raw value) divides per pixel.
+constexpr int kFinG = 4, kFinThreads = 256, kFinPx = kFinG * kFinThreads * 4;
 template <typename T, typename C, typename O>
-__global__ void __launch_bounds__(256) dee_finish_kernel(const T *__restrict__ val, const unsigned char *__restrict__ E,
-                                                         int N, int H, int W, const ImgStat *__restrict__ stats,
-                                                         O *__restrict__ out) {
+__global__ void __launch_bounds__(kFinThreads) dee_finish_kernel(const T *__restrict__ val, const unsigned char *__restrict__ E,
+                                                                 int N, int H, int W, const ImgStat *__restrict__ stats,
+                                                                 O *__restrict__ out) {
+    __shared__ C sNorm[3];   // 2 / max, 0 / max, max
     const int im = blockIdx.y;
     const int plane = H * W;
-    const ImgStat st = stats[im];
-    // np.max over {0, 2 at kept pixels, raw border values}; NaN wins
-    double mx = (H > 2 && W > 2) ? 0.0 : -INFINITY;
-    if (st.anyStrong) mx = 2.0;
-    if (st.borderMaxKey != 0ull) { const double b = dkey_inv(st.borderMaxKey); mx = b > mx ? b : mx; }
-    if (st.borderNaN) mx = NAN;
-    const C cm = (C)mx;
-    const C n2 = (C)2 / cm, n0 = (C)0 / cm;
-    const size_t base = (size_t)im * plane;
-    const int j0 = (blockIdx.x * 256 + threadIdx.x) * 4;
-    if (j0 >= plane) return;
-    int y = j0 / W, x = j0 - y * W;
-    const int cnt = min(4, plane - j0);
-    T v[4];
-    unsigned char e[4];
-    const bool vec = cnt == 4 && ((base + j0) & 3) == 0 && (reinterpret_cast<uintptr_t>(val) & 15) == 0 &&
-                     (reinterpret_cast<uintptr_t>(E) & 3) == 0 && sizeof(T) == 4;
-    if (vec) {
-        const float4 t = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(val) + base + j0);
-        v[0] = (T)t.x; v[1] = (T)t.y; v[2] = (T)t.z; v[3] = (T)t.w;
-        const uchar4 u = *reinterpret_cast<const uchar4 *>(E + base + j0);
-        e[0] = u.x; e[1] = u.y; e[2] = u.z; e[3] = u.w;
-    } else {
-        for (int k = 0; k < cnt; k++) { v[k] = val[base + j0 + k]; e[k] = E[base + j0 + k]; }
+    if (threadIdx.x == 0) {
+        const ImgStat st = stats[im];
+        // np.max over {0, 2 at kept pixels, raw border values}; NaN wins
+        double mx = (H > 2 && W > 2) ? 0.0 : -INFINITY;
+        if (st.anyStrong) mx = 2.0;
+        if (st.borderMaxKey != 0ull) { const double b = dkey_inv(st.borderMaxKey); mx = b > mx ? b : mx; }
+        if (st.borderNaN) mx = NAN;
+        const C cm = (C)mx;
+        sNorm[0] = (C)2 / cm;
+        sNorm[1] = (C)0 / cm;
+        sNorm[2] = cm;
     }
-    O r[4];
+    const size_t base = (size_t)im * plane;
+    const bool vecOk = sizeof(T) == 4 && sizeof(O) == 4 && (plane & 3) == 0 && (W & 3) == 0 &&
+                       (reinterpret_cast<uintptr_t>(val) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(E) & 3) == 0;
+    const int j00 = blockIdx.x * kFinPx + threadIdx.x * 4;
+    if (vecOk) {
+        // rows of whole float4s: a group never straddles a row, the border is its first / last pixel or a whole row
+        float4 v[kFinG];
+        unsigned e[kFinG];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        if (k < cnt) {
+        for (int g = 0; g < kFinG; g++) {
+            const int j0 = j00 + g * kFinThreads * 4;
+            v[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+            e[g] = 0xFFFFFFFFu;
+            if (j0 < plane) {
+                v[g] = __ldcs(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(val) + base + j0));
+                e[g] = __ldcs(reinterpret_cast<const unsigned *>(E + base + j0));
+            }
+        }
+        __syncthreads();
+        const C n2 = sNorm[0], n0 = sNorm[1], cm = sNorm[2];
+#pragma unroll
+        for (int g = 0; g < kFinG; g++) {
+            const int j0 = j00 + g * kFinThreads * 4;
+            if (j0 >= plane) continue;
+            const int y = j0 / W, x = j0 - y * W;
+            const float in[4] = {v[g].x, v[g].y, v[g].z, v[g].w};
+            float r[4];
+            const bool rowBorder = y == 0 || y == H - 1;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const C cv = (C)in[k];
+                const C norm = ((e[g] >> (8 * k)) & 0xFFu) == 0u ? n2 : n0;
+                r[k] = (float)(cv * norm);
+            }
+            if (rowBorder || x == 0 || x + 4 == W) {   // the border keeps its raw value as label: value * (value / max)
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (rowBorder || x + k == 0 || x + k == W - 1) { const C cv = (C)in[k]; r[k] = (float)(cv * (cv / cm)); }
+            }
+            __stcs(reinterpret_cast<float4 *>(reinterpret_cast<float *>(out) + base + j0), make_float4(r[0], r[1], r[2], r[3]));
+        }
+        return;
+    }
+    __syncthreads();
+    const C n2 = sNorm[0], n0 = sNorm[1], cm = sNorm[2];
+    for (int g = 0; g < kFinG; g++) {
+        const int j0 = j00 + g * kFinThreads * 4;
+        for (int k = 0; k < 4 && j0 + k < plane; k++) {
+            const int j = j0 + k, y = j / W, x = j - y * W;
             const bool interior = y >= 1 && y < H - 1 && x >= 1 && x < W - 1;
-            const C cv = (C)v[k];
-            const C norm = interior ? (e[k] == 0 ? n2 : n0) : cv / cm;
-            r[k] = (O)(cv * norm);
-            if (++x == W) { x = 0; y++; }
+            const C cv = (C)val[base + j];
+            const C norm = interior ? (E[base + j] == 0 ? n2 : n0) : cv / cm;
+            out[base + j] = (O)(cv * norm);
         }
     }
-    for (int k = 0; k < cnt; k++) out[base + j0 + k] = r[k];
 }
 
 template <typename T, typename O>
@@ -687,13 +723,13 @@ static int run(const T *prob, int N, int H, int W, int do_nms, int do_hyst, doub
         if (rc) return rc;
         // the reference computes in float64 once NMS has run (its output array is float64), else in the input type
         const bool c64 = do_nms || sizeof(T) == 8;
-        const dim3 fg((unsigned)ceil_div(H * W, 1024), (unsigned)N);
+        const dim3 fg((unsigned)ceil_div(H * W, kFinPx), (unsigned)N);
         if (out_dtype == MTE_F64) {
-            if (c64) dee_finish_kernel<T, double, double><<<fg, 256, 0, st>>>(val, E, N, H, W, stats, (double *)out);
-            else dee_finish_kernel<T, float, double><<<fg, 256, 0, st>>>(val, E, N, H, W, stats, (double *)out);
+            if (c64) dee_finish_kernel<T, double, double><<<fg, kFinThreads, 0, st>>>(val, E, N, H, W, stats, (double *)out);
+            else dee_finish_kernel<T, float, double><<<fg, kFinThreads, 0, st>>>(val, E, N, H, W, stats, (double *)out);
         } else {
-            if (c64) dee_finish_kernel<T, double, float><<<fg, 256, 0, st>>>(val, E, N, H, W, stats, (float *)out);
-            else dee_finish_kernel<T, float, float><<<fg, 256, 0, st>>>(val, E, N, H, W, stats, (float *)out);
+            if (c64) dee_finish_kernel<T, double, float><<<fg, kFinThreads, 0, st>>>(val, E, N, H, W, stats, (float *)out);
+            else dee_finish_kernel<T, float, float><<<fg, kFinThreads, 0, st>>>(val, E, N, H, W, stats, (float *)out);
         }
         MTE_RETURN_IF_CUDA_ERROR();
     } else if (nmsDst == val) {
