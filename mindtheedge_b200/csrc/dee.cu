@@ -333,6 +333,53 @@ __device__ __noinline__ int dee_bin_exact(double sx, double sy) {
     return 4;
 }
 
+// One output pixel entirely by the exact paths, straight from the halo tile (tile rows j .. j + 4 around output row j,
+// tile columns c + XPAD - 2 .. + 2): used by the straight-line row loop for the few pixels its fp32 candidate could not
+// decide.  Same operation order as the loop (cv2.Sobel's), same decisions as dee_front_kernel.  Returns "strong".
+template <bool NRM, bool HYST>
+__device__ __noinline__ bool dee_pixel_exact(const float *tile, int j, int c, bool interior, float thF, float tlF,
+                                             const double2 *sDir, const unsigned char *sZero, unsigned char *nrmB,
+                                             float *nmsB, unsigned char *clB, unsigned char *eB, unsigned off) {
+    double d[5], m[5];
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+        const float *tr = tile + (j + r) * XCOLS + c + XPAD - 2;
+        const double a0 = (double)tr[0], a1 = (double)tr[1], a2 = (double)tr[2], a3 = (double)tr[3], a4 = (double)tr[4];
+        double dd = __fma_rn(-2.0, a1, -a0);
+        dd = __fma_rn(0.0, a2, dd);
+        dd = __fma_rn(2.0, a3, dd);
+        d[r] = __dadd_rn(dd, a4);
+        double mm = __fma_rn(4.0, a1, a0);
+        mm = __fma_rn(6.0, a2, mm);
+        mm = __fma_rn(4.0, a3, mm);
+        m[r] = __dadd_rn(mm, a4);
+    }
+    double sx = __fma_rn(4.0, __dadd_rn(d[3], d[1]), __dmul_rn(6.0, d[2]));
+    sx = __dadd_rn(sx, __dadd_rn(d[4], d[0]));
+    const double sy = __fma_rn(2.0, __dsub_rn(m[3], m[1]), __dsub_rn(m[4], m[0]));
+    if (NRM) nrmB[off] = (unsigned char)dee_level_exact(sx, sy, -1, sDir, sZero);
+    const int cr = j + 2, cc = c + XPAD;
+    const float v = tile[cr * XCOLS + cc];
+    float keep = 0.f;
+    if (interior) {
+        const int bin = dee_bin_exact(sx, sy);
+        const int dy = bin == 0 ? 0 : (bin == 1 ? -1 : 1);
+        const int dx = bin == 0 ? 1 : (bin == 2 ? 0 : -1);
+        float q = tile[(cr + dy) * XCOLS + cc + dx], rr = tile[(cr - dy) * XCOLS + cc - dx];
+        if (bin == 4) { q = 1.f; rr = 1.f; }
+        if (v >= q && v >= rr) keep = v;
+    }
+    if (nmsB) nmsB[off] = keep;
+    bool strong = false;
+    if (HYST) {
+        strong = interior && keep > thF;
+        const bool weak = keep < tlF && !strong;
+        clB[off] = (interior && !weak) ? 0 : 255;
+        eB[off] = strong ? 0 : 255;
+    }
+    return strong;
+}
+
 #ifndef MTE_DEE_MINB
 #define MTE_DEE_MINB 5
 #endif
@@ -415,6 +462,117 @@ __global__ void __launch_bounds__(kXThreads, MTE_DEE_MINB) dee_front_tma_kernel(
         asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %0, 4, %1;\n\tst.global.f32 [a], %2;\n\t}" ::"r"(off), "l"(base), "f"(v) : "memory");
     };
     const float *tr = &tile[0][c + XPAD - 2];               // columns x - 2 .. x + 2 of the current tile row
+    if constexpr (NMS) {
+        // ---- straight-line form (every variant that runs the NMS): no branch in the body of a row except the final
+        // stores, so the scheduler interleaves the five unrolled rows (the kernel is bound by dependent-issue latency:
+        // ncu `wait` 2.3 per issue with 20 warps per SM).  Pixels whose candidate cannot decide are only FLAGGED here
+        // and redone by dee_pixel_exact after the loop; zero gradients (flat regions, common) are decided in line.
+        // Border pixels: the NMS leaves 0 there (tools.py:19-20), so their raw "label" is 0 for every tile that
+        // touches the border: one atomicMax per CTA instead of one per pixel.
+        auto row_pass = [&](int u) {
+            const float t0 = tr[0], t1 = tr[1], t2 = tr[2], t3 = tr[3], t4 = tr[4];
+            tr += XCOLS;
+            f[u][0] = t1; f[u][1] = t2; f[u][2] = t3;
+            const double a0 = (double)t0, a1 = (double)t1, a2 = (double)t2, a3 = (double)t3, a4 = (double)t4;
+            double d = __fma_rn(-2.0, a1, -a0);   // exact products: see the generic loop below
+            d = __fma_rn(0.0, a2, d);
+            d = __fma_rn(2.0, a3, d);
+            wD[u] = __dadd_rn(d, a4);
+            double m = __fma_rn(4.0, a1, a0);
+            m = __fma_rn(6.0, a2, m);
+            m = __fma_rn(4.0, a3, m);
+            wS[u] = __dadd_rn(m, a4);
+        };
+        unsigned long long flagged = 0ull;
+        const float zl0 = (float)sZero[0], zl1 = (float)sZero[1], zl2 = (float)sZero[2], zl3 = (float)sZero[3];
+        auto out_row = [&](int u, int j, unsigned &gmask) {   // output row j of the tile; tile row j + 4 is in slot u
+            const int y = y0 + j;
+            const float v = f[(u + 3) % 5][1];
+            const double d0 = wD[(u + 1) % 5], d1 = wD[(u + 2) % 5], d2 = wD[(u + 3) % 5], d3 = wD[(u + 4) % 5], d4 = wD[u];
+            const double s0 = wS[(u + 1) % 5], s1 = wS[(u + 2) % 5], s3 = wS[(u + 4) % 5], s4 = wS[u];
+            double sx = __fma_rn(4.0, __dadd_rn(d3, d1), __dmul_rn(6.0, d2));
+            sx = __dadd_rn(sx, __dadd_rn(d4, d0));
+            const double sy = __fma_rn(2.0, __dsub_rn(s3, s1), __dsub_rn(s4, s0));
+            const float fx = (float)sx, fy = (float)-sy;
+            const float big = fmaxf(fabsf(fx), fabsf(fy));
+            float a32 = atan2_candidate(fy, fx);
+            a32 = (big > 1e-30f && big < 1e30f) ? a32 : __int_as_float(0x7fc00000);
+            const bool zero = sx == 0.0 && sy == 0.0;
+            bool decided = true;
+            int lvl = 0;
+            if (NRM) {
+                const float lv = fmaf(a32, 40.5845105f, 127.5f);
+                const int k0 = (int)lv;
+                const float fl = lv - (float)k0;
+                decided = fl >= 1e-3f && fl <= 1.f - 1e-3f && (unsigned)k0 <= 254u;
+                // zero gradient: level by the signs of the two zeros (sZero), picked with selects
+                const bool ny = __double2hiint(sy) < 0, nx = __double2hiint(sx) < 0;
+                const float zl = nx ? (ny ? zl3 : zl2) : (ny ? zl1 : zl0);
+                lvl = zero ? (int)zl : k0;
+            }
+            const float uu = fmaf(-a32, 1.27323954f, 4.5f);   // bin boundaries at the integers, period 4 (see below)
+            const int iu = (int)uu;
+            const float fu = uu - (float)iu;
+            decided = decided && fu >= 5e-5f && fu <= 1.f - 5e-5f;
+            const int bin = zero ? 0 : (iu & 3);
+            const bool need = !zero && !decided;
+            const bool interior = xInterior && y >= 1 && y < H - 1;
+            const float(&up)[3] = f[(u + 2) % 5];
+            const float(&md)[3] = f[(u + 3) % 5];
+            const float(&dn)[3] = f[(u + 4) % 5];
+            float q = dn[0], rr = up[2];                       // bin 3 (SW, NE)
+            q = bin == 2 ? dn[1] : q; rr = bin == 2 ? up[1] : rr;   // (S, N)
+            q = bin == 1 ? up[0] : q; rr = bin == 1 ? dn[2] : rr;   // (NW, SE)
+            q = bin == 0 ? md[2] : q; rr = bin == 0 ? md[0] : rr;   // (E, W)
+            const float keep = (interior && v >= q && v >= rr) ? v : 0.f;
+            const bool strong = interior && keep > thF;
+            const bool weak = keep < tlF && !strong;
+            const bool ok = j < jEnd && colIn;
+            anyStrong = anyStrong || (strong && !need && ok);
+            gmask |= (need && ok) ? (1u << u) : 0u;
+            if (ok) {
+                if (NRM) st8(nrmB, oi, (unsigned)lvl);
+                if (nmsOut) st32(nmsB, oi, keep);
+                if (HYST) {
+                    st8(clB, oi, (interior && !weak) ? 0u : 255u);
+                    st8(eB, oi, strong ? 0u : 255u);
+                }
+            }
+            oi += (unsigned)W;
+        };
+        unsigned gm = 0u;
+#pragma unroll
+        for (int u = 0; u < 4; u++) row_pass(u);   // tile rows 0 .. 3: no output row is complete yet
+        row_pass(4);
+        out_row(4, 0, gm);
+        flagged = (unsigned long long)(gm >> 4);
+#pragma unroll 1
+        for (int g = 1; g < XROWS / 5; g++) {
+            gm = 0u;
+#pragma unroll
+            for (int u = 0; u < 5; u++) {
+                row_pass(u);
+                out_row(u, g * 5 + u - 4, gm);
+            }
+            flagged |= (unsigned long long)gm << (g * 5 - 4);
+        }
+        // ---- the flagged pixels, exactly
+        while (flagged) {
+            const int j = __ffsll((long long)flagged) - 1;
+            flagged &= flagged - 1ull;
+            const int y = y0 + j;
+            const bool interior = xInterior && y >= 1 && y < H - 1;
+            const bool st = dee_pixel_exact<NRM, HYST>(&tile[0][0], j, c, interior, thF, tlF, sDir, sZero, nrmB, nmsB, clB, eB,
+                                                       (unsigned)x + (unsigned)j * (unsigned)W);
+            anyStrong = anyStrong || st;
+        }
+        if (HYST) {
+            if (threadIdx.x == 0 && (x0 == 0 || y0 == 0 || x0 + XW >= W || y0 + XH >= H))
+                atomicMax(&stats[im].borderMaxKey, dkey(0.0));
+            if (__syncthreads_or(anyStrong ? 1 : 0) && threadIdx.x == 0) atomicOr(&stats[im].anyStrong, 1u);
+        }
+    } else {
+    // ---- generic form (no NMS: normals only, or hysteresis of the raw map, whose border labels are the raw values)
 #pragma unroll 1
     for (int g = 0; g < XROWS / 5; g++) {
 #pragma unroll
@@ -533,6 +691,7 @@ __global__ void __launch_bounds__(kXThreads, MTE_DEE_MINB) dee_front_tma_kernel(
         }
     }
     if (HYST && __syncthreads_or(anyStrong ? 1 : 0) && threadIdx.x == 0) atomicOr(&stats[im].anyStrong, 1u);
+    }
 }
 
 // out = img * (labels / max(labels))  in the dtype the reference computes in (C = float or double).  One image per
