@@ -67,6 +67,26 @@ __device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned nCtas) {
     __syncthreads();
 }
 
+#ifdef MTE_FUSED_TRACE
+// timing build only (scripts/trace_fused.py): per-phase time stamps folded over all CTAs into eight u64 slots at byte
+// 1024 of the workspace header (min via max of the complement).  Breaks the zero-header invariant: never in a release.
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define MTE_TRACE(slot, isMin)                                                                                   \
+    do {                                                                                                         \
+        __syncthreads();                                                                                         \
+        if (threadIdx.x == 0) {                                                                                  \
+            const unsigned long long t_ = gtime();                                                               \
+            atomicMax(reinterpret_cast<unsigned long long *>(F.barrier) + 128 + (slot), (isMin) ? ~t_ : t_); \
+        }                                                                                                        \
+    } while (0)
+#else
+#define MTE_TRACE(slot, isMin) do {} while (0)
+#endif
+
 struct FusedP {
     LossP L;
     const float *expectG;   // device [1 + nScales] upstream gradient the caller expects, or nullptr = {1, 0, ...}
@@ -375,6 +395,8 @@ __global__ void __maxnreg__(MTE_FUSED_REGS) edge_loss_fused_kernel(const __grid_
     const int uBeg = (int)((long long)P.totalUnits * gw / nWarps);
     const int uEnd = (int)((long long)P.totalUnits * (gw + 1) / nWarps);
     pdl_launch_dependents();   // the rescale kernel behind us may take its place on the SMs now (it waits for our end)
+    MTE_TRACE(0, true);    // first CTA starts
+    MTE_TRACE(1, false);   // last CTA starts
 
     // ---- phase 1: Wp_b = sum of the edge labels, every warp over the rows it owns (the lines stay in L2 for phase 2)
 #ifndef MTE_FUSED_TIMING_NO_PHASE1   // timing experiments only (results are wrong without it)
@@ -425,7 +447,10 @@ __global__ void __maxnreg__(MTE_FUSED_REGS) edge_loss_fused_kernel(const __grid_
     while (u0 < uEnd && !have) have = next_segment(P, u0, uEnd, sg);
     float2 xa[2], xc[2];
     if (have) fused_prologue(P.s[sg.si], sg, lane, ring, xa, xc);
+    MTE_TRACE(2, true);    // first CTA done with phase 1
+    MTE_TRACE(3, false);   // last CTA done with phase 1
     grid_barrier(F.barrier, gridDim.x);
+    MTE_TRACE(4, false);   // last CTA out of the barrier
 #else
     __syncthreads();
     int u0 = uBeg;
@@ -473,6 +498,8 @@ __global__ void __maxnreg__(MTE_FUSED_REGS) edge_loss_fused_kernel(const __grid_
         while (u0 < uEnd && !have) have = next_segment(P, u0, uEnd, sg);
         if (have) fused_prologue(P.s[sg.si], sg, lane, ring, xa, xc);
     }
+    MTE_TRACE(5, true);    // first CTA done with phase 2
+    MTE_TRACE(6, false);   // last CTA done with phase 2
     // ---- the last CTA to leave folds alpha, the normalisers and the loss (same code as the two-kernel forward)
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -498,6 +525,7 @@ __global__ void __maxnreg__(MTE_FUSED_REGS) edge_loss_fused_kernel(const __grid_
             P.ticket[1] = 0u;
             *F.barrier = 0u;
         }
+        MTE_TRACE(7, false);   // the loss is written
     }
 }
 
