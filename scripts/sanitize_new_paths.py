@@ -47,10 +47,28 @@ total, _, _ = multiscale_edge_loss(xs, es, None, ns, weight=10.0)
 (total * 0.3).backward()
 for x, (xr, _) in zip(xs, refs):
     assert (x.grad.cpu() - xr.grad).abs().max() <= 1e-5 * xr.grad.abs().max()
-# DEE: table kernel + fast quantisation + NMS + hysteresis
-p = np.stack([prob_map(48, 96, 3), np.zeros((48, 96), np.float32)])
-nrm, out = dee_postprocess(torch.from_numpy(p).cuda())
-assert np.array_equal(nrm[0].cpu().numpy(), odee.normals_u8(p[0]))
-assert np.array_equal(out[0].cpu().numpy(), odee.hysteresis(odee.non_max_suppression(p[0])), equal_nan=True)
+# one-pass loss, odd height (a one-row tail segment) and a shape with many seams per strip: the seam rows are zeroed in
+# phase 1 and added by two segments each (red.global.add.v4.f32)
+for (B, H, W) in ((3, 37, 64), (2, 130, 128)):
+    dep = torch.round((torch.rand(B, 1, H, W, generator=gen) * 79 + 1) * 64) / 64
+    e = (torch.rand(B, 1, H, W, generator=gen) < 0.05).float() * torch.rand(B, 1, H, W, generator=gen).clamp(min=0.3)
+    n = ((360 * torch.randint(0, 256, (B, 1, H, W), generator=gen).float() / 255 - 180) * np.pi / 180).float()
+    xr = dep.clone().requires_grad_(True)
+    l, _ = edge_loss_torch(xr, e, None, True, True, 4, n, weight=10.0)
+    l.backward()
+    xg = dep.cuda().requires_grad_(True)
+    tot, _, _ = multiscale_edge_loss([xg], [e.cuda()], None, [n.cuda()], weight=10.0)
+    tot.backward()
+    assert (xg.grad.cpu() - xr.grad).abs().max() <= 1e-5 * xr.grad.abs().max(), (B, H, W)
+# DEE: table kernel + straight-line front kernel (flagged pixels redone by dee_pixel_exact: the flat plane, the tiny-range
+# plane and the NaN plane all take that path) + NMS + hysteresis + finish kernel
+rng = np.random.default_rng(5)
+p = np.stack([prob_map(48, 96, 3), np.zeros((48, 96), np.float32), (rng.random((48, 96)) * 1e-31).astype(np.float32),
+              np.where(rng.random((48, 96)) < 0.05, np.nan, rng.random((48, 96))).astype(np.float32)])
+with np.errstate(all="ignore"):
+    nrm, out = dee_postprocess(torch.from_numpy(p).cuda())
+    for k in range(4):
+        assert np.array_equal(nrm[k].cpu().numpy(), odee.normals_u8(p[k])), k
+        assert np.array_equal(out[k].cpu().numpy(), odee.hysteresis(odee.non_max_suppression(p[k])), equal_nan=True), k
 torch.cuda.synchronize()
 print("sanitize driver ok", c[[0, 11]].tolist(), float(total))
