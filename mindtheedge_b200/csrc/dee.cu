@@ -381,7 +381,7 @@ __device__ __noinline__ bool dee_pixel_exact(const float *tile, int j, int c, bo
 }
 
 #ifndef MTE_DEE_MINB
-#define MTE_DEE_MINB 5
+#define MTE_DEE_MINB 6
 #endif
 template <bool NRM, bool NMS, bool HYST>
 __global__ void __launch_bounds__(kXThreads, MTE_DEE_MINB) dee_front_tma_kernel(const __grid_constant__ CUtensorMap tmap,
@@ -882,13 +882,18 @@ static int run(const T *prob, int N, int H, int W, int do_nms, int do_hyst, doub
         if (rc) return rc;
         // the reference computes in float64 once NMS has run (its output array is float64), else in the input type
         const bool c64 = do_nms || sizeof(T) == 8;
-        const dim3 fg((unsigned)ceil_div(H * W, kFinPx), (unsigned)N);
-        if (out_dtype == MTE_F64) {
-            if (c64) dee_finish_kernel<T, double, double><<<fg, kFinThreads, 0, st>>>(val, E, N, H, W, stats, (double *)out);
-            else dee_finish_kernel<T, float, double><<<fg, kFinThreads, 0, st>>>(val, E, N, H, W, stats, (double *)out);
-        } else {
-            if (c64) dee_finish_kernel<T, double, float><<<fg, kFinThreads, 0, st>>>(val, E, N, H, W, stats, (float *)out);
-            else dee_finish_kernel<T, float, float><<<fg, kFinThreads, 0, st>>>(val, E, N, H, W, stats, (float *)out);
+        // one image per blockIdx.y: batches beyond the grid's y limit go in slices
+        for (int n0 = 0; n0 < N; n0 += 65535) {
+            const int nn = N - n0 < 65535 ? N - n0 : 65535;
+            const size_t po = (size_t)n0 * H * W;
+            const dim3 fg((unsigned)ceil_div(H * W, kFinPx), (unsigned)nn);
+            if (out_dtype == MTE_F64) {
+                if (c64) dee_finish_kernel<T, double, double><<<fg, kFinThreads, 0, st>>>(val + po, E + po, nn, H, W, stats + n0, (double *)out + po);
+                else dee_finish_kernel<T, float, double><<<fg, kFinThreads, 0, st>>>(val + po, E + po, nn, H, W, stats + n0, (double *)out + po);
+            } else {
+                if (c64) dee_finish_kernel<T, double, float><<<fg, kFinThreads, 0, st>>>(val + po, E + po, nn, H, W, stats + n0, (float *)out + po);
+                else dee_finish_kernel<T, float, float><<<fg, kFinThreads, 0, st>>>(val + po, E + po, nn, H, W, stats + n0, (float *)out + po);
+            }
         }
         MTE_RETURN_IF_CUDA_ERROR();
     } else if (nmsDst == val) {

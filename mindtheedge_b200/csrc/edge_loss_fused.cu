@@ -61,7 +61,11 @@ __device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned nCtas) {
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(ctr, 1u);
+#ifdef MTE_FUSED_NOSLEEP
+        while (ld_acquire_u32(ctr) < nCtas) {}
+#else
         while (ld_acquire_u32(ctr) < nCtas) __nanosleep(20);
+#endif
         __threadfence();
     }
     __syncthreads();

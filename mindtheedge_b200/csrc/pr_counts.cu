@@ -823,7 +823,10 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
             const int nChunks = cpr * h;
             // kScanU independent word pairs per thread in flight: the scan is one CTA streaming 0.5 MB, i.e. latency-
             // bound (4 in flight: 31 round trips for the KITTI crop, 80 us of every image's critical path)
-            constexpr int kScanU = 12;
+#ifndef MTE_SCAN_U
+#define MTE_SCAN_U 12
+#endif
+            constexpr int kScanU = MTE_SCAN_U;
             for (int base = 0; base < nChunks; base += kScanU * kSwThreads) {
                 unsigned lw[kScanU], gw[kScanU];
 #pragma unroll
