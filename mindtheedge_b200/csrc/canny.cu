@@ -437,23 +437,36 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
     unsigned *cbits = BIG ? qbits + nW : reinterpret_cast<unsigned *>(dyn + P.oParent);   // smem: borrowed until the flood is done
     WL *wlA = reinterpret_cast<WL *>(dyn + P.oWork), *wlB = wlA + kWorkCap;
     const int HPR = WPR * 2;  // 16-pixel chunks per bitmap row
-    for (int hc = threadIdx.x; hc < H * HPR; hc += kUfThreads) {
-        const int y = hc / HPR, x0 = (hc - y * HPR) * 16;
-        const int i0 = hc * 16;  // bit index of the chunk
-        unsigned char v[16], sv[16];
-        if (x0 < W) { load16(v, cl, y * W + x0, HW, vec); load16(sv, E, y * W + x0, HW, vec); }
-        else {
+    //      (kP1U chunk pairs per thread in flight: one CTA streams the image's two level planes, i.e. the pass is a
+    //      chain of round trips -- 30 of them at KITTI size with one chunk per step)
+    constexpr int kP1U = 4;
+    for (int hc0 = threadIdx.x; hc0 < H * HPR; hc0 += kP1U * kUfThreads) {
+        unsigned char v[kP1U][16], sv[kP1U][16];
 #pragma unroll
-            for (int k = 0; k < 16; k++) { v[k] = (unsigned char)kNever; sv[k] = (unsigned char)kNever; }
-        }
-        unsigned half = 0, shalf = 0;
+        for (int u = 0; u < kP1U; u++) {
+            const int hc = hc0 + u * kUfThreads;
+            const int y = hc / HPR, x0 = (hc - y * HPR) * 16;
+            if (hc < H * HPR && x0 < W) { load16(v[u], cl, y * W + x0, HW, vec); load16(sv[u], E, y * W + x0, HW, vec); }
+            else {
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            half |= (v[k] != kNever ? 1u : 0u) << k;
-            shalf |= (sv[k] != kNever ? 1u : 0u) << k;
+                for (int k = 0; k < 16; k++) { v[u][k] = (unsigned char)kNever; sv[u][k] = (unsigned char)kNever; }
+            }
         }
-        const unsigned hi = __shfl_down_sync(__activemask(), half, 1), shi = __shfl_down_sync(__activemask(), shalf, 1);
-        if (!(lane & 1)) { cbits[i0 >> 5] = half | (hi << 16); qbits[i0 >> 5] = (shalf | (shi << 16)) & (half | (hi << 16)); }
+#pragma unroll
+        for (int u = 0; u < kP1U; u++) {
+            const int hc = hc0 + u * kUfThreads;
+            if (hc < H * HPR) {   // (H * HPR is even: the two lanes of a bitmap word are in range together)
+                const int i0 = hc * 16;  // bit index of the chunk
+                unsigned half = 0, shalf = 0;
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    half |= (v[u][k] != kNever ? 1u : 0u) << k;
+                    shalf |= (sv[u][k] != kNever ? 1u : 0u) << k;
+                }
+                const unsigned hi = __shfl_down_sync(__activemask(), half, 1), shi = __shfl_down_sync(__activemask(), shalf, 1);
+                if (!(lane & 1)) { cbits[i0 >> 5] = half | (hi << 16); qbits[i0 >> 5] = (shalf | (shi << 16)) & (half | (hi << 16)); }
+            }
+        }
     }
     if (threadIdx.x == 0) { sCntA = 0; sCntB = 0; sFull = 0; }
     __syncthreads();
@@ -538,10 +551,14 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
         unsigned bits = qbits[wi];
         if (!bits) continue;
         const int y = wi / WPR, pbase = y * W + (wi - y * WPR) * 32;  // pixel of bit 0
-        while (bits) {
-            const int b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            atomicAdd(&sHist[cl[pbase + b]], 1);
+        while (bits) {   // four level bytes in flight (one L2 round trip per bit otherwise)
+            int lvl[4], n = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (bits) { lvl[j] = cl[pbase + __ffs(bits) - 1]; bits &= bits - 1; n = j + 1; }
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (j < n) atomicAdd(&sHist[lvl[j]], 1);   // (warp-aggregating the adds with __match_any_sync was measured slower)
         }
     }
     __syncthreads();
@@ -606,14 +623,26 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
         if (!bits) continue;
         int r = (int)qrank[wi >> 1] + ((wi & 1) ? __popc(qbits[wi - 1]) : 0);
         const int y = wi / WPR, pbase = y * W + (wi - y * WPR) * 32;
-        while (bits) {
-            const int b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const int px = pbase + b;
-            const int at = atomicAdd(&sHist[cl[px]], 1);
-            list[at] = px;
-            perm[r++] = (unsigned short)at;
-            Ec[at] = E[px];
+        while (bits) {   // four pixels' two level bytes in flight
+            int px[4], lvl[4], n = 0;
+            unsigned char el[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (bits) {
+                    px[j] = pbase + __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    lvl[j] = cl[px[j]];
+                    el[j] = E[px[j]];
+                    n = j + 1;
+                }
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (j < n) {
+                    const int at = atomicAdd(&sHist[lvl[j]], 1);
+                    list[at] = px[j];
+                    perm[r++] = (unsigned short)at;
+                    Ec[at] = el[j];
+                }
         }
     }
     __syncthreads();
