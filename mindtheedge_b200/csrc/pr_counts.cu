@@ -913,9 +913,13 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
         }
         __syncthreads();
         // ---- predicted pixels grouped by stage (order inside a stage is arbitrary: counts do not depend on it)
-        for (int k = threadIdx.x; k < nPall; k += kSwThreads) {
-            const unsigned v = tmpList[k];
-            gpix[atomicAdd(&sCursor[v >> 24], 1)] = v & 0xFFFFFFu;
+        for (int k0 = threadIdx.x; k0 < nPall; k0 += 4 * kSwThreads) {   // four list entries per thread in flight
+            unsigned v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = k0 + u * kSwThreads < nPall ? __ldcg(tmpList + k0 + u * kSwThreads) : 0xFFFFFFFFu;
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (k0 + u * kSwThreads < nPall) gpix[atomicAdd(&sCursor[v[u] >> 24], 1)] = v[u] & 0xFFFFFFu;
         }
         __syncthreads();
         // Everything resident at once when it fits.  Otherwise ("compact" mode) the predicted arrays only ever hold the
@@ -923,7 +927,14 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
         // can never be matched later (Kuhn), are never reached as somebody's mate, and are dropped after every chunk.
         const bool compact = nPall > SL.capP;
         if (!compact)
-            for (int k = threadIdx.x; k < nPall; k += kSwThreads) { ppix[k] = pack_yx(__ldcg(gpix + k)); mateP[k] = kFree; }
+            for (int k0 = threadIdx.x; k0 < nPall; k0 += 4 * kSwThreads) {
+                unsigned v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = k0 + u * kSwThreads < nPall ? __ldcg(gpix + k0 + u * kSwThreads) : 0u;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (k0 + u * kSwThreads < nPall) { ppix[k0 + u * kSwThreads] = pack_yx(v[u]); mateP[k0 + u * kSwThreads] = kFree; }
+            }
         // ---- rank: exclusive prefix popcount over pairs of bitmap words
         {
             const int nW2 = (SL.nW + 1) >> 1;
