@@ -380,7 +380,7 @@ template <bool BIG>
 __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const UfP P) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ int sHist[256], sEnd[256], sScan[kUfThreads];
-    __shared__ int sCntA, sCntB, sFull;
+    __shared__ int sCnt[3], sFullA[3];   // flood worklists: three rotating counters (read / append / clear), one barrier per round
     __shared__ unsigned char sRep[256];
     using WL = typename std::conditional<BIG, unsigned, unsigned short>::type;  // worklist entry: a bitmap word index
     const int img = blockIdx.x;
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
             }
         }
     }
-    if (threadIdx.x == 0) { sCntA = 0; sCntB = 0; sFull = 0; }
+    if (threadIdx.x < 3) { sCnt[threadIdx.x] = 0; sFullA[threadIdx.x] = 0; }
     __syncthreads();
     // ---- flood: only candidates connected to a strong pixel can ever become edges (the edge sets of the pairs are
     //      nested), and on noisy depth they are a fraction of the candidates (~6 k of ~30 k per KITTI image), so the
@@ -485,19 +485,23 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
         return f;
     };
     for (int i = threadIdx.x; i < nW; i += kUfThreads)
-        if (qbits[i]) { const int s = atomicAdd(&sCntA, 1); if (s < kWorkCap) wlA[s] = (WL)i; else sFull = 1; }
+        if (qbits[i]) { const int s = atomicAdd(&sCnt[0], 1); if (s < kWorkCap) wlA[s] = (WL)i; else sFullA[0] = 1; }
     __syncthreads();
     for (int iter = 0;; iter++) {
-        const int nA = min(sCntA, kWorkCap);
-        const bool full = sFull != 0;
+        // Round `iter` reads list / counter cur, appends to nxt and clears clr, the counter that round iter - 1 read (every
+        // thread passed the barrier that ended that round) and that round iter + 1 appends to (after this round's
+        // barrier): ONE barrier per round instead of four -- a flood over long contours is a few dozen rounds of a
+        // thousand threads.  The two lists alternate: the one appended to now was read in the previous round.
+        const int cur = iter % 3, nxt = (iter + 1) % 3, clr = (iter + 2) % 3;
+        const int nA = min(sCnt[cur], kWorkCap);
+        const bool full = sFullA[cur] != 0;
         if (nA == 0 && !full) break;
-        __syncthreads();
-        if (threadIdx.x == 0) { sCntA = 0; sFull = 0; }
-        __syncthreads();
-        // (sCntB counts the next worklist; the lists swap roles every iteration)
+        if (threadIdx.x == 0) { sCnt[clr] = 0; sFullA[clr] = 0; }
+        const WL *src = (iter & 1) ? wlB : wlA;
+        WL *dst = (iter & 1) ? wlA : wlB;
         const int nSrc = full ? nW : nA;
         for (int k = threadIdx.x; k < nSrc; k += kUfThreads) {
-            const int wi = full ? k : (int)wlA[k];
+            const int wi = full ? k : (int)src[k];
             const unsigned v = ((volatile unsigned *)qbits)[wi];
             if (!v) continue;
             const int r = wi / WPR, c = wi - r * WPR;
@@ -518,15 +522,12 @@ __global__ void __launch_bounds__(kUfThreads) canny_uf_hyst_smem_kernel(const Uf
                     const unsigned add = hfill(contrib | cur, cm) & ~cur;
                     const unsigned old = atomicOr(&qbits[ti], add);
                     if (add & ~old) {
-                        const int s2 = atomicAdd(&sCntB, 1);
-                        if (s2 < kWorkCap) wlB[s2] = (WL)ti; else sFull = 1;
+                        const int s2 = atomicAdd(&sCnt[nxt], 1);
+                        if (s2 < kWorkCap) dst[s2] = (WL)ti; else sFullA[nxt] = 1;
                     }
                 }
             }
         }
-        __syncthreads();
-        if (threadIdx.x == 0) { sCntA = sCntB; sCntB = 0; }
-        WL *tmp = wlA; wlA = wlB; wlB = tmp;
         __syncthreads();
     }
     tick(0);
