@@ -694,6 +694,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                                                                     int tablesInParam, const SweepLayout SL) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ int sImage, sNP, sNQ, sCntA, sEnds, sMatched, sHead, sTail, sPending;
+    __shared__ int sGr[3];   // greedy rounds: rotating append counters (one barrier per round)
     __shared__ int sScan[kSwThreads];
     __shared__ int sStage[MTE_MAX_THRESHOLDS + 2];   // histogram, then start offset of every stage
     __shared__ int sCursor[MTE_MAX_THRESHOLDS + 2];
@@ -984,28 +985,57 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                 cur = G1;
             }
             if (p1 > p0) {
-                // ---- greedy start: nearest free GT pixel, one THREAD per new predicted pixel walking the offsets nearest
-                //      first (most pixels succeed within the first few; any greedy start is a valid matching)
-                for (int pi = p0 + threadIdx.x; pi < p1; pi += kSwThreads) {
-                    const unsigned p = ppix[pi];
-                    const int py = (int)(p >> 16), px = (int)(p & 0xFFFFu);
-                    bool done = false, anyQ = false;
-                    for (int k = 0; k < noff && !done; k++) {
-                        const short2 o = sOff[k];
-                        const int qy = py + o.y, qx = px + o.x;
-                        if (qy < 0 || qy >= h || qx < 0 || qx >= w) continue;
-                        const int q = qy * w + qx;
-                        int qi;
-                        if (!qprobe(q, qi)) continue;
-                        anyQ = true;
-                        if (((volatile unsigned short *)mateQ)[qi] != kFree) continue;
-                        if (cas16(&mateQ[qi], kFree, (unsigned short)pi) == kFree) {
-                            mateP[pi] = (unsigned short)qi;
-                            done = true;
+                // ---- greedy start: nearest free GT pixel, one THREAD per new predicted pixel, the offsets nearest first
+                //      (any greedy start is a valid matching).  The walk is cut into ROUNDS of a few offsets: the pixels
+                //      that are still unmatched after a round are compacted into a list for the next one, so that the
+                //      few pixels that have to try all offsets do not hold their whole warps for 21 serial probes
+                //      (one thread walking everything: 8 rounds x 21 probes per warp, 80 us on the heaviest image).
+                //      Lists live in the frontier / root arrays, which are idle until the phases; "saw a GT pixel" is
+                //      remembered in the pixel's own mate entry (kSeenQ) until the walk ends.
+                {
+                    constexpr unsigned short kSeenQ = 0xFFFC;
+                    unsigned short *lst[2] = {fa, rootP};
+                    if (threadIdx.x < 3) sGr[threadIdx.x] = 0;
+                    __syncthreads();
+                    int n = p1 - p0, kLo = 0, round = 0;
+                    for (; n > 0 && kLo < noff; round++) {
+                        const int kHi = min(noff, kLo < 1 ? 1 : (kLo < 5 ? 5 : (kLo < 9 ? 9 : (kLo < 21 ? 21 : kLo + 32))));
+                        const int nxt = (round + 1) % 3;
+                        const unsigned short *src = lst[round & 1];
+                        unsigned short *dst = lst[(round + 1) & 1];
+                        if (threadIdx.x == 0) sGr[(round + 2) % 3] = 0;   // next round's append counter (read two rounds ago)
+                        for (int i = threadIdx.x; i < n; i += kSwThreads) {
+                            const int pi = round == 0 ? p0 + i : (int)src[i];
+                            const unsigned p = ppix[pi];
+                            const int py = (int)(p >> 16), px = (int)(p & 0xFFFFu);
+                            bool done = false;
+                            for (int k = kLo; k < kHi && !done; k++) {
+                                const short2 o = sOff[k];
+                                const int qy = py + o.y, qx = px + o.x;
+                                if (qy < 0 || qy >= h || qx < 0 || qx >= w) continue;
+                                const int q = qy * w + qx;
+                                int qi;
+                                if (!qprobe(q, qi)) continue;
+                                if (mateP[pi] == kFree) mateP[pi] = kSeenQ;
+                                if (((volatile unsigned short *)mateQ)[qi] != kFree) continue;
+                                if (cas16(&mateQ[qi], kFree, (unsigned short)pi) == kFree) {
+                                    mateP[pi] = (unsigned short)qi;
+                                    done = true;
+                                }
+                            }
+                            if (done) atomicAdd(&sMatched, 1);
+                            else dst[atomicAdd(&sGr[nxt], 1)] = (unsigned short)pi;
                         }
+                        __syncthreads();
+                        n = sGr[nxt];
+                        kLo = kHi;
                     }
-                    if (done) atomicAdd(&sMatched, 1);
-                    else if (!anyQ) mateP[pi] = kDead;
+                    // what is left went through every offset: free again if it saw a GT pixel, dead (never matchable) if not
+                    const unsigned short *rest = lst[round & 1];
+                    for (int i = threadIdx.x; i < n; i += kSwThreads) {
+                        const int pi = round == 0 ? p0 + i : (int)rest[i];
+                        mateP[pi] = mateP[pi] == kSeenQ ? kFree : kDead;
+                    }
                 }
                 __syncthreads();
                 tick(5);
