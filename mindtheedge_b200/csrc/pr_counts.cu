@@ -1093,6 +1093,9 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                         }
                         my = __shfl_sync(MTE_FULL_MASK, my, 0);
                         if (my == -2) break;
+#ifdef MTE_DEBUG_KNOBS   // profiling: queue items (roots + published successors)
+                        if (P.stats && lane == 0) atomicAdd(P.stats + 22, 1u);
+#endif
                         int pi = my;
                         const int root = rootP[pi];  // a successor inherits the tree of its predecessor
                         const unsigned mine = ((unsigned)phase << 16) | (unsigned)root;
@@ -1186,6 +1189,13 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                         }
                     }
                     __syncthreads();
+#ifdef MTE_DEBUG_KNOBS   // profiling: explore cycles (>> 8) and phase counts by the number of roots of the phase
+                    if (P.stats && threadIdx.x == 0) {
+                        const int b = nRoots == 1 ? 0 : (nRoots < 4 ? 1 : (nRoots < 16 ? 2 : 3));
+                        atomicAdd(P.stats + 23 + b, (unsigned)((clock64() - tk) >> 8));
+                        atomicAdd(P.stats + 27 + b, 1u);
+                    }
+#endif
                     tick(7);
                     const int nEnds = min(sEnds, kEndsCap);
                     // a find anywhere in a class keeps the whole class alive (fa[0..nRoots) still holds the roots: the
