@@ -7,12 +7,16 @@
 // and the third-party cv2.Sobel(img, CV_64F, dx, dy, ksize=5) they call: separable
 // [1,4,6,4,1] x [-1,-2,0,2,1], BORDER_REFLECT_101, row pass first, fp64 accumulation in tap order, the
 // column pass folded symmetrically / anti-symmetrically.  Every fp64 operation below is an explicit
-// __dmul_rn / __dadd_rn in exactly that order (no FMA contraction), so the Sobel responses are
-// bit-identical to OpenCV's and the orientation bins / uint8 normals follow.
+// __dmul_rn / __dadd_rn / __fma_rn in exactly that order (no compiler contraction; a fused multiply-add appears only
+// where the product is exact -- a tap times an fp32 value, a power of two times a double -- so that it rounds exactly
+// like the separate multiply and add), so the Sobel responses are bit-identical to OpenCV's and the orientation bins /
+// uint8 normals follow.
 //
-// Kernels:  dee_front_kernel  (Sobel5 + normals + NMS + hysteresis labels, shared-memory halo tile)
-//           canny::run_level_hysteresis (shared 8-connected union-find hysteresis)
-//           dee_finish_kernel (img * labels / max(labels), the reference's normalisation quirk included)
+// Kernels:  dee_front_tma_kernel (fp32 planes: TMA halo tile, Sobel5 + normals + NMS + hysteresis labels out of a register
+//                                 window, candidate-only fast paths, flagged pixels redone by dee_pixel_exact)
+//           dee_front_kernel     (fp64 planes and odd shapes: shared-memory halo tile, same decisions)
+//           canny::run_level_hysteresis (shared 8-connected flood / union-find hysteresis)
+//           dee_finish_kernel    (img * labels / max(labels), the reference's normalisation quirk included)
 #include <cuda.h>
 #include <math.h>
 #include <string.h>
@@ -465,7 +469,7 @@ __global__ void __launch_bounds__(kXThreads, MTE_DEE_MINB) dee_front_tma_kernel(
     if constexpr (NMS) {
         // ---- straight-line form (every variant that runs the NMS): no branch in the body of a row except the final
         // stores, so the scheduler interleaves the five unrolled rows (the kernel is bound by dependent-issue latency:
-        // ncu `wait` 2.3 per issue with 20 warps per SM).  Pixels whose candidate cannot decide are only FLAGGED here
+        // ncu `wait` 2.3 per issue at 20-24 warps per SM).  Pixels whose candidate cannot decide are only FLAGGED here
         // and redone by dee_pixel_exact after the loop; zero gradients (flat regions, common) are decided in line.
         // Border pixels: the NMS leaves 0 there (tools.py:19-20), so their raw "label" is 0 for every tile that
         // touches the border: one atomicMax per CTA instead of one per pixel.
@@ -474,7 +478,7 @@ __global__ void __launch_bounds__(kXThreads, MTE_DEE_MINB) dee_front_tma_kernel(
             tr += XCOLS;
             f[u][0] = t1; f[u][1] = t2; f[u][2] = t3;
             const double a0 = (double)t0, a1 = (double)t1, a2 = (double)t2, a3 = (double)t3, a4 = (double)t4;
-            double d = __fma_rn(-2.0, a1, -a0);   // exact products: see the generic loop below
+            double d = __fma_rn(-2.0, a1, -a0);   // exact products: see the generic loop at the end of the kernel
             d = __fma_rn(0.0, a2, d);
             d = __fma_rn(2.0, a3, d);
             wD[u] = __dadd_rn(d, a4);
@@ -510,7 +514,7 @@ __global__ void __launch_bounds__(kXThreads, MTE_DEE_MINB) dee_front_tma_kernel(
                 const float zl = nx ? (ny ? zl3 : zl2) : (ny ? zl1 : zl0);
                 lvl = zero ? (int)zl : k0;
             }
-            const float uu = fmaf(-a32, 1.27323954f, 4.5f);   // bin boundaries at the integers, period 4 (see below)
+            const float uu = fmaf(-a32, 1.27323954f, 4.5f);   // bin boundaries at the integers, period 4 (see the generic loop)
             const int iu = (int)uu;
             const float fu = uu - (float)iu;
             decided = decided && fu >= 5e-5f && fu <= 1.f - 5e-5f;
