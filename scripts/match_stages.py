@@ -24,7 +24,7 @@ for i in (only or range(102)):
     e0.record(); c = pr_counts(lv[i:i+1], g[i:i+1], n_levels=12, max_dist=0.002, crop=[44, 1197, 153, 371]); e1.record(); torch.cuda.synchronize()
     hdr = runtime.workspace(d.device, 1 << 20)[:256].view(torch.int32).cpu().numpy()
     st = hdr[32:64]
-    rows.append((e0.elapsed_time(e1), i, st[0:9].tolist(), st[9:21].tolist(), int(st[21]), c.cpu().numpy()[[0, 11], 3].tolist(), st[22:31].tolist()))
+    rows.append((e0.elapsed_time(e1), i, st[0:9].tolist(), st[9:21].tolist(), int(st[21]), c.cpu().numpy()[[0, 11], 3].tolist(), st[22:32].tolist()))
 rows.sort(reverse=True)
 print("seed", seed, "mean ms %.3f" % np.mean([r[0] for r in rows]), "max %.3f" % rows[0][0])
 for r in rows[:8]:
@@ -32,6 +32,6 @@ for r in rows[:8]:
     print("ms %.3f img %d | phases,levels,expanded,roots|scan,greedy,setup,explore,augment %s | stage kcyc>>8 %s share0 %.2f | stage0 px %d, pred px [t0,t11] %s"
           % (r[0], r[1], r[2], r[3], r[3][0] / tot, r[4], r[5]))
     x = r[6]
-    print("      queue items %d | explore kcyc>>8 by roots of the phase (1 / 2-3 / 4-15 / 16+): %s in %s phases" % (x[0], x[1:5], x[5:9]))
+    print("      queue items %d | explore kcyc>>8 by roots of the phase (1 / 2-3 / 4-15 / 16+): %s in %s phases; longest walks of the 16+ phases summed: %d hops" % (x[0], x[1:5], x[5:9], x[9]))
 allst = np.array([r[3] for r in rows], dtype=np.float64)
 print("mean share of stage 0 over images: %.3f; over the 10 slowest: %.3f" % ((allst[:, 0] / allst.sum(1).clip(1)).mean(), (allst[:10, 0] / allst[:10].sum(1)).mean()))
