@@ -56,6 +56,7 @@ struct MatchP {
     int *overflowList;
     int truncate;              // stop each BFS at the first level that reaches a free GT pixel
     unsigned int *stats;       // optional profiling counters {phases, levels, expanded vertices, free roots}
+    unsigned int *trace;       // debug builds: per-item cycle stamps of the many-root phases of stage 0 (scripts/match_trace.py)
     unsigned int *nextProblem; // dynamic scheduler (self-resetting)
     unsigned int *doneCtas;
 };
@@ -725,6 +726,10 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
         for (int i = threadIdx.x; i < T; i += kSwThreads) sThr[i] = tablesInParam ? tabs.thr[i] : P.thr[i];
     __syncthreads();
     const int noff = P.noff;
+#ifdef MTE_DEBUG_KNOBS
+    const long long tZero = clock64();
+    if (P.trace && blockIdx.x == 0 && threadIdx.x == 0) { P.trace[0] = 0x7ACE7ACEu; P.trace[1] = 0u; }
+#endif
     long long tk = 0;
     auto tick = [&](int slot) {  // profiling: cycles (>> 8) per section, accumulated by thread 0
         if (P.stats && threadIdx.x == 0) {
@@ -1082,6 +1087,9 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                     tick(6);
                     for (;;) {
                         int my = -1;
+#ifdef MTE_DEBUG_KNOBS
+                        const long long tWait = (P.trace && lane == 0) ? clock64() : 0;
+#endif
                         if (lane == 0) {
                             for (;;) {
                                 const int hd = *(volatile int *)&sHead, tl = *(volatile int *)&sTail;
@@ -1103,6 +1111,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
 #ifdef MTE_DEBUG_KNOBS   // profiling: queue items (roots + published successors)
                         if (P.stats && lane == 0) atomicAdd(P.stats + 22, 1u);
                         int nHops = 0;
+                        const long long tBeg = (P.trace && lane == 0) ? clock64() : 0;
 #endif
                         int pi = my;
                         const int root = rootP[pi];  // a successor inherits the tree of its predecessor
@@ -1204,6 +1213,16 @@ __global__ void __launch_bounds__(kSwThreads, 1) match_sweep_kernel(const __grid
                             atomicSub(&sPending, 1);
 #ifdef MTE_DEBUG_KNOBS
                             if (P.stats) atomicMax(&sMaxChain, nHops);
+                            if (P.trace && s == 0 && nRoots >= 16) {
+                                const unsigned at = atomicAdd(P.trace + 1, 1u);
+                                if (at < 8000u) {
+                                    unsigned *e = P.trace + 4 + 4 * at;
+                                    e[0] = (unsigned)warp | ((unsigned)(phase & 0xFF) << 8) | ((unsigned)min(nHops, 0xFFFF) << 16);
+                                    e[1] = (unsigned)((tWait - tZero) >> 2);
+                                    e[2] = (unsigned)((tBeg - tZero) >> 2);
+                                    e[3] = (unsigned)((clock64() - tZero) >> 2);
+                                }
+                            }
 #endif
                         }
                     }
@@ -1466,6 +1485,9 @@ static int launch(MatchP &P, const Layout &L, char *ws, double max_dist, const d
     WsHeader *hdr = reinterpret_cast<WsHeader *>(ws);
     P.truncate = debug_knob("MTE_MATCH_TRUNCATE") ? 1 : 0;
     P.stats = debug_knob("MTE_MATCH_STATS") ? hdr->pad : nullptr;
+    P.trace = nullptr;
+    if (debug_knob("MTE_MATCH_TRACE") && L.nArenas >= 2)   // the last arena is idle when a single image is matched
+        P.trace = reinterpret_cast<unsigned int *>(ws + L.offArena + L.arenaBytes * (size_t)(L.nArenas - 1));
     P.nextProblem = hdr->ticket + 4;
     P.doneCtas = hdr->ticket + 5;
     P.overflowCount = hdr->ticket + 6;
