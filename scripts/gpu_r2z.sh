@@ -1,4 +1,7 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
-timeout -s KILL 120 python -m pytest tests -m gpu -q 2>&1 | tail -1
-timeout -s KILL 60 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+for v in _sw768 _sw640 ""; do
+MTE_LIB=$PWD/mindtheedge_b200/libmte$v.so timeout -s KILL 40 python bench.py --workload auc --steps 20 --warmup 3 --no-secondary 2>/dev/null | python -c "
+import json,sys
+d=json.loads([l for l in sys.stdin if l.startswith('{')][0]); print('auc$v', d['ms_per_step'], d['counts'][0], d['counts'][11])"
+done
